@@ -1,0 +1,269 @@
+// C-ABI entry points of include/fem2d.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/fem2d.h"
+#include "device_plan.hpp"
+
+struct fem2d_plan { fem2d::Plan p; };
+
+namespace {
+thread_local std::string g_err;
+int fail(int status, const std::string& msg) { g_err = msg; return status; }
+#define CKS(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? FEM2D_ERR_OUT_OF_MEMORY : FEM2D_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+int device_available(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(FEM2D_ERR_NO_DEVICE, "no CUDA device available: the fem2d numeric path has no CPU fallback"); }
+    if (device < 0 || device >= n) return fail(FEM2D_ERR_BAD_ARGUMENT, "device index out of range");
+    return FEM2D_OK;
+}
+
+int check_numeric_args(const fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w,
+                       uint32_t nu, const double* v_pts, const double* v_w, uint32_t nv) {
+    if (!plan) return fail(FEM2D_ERR_BAD_ARGUMENT, "null plan");
+    // MIN_GLQ_ORDER check (galerkin.rs:51-57) comes first among the numeric arguments
+    if (nu < 4 || nv < 4) return fail(FEM2D_ERR_INVALID_GLQ, "Invalid GLQ Settings (the number of GLQ points must be at least 4)");
+    if (nu > fem2d::MAX_GLQ || nv > fem2d::MAX_GLQ) return fail(FEM2D_ERR_UNSUPPORTED, "more than 128 GLQ points per axis");
+    if (!u_pts || !u_w || !v_pts || !v_w) return fail(FEM2D_ERR_BAD_ARGUMENT, "null GLQ array");
+    if (basis_kind != FEM2D_BASIS_HIER_POLY && basis_kind != FEM2D_BASIS_HIER_MAX_ORTHO) return fail(FEM2D_ERR_UNSUPPORTED, "unknown basis space");
+    if (basis_kind == FEM2D_BASIS_HIER_MAX_ORTHO && (plan->p.host.i_max > 12 || plan->p.host.j_max > 12))
+        return fail(FEM2D_ERR_UNSUPPORTED, "HierMaxOrtho is tabulated up to order 12 (hierarchical_basis_fns.rs:240-252)");
+    if ((a_kind != FEM2D_INTEGRAL_CURL_CURL && a_kind != FEM2D_INTEGRAL_L2_INNER) || (b_kind != FEM2D_INTEGRAL_CURL_CURL && b_kind != FEM2D_INTEGRAL_L2_INNER))
+        return fail(FEM2D_ERR_UNSUPPORTED, "unknown integral kind");
+    if (mode != FEM2D_MODE_EXACT && mode != FEM2D_MODE_SUMFACT && mode != FEM2D_MODE_DMMA) return fail(FEM2D_ERR_UNSUPPORTED, "unknown mode");
+    if (plan->p.device < 0) return fail(FEM2D_ERR_NO_DEVICE, "host-only plan: the fem2d numeric path has no CPU fallback");
+    return FEM2D_OK;
+}
+}  // namespace
+
+extern "C" {
+
+const char* fem2d_version(void) { return "fem2d-b200 0.1.0 (sm_100a)"; }
+const char* fem2d_last_error(void) { return g_err.c_str(); }
+const char* fem2d_status_string(int s) {
+    switch (s) {
+        case FEM2D_OK: return "ok";
+        case FEM2D_ERR_WRONG_CONTINUITY: return "Wrong Continuity Condition on Domain; Cannot execute Galerkin Sampling!";
+        case FEM2D_ERR_EMPTY_DOF_SET: return "No Degrees-of-Freedom Defined over Domain; Cannot execute Galerkin Sampling!";
+        case FEM2D_ERR_INVALID_GLQ: return "Invalid GLQ Settings (the number of GLQ points must be at least 4); Cannot execute Galerkin Sampling!";
+        case FEM2D_ERR_BAD_ARGUMENT: return "bad argument";
+        case FEM2D_ERR_NO_DEVICE: return "no CUDA device (no CPU fallback)";
+        case FEM2D_ERR_CUDA: return "CUDA error";
+        case FEM2D_ERR_UNSUPPORTED: return "unsupported";
+        case FEM2D_ERR_INTERNAL: return "internal error";
+        case FEM2D_ERR_OUT_OF_MEMORY: return "out of memory";
+    }
+    return "unknown status";
+}
+
+int fem2d_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int fem2d_symbolic(const fem2d_domain_view* view, int device, int dedupe, fem2d_plan** out) {
+    if (!out) return fail(FEM2D_ERR_BAD_ARGUMENT, "null out");
+    *out = nullptr;
+    try {
+        fem2d_plan* plan = new fem2d_plan();
+        std::string err;
+        int st = fem2d::build_host_plan(view, dedupe != 0, plan->p.host, err);
+        if (st != FEM2D_OK) { delete plan; return fail(st, err); }
+        if (plan->p.host.n_pairs >= (1ull << 31)) { delete plan; return fail(FEM2D_ERR_UNSUPPORTED, "more than 2^31 pairs"); }
+        plan->p.device = device;
+        if (device < 0) {
+            fem2d::build_host_pattern(plan->p.host, plan->p.host_pattern);
+            plan->p.nnz = plan->p.host_pattern.rows.size();
+            plan->p.n_extra = plan->p.host_pattern.extra_slot.size();
+            plan->p.max_contrib = plan->p.host_pattern.max_contrib;
+            uint64_t multi = 0;
+            for (size_t k = 0; k < plan->p.host_pattern.extra_slot.size(); k++)
+                if (k == 0 || plan->p.host_pattern.extra_slot[k] != plan->p.host_pattern.extra_slot[k - 1]) multi++;
+            plan->p.n_multi = multi;
+        } else {
+            st = device_available(device);
+            if (st != FEM2D_OK) { delete plan; return st; }
+            st = fem2d::device_symbolic(plan->p, err);
+            if (st != FEM2D_OK) { fem2d::device_plan_release(plan->p); delete plan; return fail(st, err); }
+        }
+        *out = plan;
+        return FEM2D_OK;
+    } catch (std::bad_alloc&) { return fail(FEM2D_ERR_OUT_OF_MEMORY, "host allocation failed");
+    } catch (std::exception& e) { return fail(FEM2D_ERR_INTERNAL, e.what()); }
+}
+
+void fem2d_plan_free(fem2d_plan* plan) {
+    if (!plan) return;
+    fem2d::device_plan_release(plan->p);
+    delete plan;
+}
+
+int fem2d_plan_info(const fem2d_plan* plan, uint64_t info[16]) {
+    if (!plan || !info) return fail(FEM2D_ERR_BAD_ARGUMENT, "null argument");
+    std::memset(info, 0, 16 * sizeof(uint64_t));
+    const fem2d::Plan& p = plan->p;
+    info[0] = p.nnz; info[1] = p.host.n_pairs; info[2] = p.host.blocks.size(); info[3] = p.host.classes.size();
+    info[4] = p.host.n_values; info[5] = p.n_multi; info[6] = p.max_contrib; info[7] = p.host.tables.size();
+    info[8] = p.host.items.size(); info[9] = p.host.n_dofs; info[10] = p.host.lists.size(); info[11] = p.n_extra;
+    return FEM2D_OK;
+}
+
+int fem2d_plan_pattern(const fem2d_plan* plan, uint32_t* rows, uint32_t* cols) {
+    if (!plan) return fail(FEM2D_ERR_BAD_ARGUMENT, "null plan");
+    const fem2d::Plan& p = plan->p;
+    if (p.device < 0) {
+        if (rows) std::copy(p.host_pattern.rows.begin(), p.host_pattern.rows.end(), rows);
+        if (cols) std::copy(p.host_pattern.cols.begin(), p.host_pattern.cols.end(), cols);
+        return FEM2D_OK;
+    }
+    CKS(cudaSetDevice(p.device));
+    if (rows) CKS(cudaMemcpy(rows, p.d_rows, p.nnz * 4, cudaMemcpyDeviceToHost));
+    if (cols) CKS(cudaMemcpy(cols, p.d_cols, p.nnz * 4, cudaMemcpyDeviceToHost));
+    return FEM2D_OK;
+}
+
+int fem2d_plan_pattern_device(const fem2d_plan* plan, const uint32_t** d_rows, const uint32_t** d_cols) {
+    if (!plan) return fail(FEM2D_ERR_BAD_ARGUMENT, "null plan");
+    if (plan->p.device < 0) return fail(FEM2D_ERR_NO_DEVICE, "host-only plan");
+    if (d_rows) *d_rows = plan->p.d_rows;
+    if (d_cols) *d_cols = plan->p.d_cols;
+    return FEM2D_OK;
+}
+
+int fem2d_plan_row_blocks(const fem2d_plan* plan, uint32_t world, uint64_t* bounds) {
+    if (!plan || !bounds || world == 0) return fail(FEM2D_ERR_BAD_ARGUMENT, "bad argument");
+    const fem2d::Plan& p = plan->p;
+    if (p.device < 0) {
+        const auto& rows = p.host_pattern.rows;
+        bounds[0] = 0; bounds[world] = p.nnz;
+        for (uint32_t r = 1; r < world; r++) {
+            uint64_t s = p.nnz * r / world;
+            while (s < p.nnz && s > 0 && rows[s] == rows[s - 1]) s++;
+            bounds[r] = s;
+        }
+        return FEM2D_OK;
+    }
+    std::string err;
+    int st = fem2d::device_row_block_bounds(p, world, bounds, err);
+    return st == FEM2D_OK ? st : fail(st, err);
+}
+
+int fem2d_assemble_device(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w, uint32_t nu,
+                          const double* v_pts, const double* v_w, uint32_t nv, uint64_t slot_begin, uint64_t slot_end, double* d_a, double* d_b,
+                          void* stream) {
+    int st = check_numeric_args(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv);
+    if (st != FEM2D_OK) return st;
+    if (!d_a || !d_b) return fail(FEM2D_ERR_BAD_ARGUMENT, "null output pointer");
+    fem2d::Plan& p = plan->p;
+    cudaStream_t s = (cudaStream_t)stream;
+    CKS(cudaSetDevice(p.device));
+    // GLQ nodes/weights (inputs of the path, basis.rs:83-90): u_pts | u_w | v_pts | v_w, 128 doubles each
+    double h_glq[512];
+    std::memset(h_glq, 0, sizeof(h_glq));
+    std::copy(u_pts, u_pts + nu, h_glq); std::copy(u_w, u_w + nu, h_glq + 128);
+    std::copy(v_pts, v_pts + nv, h_glq + 256); std::copy(v_w, v_w + nv, h_glq + 384);
+    CKS(cudaMemcpyAsync(p.d_glq, h_glq, sizeof(h_glq), cudaMemcpyHostToDevice, s));
+    const uint32_t NO = std::max(p.host.i_max, p.host.j_max) + 1, NPT = std::max(nu, nv);
+    const size_t tabs_need = p.host.tables.size() * 4 * (size_t)NO * NPT;
+    if (tabs_need > p.tabs_capacity) {
+        CKS(cudaStreamSynchronize(s));
+        cudaFree(p.d_tabs); p.d_tabs = nullptr; p.tabs_capacity = 0;
+        CKS(cudaMalloc((void**)&p.d_tabs, tabs_need * sizeof(double)));
+        p.tabs_capacity = tabs_need;
+    }
+    if (!p.d_V) CKS(cudaMalloc((void**)&p.d_V, std::max<uint64_t>(p.host.n_values, 1) * sizeof(double2)));
+    for (int k = 0; k < 4; k++) p.last_launches[k] = 0;
+    CKS(cudaEventRecord(p.ev[0], s));
+    CKS(fem2d::launch_k1_tables(p, basis_kind, nu, nv, NO, NPT, s));
+    p.last_launches[0] = 1;
+    CKS(cudaEventRecord(p.ev[1], s));
+    if (mode == FEM2D_MODE_EXACT) CKS(fem2d::launch_k2_exact(p, nu, nv, NO, NPT, s, &p.last_launches[1]));
+    else if (mode == FEM2D_MODE_SUMFACT) CKS(fem2d::launch_k2_sumfact(p, nu, nv, NO, NPT, s, &p.last_launches[1]));
+    else CKS(fem2d::launch_k2_dmma(p, nu, nv, NO, NPT, s, &p.last_launches[1]));
+    CKS(cudaEventRecord(p.ev[2], s));
+    CKS(fem2d::launch_k3_scatter(p, slot_begin, slot_end, d_a, d_b, a_kind == FEM2D_INTEGRAL_L2_INNER, b_kind == FEM2D_INTEGRAL_L2_INNER, s, &p.last_launches[2]));
+    CKS(cudaEventRecord(p.ev[3], s));
+    p.last_launches[3] = p.last_launches[0] + p.last_launches[1] + p.last_launches[2];
+    p.timing_pending = true;
+    return FEM2D_OK;
+}
+
+int fem2d_plan_last_timing(fem2d_plan* plan, float ms[4], uint32_t launches[4]) {
+    if (!plan) return fail(FEM2D_ERR_BAD_ARGUMENT, "null plan");
+    fem2d::Plan& p = plan->p;
+    if (p.device < 0) return fail(FEM2D_ERR_NO_DEVICE, "host-only plan");
+    if (p.timing_pending) {
+        CKS(cudaSetDevice(p.device));
+        CKS(cudaEventSynchronize(p.ev[3]));
+        for (int k = 0; k < 3; k++) CKS(cudaEventElapsedTime(&p.last_ms[k], p.ev[k], p.ev[k + 1]));
+        CKS(cudaEventElapsedTime(&p.last_ms[3], p.ev[0], p.ev[3]));
+        p.timing_pending = false;
+    }
+    if (ms) std::copy(p.last_ms, p.last_ms + 4, ms);
+    if (launches) std::copy(p.last_launches, p.last_launches + 4, launches);
+    return FEM2D_OK;
+}
+
+int fem2d_assemble(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w, uint32_t nu,
+                   const double* v_pts, const double* v_w, uint32_t nv, uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals) {
+    int st = check_numeric_args(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv);
+    if (st != FEM2D_OK) return st;
+    if (!a_vals || !b_vals) return fail(FEM2D_ERR_BAD_ARGUMENT, "null output pointer");
+    fem2d::Plan& p = plan->p;
+    CKS(cudaSetDevice(p.device));
+    const size_t bytes = std::max<uint64_t>(p.nnz, 1) * sizeof(double);
+    if (!p.d_out_a) CKS(cudaMalloc((void**)&p.d_out_a, bytes));
+    if (!p.d_out_b) CKS(cudaMalloc((void**)&p.d_out_b, bytes));
+    st = fem2d_assemble_device(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, 0, UINT64_MAX, p.d_out_a, p.d_out_b, nullptr);
+    if (st != FEM2D_OK) return st;
+    // D2H of both value arrays; the pattern copies ride along when requested
+    CKS(cudaMemcpyAsync(a_vals, p.d_out_a, p.nnz * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+    CKS(cudaMemcpyAsync(b_vals, p.d_out_b, p.nnz * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+    if (rows) CKS(cudaMemcpyAsync(rows, p.d_rows, p.nnz * 4, cudaMemcpyDeviceToHost, nullptr));
+    if (cols) CKS(cudaMemcpyAsync(cols, p.d_cols, p.nnz * 4, cudaMemcpyDeviceToHost, nullptr));
+    CKS(cudaStreamSynchronize(nullptr));
+    return FEM2D_OK;
+}
+
+int fem2d_galerkin_sample_gep_hcurl(const fem2d_domain_view* view, int device, int basis_kind, int a_kind, int b_kind, int mode,
+                                    const double* u_pts, const double* u_w, uint32_t nu, const double* v_pts, const double* v_w, uint32_t nv,
+                                    uint64_t capacity, uint64_t* nnz_out, uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals) {
+    if (!view) return fail(FEM2D_ERR_BAD_ARGUMENT, "null view");
+    // reference order of the early errors (galerkin.rs:42-59)
+    if (view->continuity != FEM2D_CC_HCURL) return fail(FEM2D_ERR_WRONG_CONTINUITY, fem2d_status_string(FEM2D_ERR_WRONG_CONTINUITY));
+    if (view->n_dofs == 0) return fail(FEM2D_ERR_EMPTY_DOF_SET, fem2d_status_string(FEM2D_ERR_EMPTY_DOF_SET));
+    if (nu < 4 || nv < 4) return fail(FEM2D_ERR_INVALID_GLQ, fem2d_status_string(FEM2D_ERR_INVALID_GLQ));
+    fem2d_plan* plan = nullptr;
+    int st = fem2d_symbolic(view, device, 1, &plan);
+    if (st != FEM2D_OK) return st;
+    if (nnz_out) *nnz_out = plan->p.nnz;
+    if (plan->p.nnz > capacity) { fem2d_plan_free(plan); return fail(FEM2D_ERR_BAD_ARGUMENT, "output capacity too small (see *nnz_out)"); }
+    st = fem2d_assemble(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, rows, cols, a_vals, b_vals);
+    fem2d_plan_free(plan);
+    return st;
+}
+
+void* fem2d_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void fem2d_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int fem2d_fp64_peak(int device, int kind, double* gflops) {
+    if (!gflops) return fail(FEM2D_ERR_BAD_ARGUMENT, "null output");
+    int st = device_available(device);
+    if (st != FEM2D_OK) return st;
+    CKS(cudaSetDevice(device));
+    CKS(fem2d::fp64_peak(kind, gflops));
+    return FEM2D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// Internal: the plan object behind `fem2d_plan` and the launch wrappers implemented in the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "plan_host.hpp"
+
+namespace fem2d {
+
+struct Plan {
+    int device = -1;   // -1: host-only plan (pattern + partitioning available, numeric entry points refuse)
+    HostPlan host;
+    HostPattern host_pattern;   // filled for host-only plans only
+    uint64_t nnz = 0, n_extra = 0;
+    uint32_t max_contrib = 0;
+    uint64_t n_multi = 0;
+
+    // device-resident plan data
+    ClassDesc* d_classes = nullptr;
+    ListDesc* d_lists = nullptr;
+    uint8_t* d_spec_i = nullptr;
+    uint8_t* d_spec_j = nullptr;
+    TableDesc* d_tables = nullptr;
+    WorkItem* d_items = nullptr;
+    uint32_t* d_rows = nullptr;
+    uint32_t* d_cols = nullptr;
+    uint32_t* d_src1 = nullptr;
+    uint32_t* d_extra_slot = nullptr;
+    uint32_t* d_extra_src = nullptr;
+
+    // numeric scratch (allocated lazily, reused across calls)
+    double2* d_V = nullptr;
+    double* d_tabs = nullptr;
+    size_t tabs_capacity = 0;   // doubles
+    double* d_glq = nullptr;    // u_pts[64] u_w[64] v_pts[64] v_w[64]
+    double* d_gram = nullptr;   // fast modes scratch
+    size_t gram_capacity = 0;
+    double* d_out_a = nullptr;  // staging for host-output calls
+    double* d_out_b = nullptr;
+
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float last_ms[4] = {0, 0, 0, 0};
+    uint32_t last_launches[4] = {0, 0, 0, 0};
+    bool timing_pending = false;
+    int max_smem_optin = 0;
+    int sm_count = 0;
+};
+
+constexpr uint32_t MAX_GLQ = 128;   // default_ngq(20) = 128 (basis.rs:172-177)
+
+// device_plan.cu
+int device_symbolic(Plan& plan, std::string& err);
+int device_row_block_bounds(const Plan& plan, uint32_t world, uint64_t* bounds, std::string& err);
+void device_plan_release(Plan& plan);
+
+// kernels_exact.cu  (compiled with -fmad=false)
+cudaError_t launch_k1_tables(const Plan& plan, int basis_kind, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st);
+cudaError_t launch_k2_exact(const Plan& plan, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches);
+cudaError_t fp64_peak(int kind, double* gflops);
+
+// kernels_fast.cu
+cudaError_t launch_k2_sumfact(Plan& plan, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches);
+cudaError_t launch_k2_dmma(Plan& plan, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches);
+
+// kernels_scatter.cu
+cudaError_t launch_k3_scatter(const Plan& plan, uint64_t slot_begin, uint64_t slot_end, double* d_a, double* d_b, int selA, int selB, cudaStream_t st, uint32_t* launches);
+
+}  // namespace fem2d

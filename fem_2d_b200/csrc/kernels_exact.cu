@@ -1,0 +1,347 @@
+// K1 (basis-table sampler) and K2-exact (per-pair integrator that replays the reference's floating-point order).
+//
+// THIS FILE MUST BE COMPILED WITH -fmad=false: every product/sum below is a separately rounded IEEE-754 operation, in
+// the evaluation order of the reference expressions cited next to it.  Results are then bit-identical to the reference
+// algorithm (same GLQ nodes in).  Citations are relative to /root/reference/.
+//
+// Data flow of one pair (p on P, q on Q), per quadrature point (m, n)   [SURVEY.md App. A.4]:
+//   U-directed f:  curl_f = -(((jinv.u[0] * (N_i(m) * T'_j(n))) * ps_other[0]))        basis.rs:235-242, integrals.rs:43-48,240
+//                  val_f  =  (jinv.u[0] * N_i(m)) * T_j(n)                              basis.rs:225-227
+//   V-directed f:  curl_f =  ((jinv.v[1] * (T'_i(m) * N_j(n))) * ps_other[1])          basis.rs:245-252
+//                  val_f  =  (jinv.v[1] * T_i(m)) * N_j(n)                              basis.rs:230-232
+//   (the other vector component is (-0.0 * x): it only ever adds a signed zero, which cannot change a non-zero sum nor the
+//    +0.0 the accumulators start from, so dropping it is bit-exact)
+//   A: inner += ((curl_p * curl_q) [* ratio]) * v_w[n];  sol += inner * u_w[m];  A = (1/mu) * sol      integrals.rs:36-91, glq.rs:19-32
+//   B: inner += ((val_p * val_q) * max(det_P, det_Q)) * v_w[n]; ...; B = ((eps * glq_P) * glq_Q) * sol  integrals.rs:302-353
+// curl_f and val_f depend on one function only -> they are staged per block in shared memory ("slabs"), and each thread
+// contracts a 4 x 2 register tile of pairs over the points in strict (m outer, n inner) order.
+#include <cuda_runtime.h>
+
+#include "device_plan.hpp"
+
+namespace fem2d {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------- K1
+// HierMaxOrtho constants, verbatim incl. apparent typos (hierarchical_basis_fns.rs:206-225).
+__constant__ double c_euc_norm[12] = {0.968246, 2.561738, 0.838525, 4.248161, 0.816397, 5.882766, 0.808509, 1.0, 1.0, 1.0, 1.0, 1.0};
+__constant__ int c_q_num[12][14] = {
+    {-1, 0, 1}, {0, -3, 0, 3}, {-1, 0, -5, 0, 6}, {0, -3, 0, -7, 0, 10}, {-1, 0, -5, 0, -9, 0, 15},
+    {0, -3, 0, -7, 0, -11, 0, 21}, {-1, 0, -5, 0, -9, 0, -13, 0, 28}, {0, -3, 0, -7, 0, -11, 0, -15, 0, 36},
+    {-1, 0, -5, 0, -9, 0, -13, 0, -17, 0, 40}, {0, -3, 0, -7, 0, -11, 0, -15, 0, -19, 0, 55},
+    {-1, 0, -5, 0, -9, 0, -13, 0, -17, 0, -21, 0, 66}, {0, -3, 0, -7, 0, -11, 0, -15, 0, -19, 0, -23, 0, 72}};
+__constant__ int c_q_den[12] = {1, 3, 6, 10, 15, 21, 28, 36, 40, 55, 66, 72};
+
+// One CTA per table, one thread per point.  Output layout: out[((arr * NO) + order) * NPT + point], arr: 0 N, 1 N', 2 T, 3 T'.
+__global__ void k1_tables_kernel(const TableDesc* __restrict__ tabs, double* __restrict__ out, uint32_t NO, uint32_t NPT,
+                                 const double* __restrict__ glq, uint32_t nu, uint32_t nv, uint32_t i_max, uint32_t j_max, int basis) {
+    const TableDesc t = tabs[blockIdx.x];
+    const uint32_t np = t.axis ? nv : nu, nmax = t.axis ? j_max : i_max;
+    const double* pts = glq + (t.axis ? 256 : 0);
+    double* o = out + (size_t)blockIdx.x * 4 * NO * NPT;
+    for (uint32_t p = threadIdx.x; p < np; p += blockDim.x) {
+        // RBS ancestor -> descendant point map (basis.rs:372-393, glq.rs:238-249)
+        const double x = t.identity ? pts[p] : pts[p] * t.s + t.o;
+        auto N = [&](uint32_t n) -> double& { return o[(0 * NO + n) * NPT + p]; };
+        auto Nd = [&](uint32_t n) -> double& { return o[(1 * NO + n) * NPT + p]; };
+        auto T = [&](uint32_t n) -> double& { return o[(2 * NO + n) * NPT + p]; };
+        auto Td = [&](uint32_t n) -> double& { return o[(3 * NO + n) * NPT + p]; };
+        if (basis == FEM2D_BASIS_HIER_POLY) {   // HierPoly::new_without_d2, hierarchical_basis_fns.rs:102-162
+            double pw_prev = 1.0;
+            for (uint32_t n = 0; n <= nmax; n++) {
+                if (n == 0) { T(0) = 1.0 - x; Td(0) = -1.0; N(0) = 1.0; Nd(0) = 0.0; pw_prev = 1.0; }
+                else if (n == 1) { T(1) = 1.0 + x; Td(1) = 1.0; N(1) = x; Nd(1) = 1.0; pw_prev = x; }
+                else {
+                    const double pw = pw_prev * x;
+                    const double d1 = (double)n * pw_prev;
+                    N(n) = pw; Nd(n) = d1;
+                    if (n % 2 == 0) { T(n) = pw - 1.0; Td(n) = d1; }
+                    else { T(n) = pw - x; Td(n) = d1 - 1.0; }
+                    pw_prev = pw;
+                }
+            }
+        } else {   // HierMaxOrtho: LegendrePoly (:425-463) + QFunction (:316-352, :593-621)
+            double L[21], Ld[21];
+            for (uint32_t i = 0; i <= nmax; i++) {
+                const double i_f = (double)i;
+                if (i == 0) { L[0] = 1.0; Ld[0] = 0.0; }
+                else if (i == 1) { L[1] = x; Ld[1] = 1.0; }
+                else {
+                    L[i] = ((2.0 * i_f - 1.0) * x * L[i - 1] - (i_f - 1.0) * L[i - 2]) / i_f;
+                    Ld[i] = i_f * L[i - 1] + x * Ld[i - 1];
+                }
+                N(i) = L[i]; Nd(i) = Ld[i];
+            }
+            for (uint32_t i = 0; i <= nmax; i++) {
+                if (i == 0) { T(0) = 1.0 - x; Td(0) = -1.0; }
+                else if (i == 1) { T(1) = 1.0 + x; Td(1) = 1.0; }
+                else {
+                    double sv = 0.0, sp = 0.0;
+                    for (uint32_t k = 0; k <= i; k++) {
+                        const double w = ((double)c_q_num[i - 2][k]) / ((double)c_q_den[i - 2]);
+                        sv += w * L[k];
+                        sp += w * Ld[k];
+                    }
+                    T(i) = sv * c_euc_norm[i - 2];
+                    Td(i) = sp * c_euc_norm[i - 2];
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- K2
+struct K2Args {
+    const ClassDesc* classes; const ListDesc* lists; const uint8_t* spec_i; const uint8_t* spec_j;
+    const WorkItem* items; const double* tabs; const double* glq; double2* V;
+    uint32_t NO, NPT, nu, nv, chunk_pts;
+};
+
+__device__ __forceinline__ uint32_t pad4(uint32_t x) { return (x + 3u) & ~3u; }
+
+template <bool SAME>
+__device__ __forceinline__ void contract_point(const double* __restrict__ cp, const double* __restrict__ cq,
+                                               const double* __restrict__ fp, const double* __restrict__ fq, double ratio, double maxdet,
+                                               double w, double (&inA)[MT_P][MT_Q], double (&inB)[MT_P][MT_Q]) {
+    const double2 c01 = *reinterpret_cast<const double2*>(cp), c23 = *reinterpret_cast<const double2*>(cp + 2);
+    const double2 q01 = *reinterpret_cast<const double2*>(cq);
+    const double pc[4] = {c01.x, c01.y, c23.x, c23.y}, qc[2] = {q01.x, q01.y};
+#pragma unroll
+    for (int r = 0; r < MT_P; r++)
+#pragma unroll
+        for (int c = 0; c < MT_Q; c++) {
+            double t = pc[r] * qc[c];              // p_curl * q_curl
+            if (SAME) t = t * ratio;               // * max_uv_ratios / max_vu_ratios (integrals.rs:50,86)
+            inA[r][c] = inA[r][c] + t * w;         // inner_solution += integrand * v_w (glq.rs:27)
+        }
+    if (SAME) {
+        const double2 f01 = *reinterpret_cast<const double2*>(fp), f23 = *reinterpret_cast<const double2*>(fp + 2);
+        const double2 g01 = *reinterpret_cast<const double2*>(fq);
+        const double pf[4] = {f01.x, f01.y, f23.x, f23.y}, qf[2] = {g01.x, g01.y};
+#pragma unroll
+        for (int r = 0; r < MT_P; r++)
+#pragma unroll
+            for (int c = 0; c < MT_Q; c++) {
+                double t = pf[r] * qf[c];          // V2D::dot(f_p, f_q): the second product is a signed zero
+                t = t * maxdet;                    // * partial_max(det_P, det_Q) (integrals.rs:312-315)
+                inB[r][c] = inB[r][c] + t * w;
+            }
+    }
+}
+
+__global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g) {
+    extern __shared__ __align__(16) double smem[];
+    const WorkItem it = g.items[blockIdx.x];
+    const ClassDesc c = g.classes[it.cls];
+    const ListDesc LP = g.lists[c.listP], LQ = g.lists[c.listQ];
+    const uint32_t nP = LP.n, nUP = LP.nU, nQ = LQ.n, nUQ = LQ.nU;
+    const uint32_t strideP = pad4(nUP) + pad4(nP - nUP);
+    const uint32_t strideQ = c.local ? strideP : pad4(nUQ) + pad4(nQ - nUQ);
+    const uint32_t nu = g.nu, nv = g.nv, npts = nu * nv, chunk = g.chunk_pts;
+
+    double* s_uw = smem;                       // [128]
+    double* s_vw = smem + 128;                 // [128]
+    double* s_CP = smem + 256;                 // [chunk][strideP]
+    double* s_FP = s_CP + (size_t)chunk * strideP;
+    double* s_CQ = c.local ? s_CP : s_FP + (size_t)chunk * strideP;
+    double* s_FQ = c.local ? s_FP : s_CQ + (size_t)chunk * strideQ;
+    for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) s_uw[k] = g.glq[128 + k];
+    for (uint32_t k = threadIdx.x; k < nv; k += blockDim.x) s_vw[k] = g.glq[384 + k];
+
+    // ---- per-class constants (HierCurlBasisFn::defined_over, basis.rs:395-413; M2D::det / inverse, space.rs:138-147)
+    const double detP = c.dxP * c.dyP - 0.0 * 0.0, detQ = c.dxQ * c.dyQ - 0.0 * 0.0;
+    const double jiuP = c.dyP / detP, jivP = c.dxP / detP;     // jac_inv.u[0], jac_inv.v[1]
+    const double jiuQ = c.dyQ / detQ, jivQ = c.dxQ / detQ;
+    const double ge = (double)(detP >= detQ), lt = (double)(detP < detQ);
+    const double ratio_uv = ge * (c.dxP / c.dyP) + lt * (c.dxQ / c.dyQ);   // max_uv_ratios integrals.rs:250-259, basis.rs:341-343
+    const double ratio_vu = ge * (c.dyP / c.dxP) + lt * (c.dyQ / c.dxQ);   // max_vu_ratios integrals.rs:262-271, basis.rs:346-348
+    const double maxdet = detP > detQ ? detP : detQ;                        // partial_max integrals.rs:421-423
+    const double coefA = 1.0 / c.mu;                                        // integrals.rs:37
+    const double coefB = c.eps * (c.su * c.sv) * (1.0 * 1.0);               // eps * p.glq_scale() * q.glq_scale() integrals.rs:303-305
+
+    // ---- my micro-tile
+    const bool active = threadIdx.x < it.mt_count;
+    uint32_t sub = 0, row0 = 0, col0 = 0, row_end = 0, col_end = 0, prow = 0, pcol = 0;
+    if (active) {
+        const SubBlocks sb = make_subblocks(nP, nUP, nQ, nUQ, c.local);
+        uint32_t idx = it.mt_begin + threadIdx.x;
+        while (idx >= sb.cnt[sub]) { idx -= sb.cnt[sub]; sub++; }
+        const uint32_t nct = mt_div_up(sb.cols[sub], MT_Q);
+        uint32_t rt, ct;
+        if (sb.tri[sub]) {
+            rt = 0;
+            for (;;) { const uint32_t lo = rt * MT_P / MT_Q; const uint32_t cnt = nct > lo ? nct - lo : 0; if (idx < cnt) { ct = lo + idx; break; } idx -= cnt; rt++; }
+        } else { rt = idx / nct; ct = idx - rt * nct; }
+        row0 = sb.row0[sub] + rt * MT_P; col0 = sb.col0[sub] + ct * MT_Q;
+        row_end = sb.row0[sub] + sb.rows[sub]; col_end = sb.col0[sub] + sb.cols[sub];
+        prow = (sub >= 2 ? pad4(nUP) - nUP : 0) + row0;            // slab column of canonical row index
+        pcol = ((sub & 1) ? pad4(nUQ) - nUQ : 0) + col0;
+    }
+    const bool same = (sub == 0 || sub == 3);
+    const double ratio = sub == 0 ? ratio_uv : ratio_vu;
+
+    const double* tPu = g.tabs + (size_t)c.tabPu * 4 * g.NO * g.NPT;
+    const double* tPv = g.tabs + (size_t)c.tabPv * 4 * g.NO * g.NPT;
+    const double* tQu = g.tabs + (size_t)c.tabQu * 4 * g.NO * g.NPT;
+    const double* tQv = g.tabs + (size_t)c.tabQv * 4 * g.NO * g.NPT;
+    const uint32_t AS = g.NO * g.NPT;   // stride between the four arrays N, N', T, T'
+
+    double solA[MT_P][MT_Q], solB[MT_P][MT_Q], inA[MT_P][MT_Q], inB[MT_P][MT_Q];
+#pragma unroll
+    for (int r = 0; r < MT_P; r++)
+#pragma unroll
+        for (int q = 0; q < MT_Q; q++) { solA[r][q] = 0.0; solB[r][q] = 0.0; inA[r][q] = 0.0; inB[r][q] = 0.0; }
+
+    for (uint32_t pt0 = 0; pt0 < npts; pt0 += chunk) {
+        const uint32_t cn = min(chunk, npts - pt0);
+        __syncthreads();
+        // ---- stage the slabs: curl_f and val_f of every function at the chunk's points (the "sampler" applied per block)
+        for (int side = 0; side < (c.local ? 1 : 2); side++) {
+            const uint32_t stride = side ? strideQ : strideP, nF = side ? nQ : nP, nUF = side ? nUQ : nUP;
+            const ListDesc& L = side ? LQ : LP;
+            const double* tu = side ? tQu : tPu; const double* tv = side ? tQv : tPv;
+            const double jiu = side ? jiuQ : jiuP, jiv = side ? jivQ : jivP;
+            // derivative scale = the OTHER function's para_scale (integrals.rs:44,47); Q's is (1,1), P's is (su,sv)
+            const double ps0 = side ? c.su : 1.0, ps1 = side ? c.sv : 1.0;
+            double* sC = side ? s_CQ : s_CP; double* sF = side ? s_FQ : s_FP;
+            const uint32_t padU = pad4(nUF);
+            for (uint32_t k = threadIdx.x; k < cn * stride; k += blockDim.x) {
+                const uint32_t pl = k / stride, col = k - pl * stride;
+                const uint32_t pt = pt0 + pl, m = pt / nv, n = pt - m * nv;
+                double cv = 0.0, fv = 0.0;
+                if (col < nUF) {
+                    const uint32_t i = g.spec_i[L.off + col], j = g.spec_j[L.off + col];
+                    const double Ni = tu[(0 * g.NO + i) * g.NPT + m];
+                    const double Tj = tv[2 * AS + j * g.NPT + n], Tdj = tv[3 * AS + j * g.NPT + n];
+                    cv = -((jiu * (Ni * Tdj)) * ps0);
+                    fv = (jiu * Ni) * Tj;
+                } else if (col >= padU && col - padU < nF - nUF) {
+                    const uint32_t a = nUF + (col - padU);
+                    const uint32_t i = g.spec_i[L.off + a], j = g.spec_j[L.off + a];
+                    const double Ti = tu[2 * AS + i * g.NPT + m], Tdi = tu[3 * AS + i * g.NPT + m];
+                    const double Nj = tv[(0 * g.NO + j) * g.NPT + n];
+                    cv = (jiv * (Tdi * Nj)) * ps1;
+                    fv = (jiv * Ti) * Nj;
+                }
+                sC[k] = cv; sF[k] = fv;
+            }
+        }
+        __syncthreads();
+        if (active) {
+            uint32_t m = pt0 / nv, n = pt0 - m * nv;
+            const double* cp = s_CP + prow; const double* fp = s_FP + prow;
+            const double* cq = s_CQ + pcol; const double* fq = s_FQ + pcol;
+            for (uint32_t pl = 0; pl < cn; pl++) {
+                const double w = s_vw[n];
+                if (same) contract_point<true>(cp, cq, fp, fq, ratio, maxdet, w, inA, inB);
+                else contract_point<false>(cp, cq, fp, fq, ratio, maxdet, w, inA, inB);
+                cp += strideP; fp += strideP; cq += strideQ; fq += strideQ;
+                if (++n == nv) {   // end of the inner (v) loop: solution += inner_solution * u_w (glq.rs:29)
+                    const double uw = s_uw[m];
+#pragma unroll
+                    for (int r = 0; r < MT_P; r++)
+#pragma unroll
+                        for (int q = 0; q < MT_Q; q++) {
+                            solA[r][q] = solA[r][q] + inA[r][q] * uw; inA[r][q] = 0.0;
+                            solB[r][q] = solB[r][q] + inB[r][q] * uw; inB[r][q] = 0.0;
+                        }
+                    n = 0; m++;
+                }
+            }
+        }
+    }
+    if (!active) return;
+    double2* out = g.V + c.v_off;
+#pragma unroll
+    for (int r = 0; r < MT_P; r++) {
+        const uint32_t a = row0 + r;
+        if (a >= row_end) continue;
+#pragma unroll
+        for (int q = 0; q < MT_Q; q++) {
+            const uint32_t b = col0 + q;
+            if (b >= col_end) continue;
+            // cross-direction mass entries: every integrand term is a signed zero, the quadrature returns +0.0 (integrals.rs:318-339)
+            out[(size_t)a * nQ + b] = make_double2(coefA * solA[r][q], coefB * (same ? solB[r][q] : 0.0));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- FP64 peak
+template <int KIND>
+__global__ void fp64_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9 + 1.0, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3, a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double m = 1.0000001, b = 1e-9;
+    for (int k = 0; k < iters; k++) {
+        if (KIND == 0) {
+            a0 = __fma_rn(a0, m, b); a1 = __fma_rn(a1, m, b); a2 = __fma_rn(a2, m, b); a3 = __fma_rn(a3, m, b);
+            a4 = __fma_rn(a4, m, b); a5 = __fma_rn(a5, m, b); a6 = __fma_rn(a6, m, b); a7 = __fma_rn(a7, m, b);
+        } else {
+            a0 = __dadd_rn(__dmul_rn(a0, m), b); a1 = __dadd_rn(__dmul_rn(a1, m), b); a2 = __dadd_rn(__dmul_rn(a2, m), b); a3 = __dadd_rn(__dmul_rn(a3, m), b);
+            a4 = __dadd_rn(__dmul_rn(a4, m), b); a5 = __dadd_rn(__dmul_rn(a5, m), b); a6 = __dadd_rn(__dmul_rn(a6, m), b); a7 = __dadd_rn(__dmul_rn(a7, m), b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace
+
+cudaError_t launch_k1_tables(const Plan& P, int basis_kind, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st) {
+    k1_tables_kernel<<<(unsigned)P.host.tables.size(), 64, 0, st>>>(P.d_tables, P.d_tabs, NO, NPT, P.d_glq, nu, nv, P.host.i_max, P.host.j_max, basis_kind);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k2_exact(const Plan& P, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches) {
+    if (P.host.items.empty()) return cudaSuccess;
+    // shared memory: 256 doubles of weights + chunk * (C and F slabs of both sides).  Prefer <= ~100 KB so two CTAs share an SM.
+    uint32_t max_stride = 0;
+    for (const ClassDesc& c : P.host.classes) {
+        const ListDesc& LP = P.host.lists[c.listP]; const ListDesc& LQ = P.host.lists[c.listQ];
+        auto p4 = [](uint32_t x) { return (x + 3u) & ~3u; };
+        uint32_t s = p4(LP.nU) + p4(LP.n - LP.nU);
+        if (!c.local) s += p4(LQ.nU) + p4(LQ.n - LQ.nU);
+        max_stride = std::max(max_stride, s);
+    }
+    const size_t per_pt = (size_t)max_stride * 2 * sizeof(double);
+    const size_t fixed = 256 * sizeof(double);
+    const size_t soft = 100 * 1024, hard = (size_t)P.max_smem_optin - 1024;
+    const uint32_t npts = nu * nv;
+    uint32_t chunk = (uint32_t)std::min<size_t>(npts, (soft - fixed) / per_pt);
+    if (chunk < std::min<uint32_t>(npts, nv)) chunk = (uint32_t)std::min<size_t>(npts, (hard - fixed) / per_pt);   // at least one row if possible
+    if (chunk == 0) return cudaErrorInvalidConfiguration;
+    const size_t smem = fixed + (size_t)chunk * per_pt;
+    cudaError_t e = cudaFuncSetAttribute(k2_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, P.d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, chunk};
+    k2_exact_kernel<<<(unsigned)P.host.items.size(), K2_THREADS, smem, st>>>(g);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t fp64_peak(int kind, double* gflops) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, threads = 256, iters = 1 << 14;
+    double* d = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d, (size_t)blocks * threads * sizeof(double));
+    if (e != cudaSuccess) return e;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(a);
+        if (kind == 0) fp64_peak_kernel<0><<<blocks, threads>>>(d, iters); else fp64_peak_kernel<1><<<blocks, threads>>>(d, iters);
+        cudaEventRecord(b);
+        e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) break;
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    if (e != cudaSuccess) return e;
+    *gflops = (double)blocks * threads * iters * 8.0 * 2.0 / (best * 1e-3) / 1e9;   // 2 flops per (fma | mul+add)
+    return cudaGetLastError();
+}
+
+}  // namespace fem2d

@@ -1,0 +1,249 @@
+// Host part of the symbolic phase (see plan_host.hpp).  Compile with -ffp-contract=off.
+#include "plan_host.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <unordered_map>
+
+namespace fem2d {
+
+namespace {
+
+inline uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
+    const uint8_t* p = (const uint8_t*)data;
+    for (size_t k = 0; k < n; k++) { h ^= p[k]; h *= 1099511628211ull; }
+    return h;
+}
+
+// Child sub-range (h_refinement.rs:247-279).
+inline void sub_range(uint8_t loc, const double in[4], double out[4]) {
+    const double mu = (in[0] + in[1]) / 2.0, mv = (in[2] + in[3]) / 2.0;
+    const bool west = (loc == FEM2D_LOC_SW || loc == FEM2D_LOC_NW || loc == FEM2D_LOC_W);
+    const bool east = (loc == FEM2D_LOC_SE || loc == FEM2D_LOC_NE || loc == FEM2D_LOC_E);
+    const bool south = (loc == FEM2D_LOC_SW || loc == FEM2D_LOC_SE || loc == FEM2D_LOC_S);
+    const bool north = (loc == FEM2D_LOC_NW || loc == FEM2D_LOC_NE || loc == FEM2D_LOC_N);
+    out[0] = east ? mu : in[0];
+    out[1] = west ? mu : in[1];
+    out[2] = north ? mv : in[2];
+    out[3] = south ? mv : in[3];
+}
+// element.rs:76-78
+inline double map_range(double val, double in_min, double in_max, double out_min, double out_max) {
+    return (val - in_min) * (out_max - out_min) / (in_max - in_min) + out_min;
+}
+
+struct ClassKey {
+    double g[10];          // dxP dyP dxQ dyQ su ou sv ov eps mu
+    uint32_t listP, listQ, local, pad;
+    bool operator==(const ClassKey& o) const { return std::memcmp(this, &o, sizeof(ClassKey)) == 0; }
+};
+struct ClassKeyHash { size_t operator()(const ClassKey& k) const { return (size_t)fnv1a(&k, sizeof(ClassKey)); } };
+struct TabKey {
+    double s, o; uint32_t axis, identity;
+    bool operator==(const TabKey& t) const { return std::memcmp(this, &t, sizeof(TabKey)) == 0; }
+};
+struct TabKeyHash { size_t operator()(const TabKey& k) const { return (size_t)fnv1a(&k, sizeof(TabKey)); } };
+
+}  // namespace
+
+int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::string& err) {
+    if (!v) { err = "null view"; return FEM2D_ERR_BAD_ARGUMENT; }
+    // Reference error order: continuity condition, then empty DoF set (galerkin.rs:42-50).
+    if (v->continuity != FEM2D_CC_HCURL) { err = "Wrong Continuity Condition on Domain (required: H(Curl))"; return FEM2D_ERR_WRONG_CONTINUITY; }
+    if (v->n_dofs == 0) { err = "No Degrees-of-Freedom Defined over Domain"; return FEM2D_ERR_EMPTY_DOF_SET; }
+    const uint32_t ne = v->n_elems;
+    if (!v->elem_element || !v->elem_parent || !v->elem_loc || !v->element_p0 || !v->element_p3 || !v->element_eps_re ||
+        !v->element_mu_re || !v->bs_off) { err = "null array in view"; return FEM2D_ERR_BAD_ARGUMENT; }
+    const uint32_t nbs = v->bs_off[ne];
+    if (nbs && (!v->bs_i || !v->bs_j || !v->bs_dir || !v->bs_dof)) { err = "null basis-spec array in view"; return FEM2D_ERR_BAD_ARGUMENT; }
+    if (v->i_max > 20 || v->j_max > 20) { err = "expansion order exceeds MAX_POLYNOMIAL_ORDER (20)"; return FEM2D_ERR_UNSUPPORTED; }
+    P = HostPlan();
+    P.n_elems = ne; P.n_dofs = v->n_dofs; P.i_max = v->i_max; P.j_max = v->j_max;
+    P.bs_off.assign(v->bs_off, v->bs_off + ne + 1);
+
+    // ---- per-Elem geometry: parametric range (elem.rs:191-197) then the constant Jacobian diag(dx_du, dy_dv) (element.rs:33-50)
+    std::vector<double> range(4 * (size_t)ne);
+    P.elem_dx.resize(ne); P.elem_dy.resize(ne);
+    for (uint32_t e = 0; e < ne; e++) {
+        const int32_t par = v->elem_parent[e];
+        if (par >= (int32_t)e) { err = "elem_parent must precede its children"; return FEM2D_ERR_BAD_ARGUMENT; }
+        if (v->elem_element[e] >= v->n_elements) { err = "elem_element out of range"; return FEM2D_ERR_BAD_ARGUMENT; }
+        double* r = &range[4 * (size_t)e];
+        if (par < 0) { r[0] = -1.0; r[1] = 1.0; r[2] = -1.0; r[3] = 1.0; }
+        else {
+            if (v->elem_loc[e] > FEM2D_LOC_N) { err = "elem_loc out of range"; return FEM2D_ERR_BAD_ARGUMENT; }
+            sub_range(v->elem_loc[e], &range[4 * (size_t)par], r);
+        }
+        const double* p0 = &v->element_p0[2 * v->elem_element[e]];
+        const double* p3 = &v->element_p3[2 * v->elem_element[e]];
+        const double real_x_min = map_range(r[0], -1.0, 1.0, p0[0], p3[0]);
+        const double real_x_max = map_range(r[1], -1.0, 1.0, p0[0], p3[0]);
+        const double real_y_min = map_range(r[2], -1.0, 1.0, p0[1], p3[1]);
+        const double real_y_max = map_range(r[3], -1.0, 1.0, p0[1], p3[1]);
+        P.elem_dx[e] = (real_x_max - real_x_min) / 2.0;
+        P.elem_dy[e] = (real_y_max - real_y_min) / 2.0;
+    }
+
+    // ---- canonical BasisSpec lists, pooled by content
+    P.canon_dof.resize(nbs);
+    P.elem_list.assign(ne, UINT32_MAX);
+    std::unordered_map<uint64_t, std::vector<uint32_t>> list_pool;   // hash -> candidate list ids
+    std::vector<uint32_t> order;
+    std::vector<uint8_t> tmp;
+    for (uint32_t e = 0; e < ne; e++) {
+        const uint32_t b = v->bs_off[e], n = v->bs_off[e + 1] - b;
+        if (v->bs_off[e + 1] < b) { err = "bs_off must be non-decreasing"; return FEM2D_ERR_BAD_ARGUMENT; }
+        if (n == 0) continue;
+        order.resize(n);
+        std::iota(order.begin(), order.end(), 0u);
+        for (uint32_t k = 0; k < n; k++) {
+            if (v->bs_dir[b + k] > 1) { err = "bs_dir must be 0 (U) or 1 (V)"; return FEM2D_ERR_BAD_ARGUMENT; }
+            if (v->bs_dof[b + k] >= v->n_dofs) { err = "bs_dof out of range"; return FEM2D_ERR_BAD_ARGUMENT; }
+            if (v->bs_i[b + k] > v->i_max || v->bs_j[b + k] > v->j_max) { err = "basis-spec order exceeds i_max/j_max"; return FEM2D_ERR_BAD_ARGUMENT; }
+        }
+        std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+            const uint32_t kx = (uint32_t)v->bs_dir[b + x] << 16 | (uint32_t)v->bs_i[b + x] << 8 | v->bs_j[b + x];
+            const uint32_t ky = (uint32_t)v->bs_dir[b + y] << 16 | (uint32_t)v->bs_i[b + y] << 8 | v->bs_j[b + y];
+            return kx < ky;
+        });
+        tmp.resize(3 * (size_t)n);
+        uint32_t nU = 0;
+        for (uint32_t k = 0; k < n; k++) {
+            const uint32_t s = b + order[k];
+            P.canon_dof[b + k] = v->bs_dof[s];
+            tmp[3 * k] = v->bs_dir[s]; tmp[3 * k + 1] = v->bs_i[s]; tmp[3 * k + 2] = v->bs_j[s];
+            nU += v->bs_dir[s] == 0;
+        }
+        const uint64_t h = fnv1a(tmp.data(), tmp.size());
+        uint32_t id = UINT32_MAX;
+        for (uint32_t cand : list_pool[h]) {
+            const ListDesc& L = P.lists[cand];
+            if (L.n != n || L.nU != nU) continue;
+            bool same = true;
+            for (uint32_t k = 0; k < n && same; k++) same = P.spec_i[L.off + k] == tmp[3 * k + 1] && P.spec_j[L.off + k] == tmp[3 * k + 2];
+            if (same) { id = cand; break; }
+        }
+        if (id == UINT32_MAX) {
+            id = (uint32_t)P.lists.size();
+            P.lists.push_back(ListDesc{(uint32_t)P.spec_i.size(), n, nU, 0});
+            for (uint32_t k = 0; k < n; k++) { P.spec_i.push_back(tmp[3 * k + 1]); P.spec_j.push_back(tmp[3 * k + 2]); }
+            list_pool[h].push_back(id);
+        }
+        P.elem_list[e] = id;
+        P.max_list_n = std::max(P.max_list_n, n);
+    }
+
+    // ---- tables: ids 0 / 1 are the unscaled u / v tables
+    std::unordered_map<TabKey, uint32_t, TabKeyHash> tab_pool;
+    auto table_id = [&](double s, double o, uint32_t axis, uint32_t identity) {
+        TabKey k; std::memset(&k, 0, sizeof(k));
+        k.s = s; k.o = o; k.axis = axis; k.identity = identity;
+        auto it = tab_pool.find(k);
+        if (it != tab_pool.end()) return it->second;
+        const uint32_t id = (uint32_t)P.tables.size();
+        P.tables.push_back(TableDesc{s, o, axis, identity});
+        tab_pool.emplace(k, id);
+        return id;
+    };
+    table_id(1.0, 0.0, 0, 1);
+    table_id(1.0, 0.0, 1, 1);
+
+    // ---- blocks and classes.  Block order: for every Elem d (ascending) its local block, then its blocks with each
+    // ancestor that carries functions (nearest ancestor first).
+    std::unordered_map<ClassKey, uint32_t, ClassKeyHash> class_pool;
+    std::vector<uint8_t> locs;
+    for (uint32_t d = 0; d < ne; d++) {
+        const uint32_t nd = v->bs_off[d + 1] - v->bs_off[d];
+        if (nd == 0) continue;
+        locs.clear();
+        uint32_t child_on_path = d;
+        for (int32_t e = (int32_t)d; e >= 0; e = v->elem_parent[e]) {
+            const bool local = (uint32_t)e == d;
+            if (!local) locs.push_back(v->elem_loc[child_on_path]);   // locs: from d upwards to the child of e
+            child_on_path = (uint32_t)e;
+            const uint32_t nE = v->bs_off[e + 1] - v->bs_off[e];
+            if (nE == 0) continue;
+            ClassKey key; std::memset(&key, 0, sizeof(key));
+            double su = 1.0, ou = 0.0, sv = 1.0, ov = 0.0;
+            if (!local) {
+                // relative_parametric_range(e) of d: fold from the child of e down to d (elem.rs:170-188)
+                double r[4] = {-1.0, 1.0, -1.0, 1.0}, t[4];
+                for (auto it = locs.rbegin(); it != locs.rend(); ++it) { sub_range(*it, r, t); std::memcpy(r, t, sizeof(r)); }
+                su = (r[1] - r[0]) / 2.0; ou = (r[1] + r[0]) / 2.0;   // scale_gauss_quad_points glq.rs:238-249
+                sv = (r[3] - r[2]) / 2.0; ov = (r[3] + r[2]) / 2.0;
+            }
+            const uint32_t elP = v->elem_element[e];
+            key.g[0] = P.elem_dx[e]; key.g[1] = P.elem_dy[e]; key.g[2] = P.elem_dx[d]; key.g[3] = P.elem_dy[d];
+            key.g[4] = su; key.g[5] = ou; key.g[6] = sv; key.g[7] = ov;
+            key.g[8] = v->element_eps_re[elP]; key.g[9] = v->element_mu_re[elP];
+            key.listP = P.elem_list[e]; key.listQ = P.elem_list[d]; key.local = local ? 1u : 0u;
+            if (!dedupe) key.pad = (uint32_t)P.blocks.size() + 1;   // unique per block
+            uint32_t cls;
+            auto it = class_pool.find(key);
+            if (it != class_pool.end()) cls = it->second;
+            else {
+                cls = (uint32_t)P.classes.size();
+                ClassDesc c; std::memset(&c, 0, sizeof(c));
+                c.dxP = key.g[0]; c.dyP = key.g[1]; c.dxQ = key.g[2]; c.dyQ = key.g[3];
+                c.su = su; c.sv = sv; c.eps = key.g[8]; c.mu = key.g[9];
+                c.listP = key.listP; c.listQ = key.listQ; c.local = key.local;
+                c.tabPu = local ? 0u : table_id(su, ou, 0, 0);
+                c.tabPv = local ? 1u : table_id(sv, ov, 1, 0);
+                c.tabQu = 0; c.tabQv = 1;
+                c.v_off = P.n_values;
+                const ListDesc& LP = P.lists[c.listP]; const ListDesc& LQ = P.lists[c.listQ];
+                P.n_values += (uint64_t)LP.n * LQ.n;
+                const SubBlocks sb = make_subblocks(LP.n, LP.nU, LQ.n, LQ.nU, c.local);
+                c.n_mt = sb.cnt[0] + sb.cnt[1] + sb.cnt[2] + sb.cnt[3];
+                P.classes.push_back(c);
+                class_pool.emplace(key, cls);
+            }
+            BlockDesc b; b.pair_off = P.n_pairs; b.cls = cls; b.elemP = (uint32_t)e; b.elemQ = d; b.pad = 0;
+            P.blocks.push_back(b);
+            P.n_pairs += local ? (uint64_t)nd * (nd + 1) / 2 : (uint64_t)nE * nd;
+        }
+    }
+    if (P.n_values >= (1ull << 31) || P.n_pairs >= (1ull << 32)) { err = "domain too large for 32-bit source indices"; return FEM2D_ERR_UNSUPPORTED; }
+
+    // ---- work items: <= K2_THREADS micro-tiles each; largest classes first (longest-processing-time order)
+    std::vector<uint32_t> cls_order(P.classes.size());
+    std::iota(cls_order.begin(), cls_order.end(), 0u);
+    std::stable_sort(cls_order.begin(), cls_order.end(), [&](uint32_t a, uint32_t b) { return P.classes[a].n_mt > P.classes[b].n_mt; });
+    for (uint32_t c : cls_order)
+        for (uint32_t b = 0; b < P.classes[c].n_mt; b += K2_THREADS)
+            P.items.push_back(WorkItem{c, b, std::min<uint32_t>(K2_THREADS, P.classes[c].n_mt - b), 0});
+    return FEM2D_OK;
+}
+
+void build_host_pattern(const HostPlan& P, HostPattern& pat) {
+    struct Rec { uint64_t key; uint32_t src; };
+    std::vector<Rec> recs;
+    recs.reserve(P.n_pairs);
+    for (const BlockDesc& b : P.blocks) {
+        const ClassDesc& c = P.classes[b.cls];
+        const uint32_t nP = P.lists[c.listP].n, nQ = P.lists[c.listQ].n;
+        const uint32_t* dp = &P.canon_dof[P.bs_off[b.elemP]];
+        const uint32_t* dq = &P.canon_dof[P.bs_off[b.elemQ]];
+        for (uint32_t a = 0; a < nP; a++)
+            for (uint32_t q = c.local ? a : 0; q < nQ; q++) {
+                const uint32_t r = std::min(dp[a], dq[q]), cc = std::max(dp[a], dq[q]);
+                recs.push_back(Rec{(uint64_t)r << 32 | cc, (uint32_t)(c.v_off + (uint64_t)a * nQ + q)});
+            }
+    }
+    std::stable_sort(recs.begin(), recs.end(), [](const Rec& x, const Rec& y) { return x.key < y.key; });
+    pat = HostPattern();
+    uint32_t run = 0;
+    for (size_t k = 0; k < recs.size(); k++) {
+        if (k == 0 || recs[k].key != recs[k - 1].key) {
+            pat.rows.push_back((uint32_t)(recs[k].key >> 32)); pat.cols.push_back((uint32_t)recs[k].key); pat.src1.push_back(recs[k].src);
+            run = 1;
+        } else {
+            pat.extra_slot.push_back((uint32_t)pat.rows.size() - 1); pat.extra_src.push_back(recs[k].src);
+            run++;
+        }
+        pat.max_contrib = std::max(pat.max_contrib, run);
+    }
+}
+
+}  // namespace fem2d

@@ -1,0 +1,43 @@
+// Host part of the symbolic phase: turns a fem2d_domain_view into blocks / classes / lists / tables / work items
+// (plan_types.h).  Integer bookkeeping plus the per-Elem geometry of HierCurlBasisFn::defined_over (basis.rs:365-423),
+// evaluated in the reference's operation order -- compile this translation unit with -ffp-contract=off.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/fem2d.h"
+#include "plan_types.h"
+
+namespace fem2d {
+
+struct HostPlan {
+    uint32_t n_elems = 0, n_dofs = 0, i_max = 0, j_max = 0;
+    std::vector<uint32_t> bs_off;       // copy of the view's CSR offsets
+    std::vector<uint32_t> canon_dof;    // dof id of the k-th function of Elem e in canonical order, at bs_off[e] + k
+    std::vector<uint32_t> elem_list;    // list id per Elem
+    std::vector<ListDesc> lists;
+    std::vector<uint8_t> spec_i, spec_j;
+    std::vector<TableDesc> tables;
+    std::vector<ClassDesc> classes;
+    std::vector<BlockDesc> blocks;
+    std::vector<WorkItem> items;
+    std::vector<double> elem_dx, elem_dy;   // dx_du, dy_dv per Elem
+    uint64_t n_pairs = 0;    // == number of (p,q) integrations the reference performs (x2 for A and B)
+    uint64_t n_values = 0;   // entries of V
+    uint32_t max_list_n = 0;
+};
+
+// Returns FEM2D_OK or a status from include/fem2d.h; err receives a detail message.
+int build_host_plan(const fem2d_domain_view* view, bool dedupe, HostPlan& plan, std::string& err);
+
+// Host construction of the pattern (sorted unique keys, first source per slot, extra sources) -- used by device-less
+// plans (CPU tests of the host logic / partitioning) and as the cross-check of the device symbolic kernels.
+struct HostPattern {
+    std::vector<uint32_t> rows, cols, src1;
+    std::vector<uint32_t> extra_slot, extra_src;   // 2nd+ contributions, sorted by (slot, generation order)
+    uint32_t max_contrib = 0;
+};
+void build_host_pattern(const HostPlan& plan, HostPattern& pat);
+
+}  // namespace fem2d

@@ -1,0 +1,95 @@
+// Plain-data descriptors shared by the host planner (plan_host.cpp) and the CUDA kernels.
+//
+// Vocabulary (follows the reference's domain):
+//   block     one (Elem e, partner d) pair-group of galerkin.rs: d == e  -> "local-local" pairs (galerkin.rs:91-127),
+//             d a descendant of e -> "local-desc" pairs (galerkin.rs:138-178).  P = functions of e (sampled over d),
+//             Q = functions of d.
+//   class     a set of blocks whose inputs are bit-identical (Jacobians, RBS sub-range, materials, BasisSpec sets);
+//             integrated once into the value buffer V.
+//   list      canonical BasisSpec set of an Elem: sorted by (dir, i, j), U-directed first.
+//   table     1-D sampled basis table N, N', T, T' on one axis at GLQ points mapped by x*s + o (basis.rs:372-393).
+//   slot      position of a key [row<=col] in the sorted unique upper-triangular pattern.
+#pragma once
+#include <stdint.h>
+
+namespace fem2d {
+
+constexpr int MT_P = 4;   // micro-tile: P functions (rows) per thread
+constexpr int MT_Q = 2;   // micro-tile: Q functions (cols) per thread
+constexpr int K2_THREADS = 256;
+
+struct ClassDesc {
+    double dxP, dyP, dxQ, dyQ;   // dx_du, dy_dv (element.rs:46-47) of P's Elem and of Q's Elem
+    double su, sv;               // P's para_scale (basis.rs:419); (1,1) for local blocks. Q's is always (1,1).
+    double eps, mu;              // materials of P's Elem (galerkin.rs:78)
+    uint64_t v_off;              // first entry of this class in V; entry (a,b) at v_off + a*nQ + b
+    uint32_t listP, listQ;
+    uint32_t tabPu, tabPv, tabQu, tabQv;
+    uint32_t local;              // 1: d == e (symmetric block, only a <= b is consumed)
+    uint32_t n_mt;               // micro-tiles in this class
+};
+
+struct ListDesc {
+    uint32_t off;   // into spec_i / spec_j
+    uint32_t n;     // number of functions
+    uint32_t nU;    // the first nU are U-directed, the rest V-directed
+    uint32_t pad;
+};
+
+struct TableDesc {
+    double s, o;        // point map x' = x*s + o (glq.rs:238-249)
+    uint32_t axis;      // 0: u (orders up to i_max, nu points), 1: v (j_max, nv points)
+    uint32_t identity;  // 1: unscaled points (no arithmetic applied, basis.rs:375,392)
+};
+
+struct WorkItem {
+    uint32_t cls;
+    uint32_t mt_begin;   // first micro-tile handled by this item
+    uint32_t mt_count;   // <= K2_THREADS
+    uint32_t pad;
+};
+
+struct BlockDesc {
+    uint64_t pair_off;   // first pair of this block in the global pair enumeration
+    uint32_t cls;
+    uint32_t elemP, elemQ;
+    uint32_t pad;
+};
+
+// ---- micro-tile enumeration (host + device) --------------------------------------------------------------------------------
+// Sub-blocks in order: 0 = U rows x U cols, 1 = U x V, 2 = V x U (non-local only), 3 = V x V.  Local classes use the
+// upper triangle (in micro-tile granularity) of the two same-direction sub-blocks.
+struct SubBlocks {
+    uint32_t cnt[4];
+    uint32_t rows[4], cols[4];     // extents
+    uint32_t row0[4], col0[4];     // first canonical index
+    uint32_t tri[4];
+};
+#ifdef __CUDACC__
+#define FEM2D_HD __host__ __device__
+#else
+#define FEM2D_HD
+#endif
+FEM2D_HD inline uint32_t mt_div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+FEM2D_HD inline uint32_t mt_tri_count(uint32_t n) {
+    const uint32_t nrt = mt_div_up(n, MT_P), nct = mt_div_up(n, MT_Q);
+    uint32_t c = 0;
+    for (uint32_t rt = 0; rt < nrt; rt++) { const uint32_t lo = rt * MT_P / MT_Q; if (nct > lo) c += nct - lo; }
+    return c;
+}
+FEM2D_HD inline SubBlocks make_subblocks(uint32_t nP, uint32_t nUP, uint32_t nQ, uint32_t nUQ, uint32_t local) {
+    SubBlocks s;
+    const uint32_t nVP = nP - nUP, nVQ = nQ - nUQ;
+    const uint32_t R[4] = {nUP, nUP, nVP, nVP}, Cc[4] = {nUQ, nVQ, nUQ, nVQ};
+    const uint32_t r0[4] = {0, 0, nUP, nUP}, c0[4] = {0, nUQ, 0, nUQ};
+    for (int k = 0; k < 4; k++) {
+        s.rows[k] = R[k]; s.cols[k] = Cc[k]; s.row0[k] = r0[k]; s.col0[k] = c0[k];
+        s.tri[k] = (local && (k == 0 || k == 3)) ? 1u : 0u;
+        if (local && k == 2) s.cnt[k] = 0;
+        else if (s.tri[k]) s.cnt[k] = mt_tri_count(R[k]);
+        else s.cnt[k] = mt_div_up(R[k], MT_P) * mt_div_up(Cc[k], MT_Q);
+    }
+    return s;
+}
+
+}  // namespace fem2d

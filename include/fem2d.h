@@ -1,0 +1,152 @@
+/* =====================================================================================
+ * fem2d.h -- C-ABI of the B200-native Galerkin assembly path.
+ *
+ * Drop-in boundary for the reference's
+ *   galerkin_sample_gep_hcurl::<BSpace, CurlCurl, L2Inner>(&domain, Option<[usize;2]>)
+ *       -> Result<GEP, GalerkinSamplingError>            (src/fem_problem/galerkin.rs:33-40)
+ * The reference has no FFI of its own (pure Rust); these entry points are what a thin
+ * `fem_2d-sys` shim inside `fem_problem::galerkin` would bind (INTEGRATION.md shows it).
+ * Plain pointers and sizes only; no C++/torch types; never unwinds across the boundary.
+ *
+ * Everything below runs on the GPU (sm_100a).  There is no CPU fallback: without a CUDA
+ * device every numeric entry point returns FEM2D_ERR_NO_DEVICE.
+ * ===================================================================================== */
+#ifndef FEM2D_H
+#define FEM2D_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes.  1..3 mirror GalerkinSamplingError (galerkin.rs:191-195) and are decided before
+ * any compute, in the reference's order (galerkin.rs:42-59). */
+enum {
+    FEM2D_OK = 0,
+    FEM2D_ERR_WRONG_CONTINUITY = 1, /* GalerkinSamplingError::WrongContinuityCondition */
+    FEM2D_ERR_EMPTY_DOF_SET = 2,    /* GalerkinSamplingError::EmptyDOFSet */
+    FEM2D_ERR_INVALID_GLQ = 3,      /* GalerkinSamplingError::InvalidGLQSettings (< MIN_GLQ_ORDER = 4, galerkin.rs:13) */
+    FEM2D_ERR_BAD_ARGUMENT = 100,
+    FEM2D_ERR_NO_DEVICE = 101,      /* no CUDA device / driver: the product path refuses to run */
+    FEM2D_ERR_CUDA = 102,
+    FEM2D_ERR_UNSUPPORTED = 103,    /* unknown basis / integral kind, order > table limit, nnz >= 2^31 ... */
+    FEM2D_ERR_INTERNAL = 104,
+    FEM2D_ERR_OUT_OF_MEMORY = 105
+};
+
+/* BSpace type parameter (basis.rs:19-44 implementors). */
+enum {
+    FEM2D_BASIS_HIER_POLY = 0,     /* HierPoly (hierarchical_basis_fns.rs:15) == the "KOLShapeFn" of older releases */
+    FEM2D_BASIS_HIER_MAX_ORTHO = 1 /* HierMaxOrtho (hierarchical_basis_fns.rs:260), Legendre based, orders <= 12 */
+};
+/* AI / BI type parameters (integration.rs:59-90 implementors). */
+enum { FEM2D_INTEGRAL_CURL_CURL = 0 /* integrals.rs:13 */, FEM2D_INTEGRAL_L2_INNER = 1 /* integrals.rs:279 */ };
+/* ContinuityCondition (domain.rs:19-23). */
+enum { FEM2D_CC_HCURL = 0, FEM2D_CC_HDIV = 1, FEM2D_CC_DISCONTINUOUS = 2 };
+
+/* Numeric mode of the per-pair integrator.
+ * EXACT replays the reference's floating-point operation order (no FMA contraction): values are bit-identical
+ *   to the reference algorithm evaluated with the same GLQ nodes (the parity mode, default).
+ * SUMFACT evaluates the separable closed form (1-D Gram matrices); DMMA contracts Phi^T W Phi on FP64 tensor-core
+ *   tiles (mma.sync m8n8k4.f64).  Both are mathematically equal but re-ordered: they meet a scale-aware
+ *   tolerance (1e-12 relative, floor 1e-14*max|M|), not the literal one. */
+enum { FEM2D_MODE_EXACT = 0, FEM2D_MODE_SUMFACT = 1, FEM2D_MODE_DMMA = 2 };
+
+/* HRefLoc codes (h_refinement.rs:211-229) used in fem2d_domain_view::elem_loc. */
+enum { FEM2D_LOC_SW = 0, FEM2D_LOC_SE, FEM2D_LOC_NW, FEM2D_LOC_NE, FEM2D_LOC_W, FEM2D_LOC_E, FEM2D_LOC_S, FEM2D_LOC_N,
+       FEM2D_LOC_BASE = 255 };
+
+/* Read-only flattened view of a reference `Domain` (domain.rs:42-50).  All arrays are caller-owned HOST memory. */
+typedef struct fem2d_domain_view {
+    uint32_t n_elems;            /* mesh.elems.len() */
+    uint32_t n_elements;         /* mesh.elements.len() */
+    uint32_t n_dofs;             /* domain.dofs.len() */
+    uint32_t continuity;         /* domain.cc as FEM2D_CC_* (galerkin.rs:42) */
+    const uint32_t* elem_element; /* [n_elems] elem.element.id (elem.rs:105) */
+    const int32_t* elem_parent;   /* [n_elems] elem.parent_id() or -1 (elem.rs:158) */
+    const uint8_t* elem_loc;      /* [n_elems] last HRefLoc of elem.loc_stack() (elem.rs:109,165), FEM2D_LOC_BASE on the base layer */
+    const double* element_p0;     /* [n_elements][2] element.points[0].{x,y} (element.rs:38-42) */
+    const double* element_p3;     /* [n_elements][2] element.points[3].{x,y} */
+    const double* element_eps_re; /* [n_elements] materials.eps_rel.re (integrals.rs:303) */
+    const double* element_mu_re;  /* [n_elements] materials.mu_rel.re  (integrals.rs:37) */
+    const uint32_t* bs_off;       /* [n_elems+1] CSR offsets into the per-Elem BasisSpec lists (domain.basis_specs, domain.rs:47) */
+    const uint8_t* bs_i;          /* BasisSpec::i   (basis_spec.rs:13) */
+    const uint8_t* bs_j;          /* BasisSpec::j   (basis_spec.rs:15) */
+    const uint8_t* bs_dir;        /* BasisSpec::dir (0 = U, 1 = V)  (basis_spec.rs:17, :138-149) */
+    const uint32_t* bs_dof;       /* BasisSpec::dof_id (basis_spec.rs:23) */
+    uint32_t i_max, j_max;        /* mesh.max_expansion_orders() (galerkin.rs:65, mesh.rs:626) */
+} fem2d_domain_view;
+
+typedef struct fem2d_plan fem2d_plan; /* opaque: fixed sparsity pattern + scatter map + device buffers */
+
+/* Symbolic phase: validates the view (status 1/2 as the reference), enumerates the (Elem, Elem-or-descendant) pair blocks
+ * of galerkin.rs:91-178, groups bit-identical blocks into classes, and builds on `device` the sorted unique upper-
+ * triangular key set (== BTreeMap<[u32;2]> iteration order, sparse_matrix.rs:16,48-58) plus the per-slot source map.
+ * The plan is reusable across numeric calls on the same Domain. `dedupe` != 0 merges blocks whose inputs are
+ * bit-identical (geometry, materials, basis-spec sets) so they are integrated once. */
+int fem2d_symbolic(const fem2d_domain_view* view, int device, int dedupe, fem2d_plan** out);
+void fem2d_plan_free(fem2d_plan* plan);
+
+/* Plan queries. info[]: 0 nnz_upper, 1 n_pairs (galerkin.rs pair count), 2 n_blocks, 3 n_classes, 4 n_value_slots (V buffer
+ * entries), 5 n_multi (keys with >1 contribution), 6 max contributions per key, 7 n_tables, 8 n_work_items, 9 n_dofs */
+int fem2d_plan_info(const fem2d_plan* plan, uint64_t info[16]);
+/* Copy the pattern to host: rows[k] <= cols[k], sorted by (row, col). */
+int fem2d_plan_pattern(const fem2d_plan* plan, uint32_t* rows, uint32_t* cols);
+/* Device pointers of the pattern (uint32 rows, cols; length nnz_upper). */
+int fem2d_plan_pattern_device(const fem2d_plan* plan, const uint32_t** d_rows, const uint32_t** d_cols);
+
+/* Numeric phase into caller-provided DEVICE buffers d_a / d_b (nnz_upper doubles each, on the plan's device),
+ * asynchronous on `stream` (a cudaStream_t, may be NULL).  GLQ nodes / weights are HOST inputs so the caller can pass
+ * the exact values of gauss_quadrature_points (glq.rs:179-222, basis.rs:83-90).
+ * slot_begin/slot_end restrict the scatter to a row-block slice [slot_begin, slot_end) of the pattern (multi-GPU
+ * sharding, see fem2d_plan_row_blocks); pass 0 / UINT64_MAX for everything.  Values outside the slice are untouched. */
+int fem2d_assemble_device(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode,
+                          const double* u_pts, const double* u_w, uint32_t nu,
+                          const double* v_pts, const double* v_w, uint32_t nv,
+                          uint64_t slot_begin, uint64_t slot_end,
+                          double* d_a, double* d_b, void* stream);
+
+/* Numeric phase with HOST outputs (a_vals / b_vals: nnz_upper doubles each; rows / cols may be NULL). Synchronous. */
+int fem2d_assemble(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode,
+                   const double* u_pts, const double* u_w, uint32_t nu,
+                   const double* v_pts, const double* v_w, uint32_t nv,
+                   uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals);
+
+/* One-shot equivalent of the reference call: symbolic + numeric + copy-out.  The caller first asks for the size with
+ * fem2d_galerkin_nnz (or passes capacity and reads *nnz_out).  Status 1/2/3 exactly as galerkin.rs:42-59. */
+int fem2d_galerkin_sample_gep_hcurl(const fem2d_domain_view* view, int device, int basis_kind, int a_kind, int b_kind, int mode,
+                                    const double* u_pts, const double* u_w, uint32_t nu,
+                                    const double* v_pts, const double* v_w, uint32_t nv,
+                                    uint64_t capacity, uint64_t* nnz_out,
+                                    uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals);
+
+/* Row-block partition of the pattern for `world` ranks: bounds[r]..bounds[r+1] are slot indices aligned to row starts
+ * and balanced by nnz (bounds has world+1 entries). */
+int fem2d_plan_row_blocks(const fem2d_plan* plan, uint32_t world, uint64_t* bounds);
+
+/* Per-phase device timings of the last numeric call in milliseconds (CUDA events on the launch stream):
+ * ms[0] sampler (K1), ms[1] integrator (K2), ms[2] scatter (K3), ms[3] total; launches[0..2] kernel launch counts. */
+int fem2d_plan_last_timing(fem2d_plan* plan, float ms[4], uint32_t launches[4]);
+
+/* Pinned host memory for outputs (so the D2H copy of a 1 GB value array runs at PCIe speed). */
+void* fem2d_host_alloc(size_t bytes);
+void fem2d_host_free(void* p);
+
+/* Field evaluation, the caller-side "next" row: UniformFieldSpace::xy_fields (fields.rs:63-127).
+ * x_out / y_out: HOST [n_leaves][d][d] (reference indexing quirk: square densities only). leaf_ids: [n_leaves]. */
+int fem2d_xy_fields(const fem2d_domain_view* view, int device, int basis_kind, uint32_t density, const double* solution,
+                    uint64_t leaf_capacity, uint64_t* n_leaves, uint32_t* leaf_ids, double* x_out, double* y_out);
+
+/* FP64 pipe micro-benchmark (roofline denominator for the EXACT integrator): returns achieved GFLOP/s of a DFMA chain
+ * (kind 0) or of a DMUL+DADD non-fused chain (kind 1) on `device`. */
+int fem2d_fp64_peak(int device, int kind, double* gflops);
+
+int fem2d_device_count(void);
+const char* fem2d_status_string(int status);
+const char* fem2d_last_error(void); /* thread-local detail message of the last failing call */
+const char* fem2d_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEM2D_H */
