@@ -1,0 +1,142 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): CSR structure bit-exact; EXACT mode values bit-identical to the oracle (so the literal
+1e-12 relative / 1e-14 absolute tolerance holds trivially).  Re-ordered modes are judged with the scale-aware floor."""
+import numpy as np
+import pytest
+
+import recipes
+
+pytestmark = pytest.mark.gpu
+
+import fem_2d_b200 as F  # noqa: E402
+import oracle as O  # noqa: E402
+
+
+def _bits(x):
+    return np.ascontiguousarray(x, dtype=np.float64).view(np.uint64)
+
+
+def _assert_bit_identical(got, ref, what):
+    gb, rb = _bits(got), _bits(ref)
+    if not np.array_equal(gb, rb):
+        bad = np.nonzero(gb != rb)[0]
+        k = bad[0]
+        raise AssertionError(f"{what}: {len(bad)}/{len(gb)} entries differ bitwise; first at {k}: got {got[k]!r} ref {ref[k]!r}")
+
+
+def _glq(nu, nv):
+    # one node set shared by both sides: nodes/weights are inputs of the path
+    return (F.gauss_quadrature_points(nu), F.gauss_quadrature_points(nv))
+
+
+def _run_pair(name, nu, nv, basis=0, dedupe=True, mode=F.MODE_EXACT):
+    mo, mf = recipes.build_pair(name)
+    do, df = O.Domain.from_mesh(mo), F.Domain.from_mesh(mf)
+    glq = _glq(nu, nv)
+    ref = O.galerkin_sample_gep_hcurl(do, basis=basis, glq=glq)
+    plan = F.Plan(df.view(), device=0, dedupe=dedupe)
+    rows, cols, a, b = plan.assemble(glq, basis=F.HierPoly if basis == 0 else F.HierMaxOrtho, mode=mode)
+    return ref, plan, rows, cols, a, b
+
+
+@pytest.mark.parametrize("name", sorted(recipes.RECIPES))
+@pytest.mark.parametrize("dedupe", [True, False])
+def test_exact_bit_identical(name, dedupe):
+    ref, plan, rows, cols, a, b = _run_pair(name, 8, 8, dedupe=dedupe)
+    assert np.array_equal(rows, ref.rows) and np.array_equal(cols, ref.cols)
+    _assert_bit_identical(a, ref.a, f"A[{name}]")
+    _assert_bit_identical(b, ref.b, f"B[{name}]")
+    assert plan.info["max_contrib"] <= 2
+
+
+@pytest.mark.parametrize("nu,nv", [(4, 4), (5, 9), (12, 12), (7, 16), (32, 32)])
+def test_exact_glq_shapes(nu, nv):
+    # odd counts put a node at 0 (signed-zero paths), nu != nv exercises the (m outer, n inner) order
+    for name in ("slepc", "cfg4_small"):
+        ref, plan, rows, cols, a, b = _run_pair(name, nu, nv)
+        _assert_bit_identical(a, ref.a, f"A[{name},{nu}x{nv}]")
+        _assert_bit_identical(b, ref.b, f"B[{name},{nu}x{nv}]")
+
+
+def test_exact_max_ortho():
+    for name in ("slepc", "readme", "cfg4_small"):
+        ref, plan, rows, cols, a, b = _run_pair(name, 8, 8, basis=1)
+        _assert_bit_identical(a, ref.a, f"A[{name},HierMaxOrtho]")
+        _assert_bit_identical(b, ref.b, f"B[{name},HierMaxOrtho]")
+
+
+def test_device_pattern_matches_host_pattern():
+    for name in ("slepc", "edge_order", "cfg4_small"):
+        _, mf = recipes.build_pair(name)
+        df = F.Domain.from_mesh(mf)
+        pd = F.Plan(df.view(), device=0)
+        ph = F.Plan(df.view(), device=-1)
+        rd, cd = pd.pattern(); rh, ch = ph.pattern()
+        assert np.array_equal(rd, rh) and np.array_equal(cd, ch)
+        for k in ("nnz_upper", "n_pairs", "n_multi", "max_contrib", "n_extra"):
+            assert pd.info[k] == ph.info[k], k
+        assert np.array_equal(pd.row_blocks(3), ph.row_blocks(3))
+
+
+def test_reference_call_and_errors():
+    _, mf = recipes.build_pair("nalg")
+    df = F.Domain.from_mesh(mf)
+    gep = F.galerkin_sample_gep_hcurl(df, [8, 8])   # lib.rs:57-59
+    assert gep.a.dimension == 60 and len(gep.a.rows) == 660
+    sol = F.nalgebra_solve_gep(gep, 2.64)           # lib.rs:62-66
+    assert abs(sol.value - 2.6479657) < 1e-6
+    assert len(sol.vector) == df.num_dofs
+    with pytest.raises(F.GalerkinSamplingError) as e:
+        F.galerkin_sample_gep_hcurl(df, [3, 8])
+    assert e.value.kind == F.GalerkinSamplingError.InvalidGLQSettings
+    with pytest.raises(F.GalerkinSamplingError) as e:
+        F.galerkin_sample_gep_hcurl(F.Domain.blank(F.ContinuityCondition.HDiv), [8, 8])
+    assert e.value.kind == F.GalerkinSamplingError.WrongContinuityCondition
+    with pytest.raises(F.GalerkinSamplingError) as e:
+        F.galerkin_sample_gep_hcurl(F.Domain.blank(F.ContinuityCondition.HCurl), [8, 8])
+    assert e.value.kind == F.GalerkinSamplingError.EmptyDOFSet
+    # default GLQ (None): basis.rs:172-177 -> 16 points per axis for order 3... (4*3=12 -> 16)
+    gep2 = F.galerkin_sample_gep_hcurl(df, None)
+    ref = O.galerkin_sample_gep_hcurl(O.Domain.from_mesh(recipes.build_pair("nalg")[0]), glq=(F.gauss_quadrature_points(16), F.gauss_quadrature_points(16)))
+    _assert_bit_identical(gep2.a.values, ref.a, "A default glq")
+
+
+def test_slepc_fixture_residual_with_gpu_matrices():
+    """The reference's stored eigenpair (test_input/test_evec.dat, test_eval.dat) must satisfy A x = lambda B x with the GPU matrices."""
+    import struct
+    _, mf = recipes.build_pair("slepc")
+    df = F.Domain.from_mesh(mf)
+    assert df.num_dofs == 624
+    gep = F.galerkin_sample_gep_hcurl(df, [8, 8])
+    raw = open(recipes.GOLDEN + "/test_evec.dat", "rb").read()
+    cid, n = struct.unpack(">ii", raw[:8])
+    assert cid == 1211214 and n == 624
+    x = np.frombuffer(raw[8:], dtype=">f8").astype(np.float64)
+    lam = struct.unpack(">d", open(recipes.GOLDEN + "/test_eval.dat", "rb").read())[0]
+    A, B = gep.to_nalgebra_dense_mats()
+    r = A @ x - lam * (B @ x)
+    assert np.linalg.norm(r) / np.linalg.norm(A @ x) < 1e-12
+    assert abs((x @ A @ x) / (x @ B @ x) - 1.4745880937) < 1e-9   # lib.rs:104
+
+
+def test_swapped_integrals_and_slices():
+    _, mf = recipes.build_pair("readme")
+    df = F.Domain.from_mesh(mf)
+    glq = _glq(8, 8)
+    plan = F.Plan(df.view(), device=0)
+    r, c, a, b = plan.assemble(glq)
+    r2, c2, a2, b2 = plan.assemble(glq, a=F.L2Inner, b=F.CurlCurl)
+    _assert_bit_identical(a2, b, "swapped A")
+    _assert_bit_identical(b2, a, "swapped B")
+    # row-block slices through the device entry point reproduce the full result
+    import torch
+    da = torch.full((plan.nnz,), float("nan"), dtype=torch.float64, device="cuda:0")
+    db = torch.full((plan.nnz,), float("nan"), dtype=torch.float64, device="cuda:0")
+    bounds = plan.row_blocks(3)
+    for k in range(3):
+        plan.assemble_device(glq, da.data_ptr(), db.data_ptr(), slot_begin=int(bounds[k]), slot_end=int(bounds[k + 1]),
+                             stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    _assert_bit_identical(da.cpu().numpy(), a, "sliced A")
+    _assert_bit_identical(db.cpu().numpy(), b, "sliced B")
