@@ -74,7 +74,7 @@ class _View(C.Structure):
 ABI_SYMBOLS = [
     "fem2d_symbolic", "fem2d_plan_free", "fem2d_plan_info", "fem2d_plan_pattern", "fem2d_plan_pattern_device",
     "fem2d_assemble_device", "fem2d_assemble", "fem2d_galerkin_sample_gep_hcurl", "fem2d_plan_row_blocks",
-    "fem2d_plan_last_timing", "fem2d_host_alloc", "fem2d_host_free", "fem2d_xy_fields", "fem2d_fp64_peak",
+    "fem2d_plan_last_timing", "fem2d_plan_timing", "fem2d_assemble_range", "fem2d_host_alloc", "fem2d_host_free", "fem2d_xy_fields", "fem2d_fp64_peak",
     "fem2d_device_count", "fem2d_status_string", "fem2d_last_error", "fem2d_version",
 ]
 HOST_ABI_SYMBOLS = [
@@ -635,9 +635,17 @@ class Plan:
                                      _p(vp, C.c_double), _p(vw, C.c_double), C.c_uint32(len(vp)), C.c_uint64(slot_begin), C.c_uint64(slot_end),
                                      C.c_void_p(d_a), C.c_void_p(d_b), C.c_void_p(stream or None)))
 
-    def last_timing(self):
+    def assemble_range_into(self, glq, slot_begin: int, slot_end: int, a_ptr: int, b_ptr: int, rows_ptr: int = 0, cols_ptr: int = 0,
+                            basis=HierPoly, a=CurlCurl, b=L2Inner, mode: int = MODE_EXACT):
+        """fem2d_assemble_range with raw HOST pointers: numeric phase + D2H of the row-block slice."""
+        up, uw, vp, vw = self._glq_args(glq)
+        _ck(_L.fem2d_assemble_range(self._h, basis.kind, a.kind, b.kind, int(mode), _p(up, C.c_double), _p(uw, C.c_double), C.c_uint32(len(up)),
+                                    _p(vp, C.c_double), _p(vw, C.c_double), C.c_uint32(len(vp)), C.c_uint64(slot_begin), C.c_uint64(slot_end),
+                                    C.c_void_p(rows_ptr or None), C.c_void_p(cols_ptr or None), C.c_void_p(a_ptr), C.c_void_p(b_ptr)))
+
+    def last_timing(self, calls_back: int = 0):
         ms = (C.c_float * 4)(); ln = (C.c_uint32 * 4)()
-        _ck(_L.fem2d_plan_last_timing(self._h, ms, ln))
+        _ck(_L.fem2d_plan_timing(self._h, C.c_uint32(calls_back), ms, ln))
         return dict(sampler_ms=ms[0], integrator_ms=ms[1], scatter_ms=ms[2], total_ms=ms[3], launches=int(ln[3]),
                     launches_by_phase=[int(ln[0]), int(ln[1]), int(ln[2])])
 

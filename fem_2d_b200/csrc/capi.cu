@@ -180,56 +180,67 @@ int fem2d_assemble_device(fem2d_plan* plan, int basis_kind, int a_kind, int b_ki
     }
     if (!p.d_V) CKS(cudaMalloc((void**)&p.d_V, std::max<uint64_t>(p.host.n_values, 1) * sizeof(double2)));
     for (int k = 0; k < 4; k++) p.last_launches[k] = 0;
-    CKS(cudaEventRecord(p.ev[0], s));
+    cudaEvent_t* ev = p.ev[p.n_calls % fem2d::Plan::RING];
+    CKS(cudaEventRecord(ev[0], s));
     CKS(fem2d::launch_k1_tables(p, basis_kind, nu, nv, NO, NPT, s));
     p.last_launches[0] = 1;
-    CKS(cudaEventRecord(p.ev[1], s));
+    CKS(cudaEventRecord(ev[1], s));
     if (mode == FEM2D_MODE_EXACT) CKS(fem2d::launch_k2_exact(p, nu, nv, NO, NPT, s, &p.last_launches[1]));
     else if (mode == FEM2D_MODE_SUMFACT) CKS(fem2d::launch_k2_sumfact(p, nu, nv, NO, NPT, s, &p.last_launches[1]));
     else CKS(fem2d::launch_k2_dmma(p, nu, nv, NO, NPT, s, &p.last_launches[1]));
-    CKS(cudaEventRecord(p.ev[2], s));
+    CKS(cudaEventRecord(ev[2], s));
     CKS(fem2d::launch_k3_scatter(p, slot_begin, slot_end, d_a, d_b, a_kind == FEM2D_INTEGRAL_L2_INNER, b_kind == FEM2D_INTEGRAL_L2_INNER, s, &p.last_launches[2]));
-    CKS(cudaEventRecord(p.ev[3], s));
+    CKS(cudaEventRecord(ev[3], s));
     p.last_launches[3] = p.last_launches[0] + p.last_launches[1] + p.last_launches[2];
-    p.timing_pending = true;
+    p.n_calls++;
     return FEM2D_OK;
 }
 
-int fem2d_plan_last_timing(fem2d_plan* plan, float ms[4], uint32_t launches[4]) {
+int fem2d_plan_timing(fem2d_plan* plan, uint32_t calls_back, float ms[4], uint32_t launches[4]) {
     if (!plan) return fail(FEM2D_ERR_BAD_ARGUMENT, "null plan");
     fem2d::Plan& p = plan->p;
     if (p.device < 0) return fail(FEM2D_ERR_NO_DEVICE, "host-only plan");
-    if (p.timing_pending) {
-        CKS(cudaSetDevice(p.device));
-        CKS(cudaEventSynchronize(p.ev[3]));
-        for (int k = 0; k < 3; k++) CKS(cudaEventElapsedTime(&p.last_ms[k], p.ev[k], p.ev[k + 1]));
-        CKS(cudaEventElapsedTime(&p.last_ms[3], p.ev[0], p.ev[3]));
-        p.timing_pending = false;
+    if (calls_back >= fem2d::Plan::RING || calls_back >= p.n_calls) return fail(FEM2D_ERR_BAD_ARGUMENT, "no timing recorded that far back");
+    cudaEvent_t* ev = p.ev[(p.n_calls - 1 - calls_back) % fem2d::Plan::RING];
+    CKS(cudaSetDevice(p.device));
+    CKS(cudaEventSynchronize(ev[3]));
+    if (ms) {
+        for (int k = 0; k < 3; k++) CKS(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
+        CKS(cudaEventElapsedTime(&ms[3], ev[0], ev[3]));
     }
-    if (ms) std::copy(p.last_ms, p.last_ms + 4, ms);
     if (launches) std::copy(p.last_launches, p.last_launches + 4, launches);
+    return FEM2D_OK;
+}
+int fem2d_plan_last_timing(fem2d_plan* plan, float ms[4], uint32_t launches[4]) { return fem2d_plan_timing(plan, 0, ms, launches); }
+
+int fem2d_assemble_range(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w, uint32_t nu,
+                         const double* v_pts, const double* v_w, uint32_t nv, uint64_t slot_begin, uint64_t slot_end,
+                         uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals) {
+    int st = check_numeric_args(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv);
+    if (st != FEM2D_OK) return st;
+    if (!a_vals || !b_vals) return fail(FEM2D_ERR_BAD_ARGUMENT, "null output pointer");
+    fem2d::Plan& p = plan->p;
+    if (slot_end > p.nnz) slot_end = p.nnz;
+    if (slot_begin > slot_end) return fail(FEM2D_ERR_BAD_ARGUMENT, "slot_begin > slot_end");
+    CKS(cudaSetDevice(p.device));
+    const size_t bytes = std::max<uint64_t>(p.nnz, 1) * sizeof(double);
+    if (!p.d_out_a) CKS(cudaMalloc((void**)&p.d_out_a, bytes));
+    if (!p.d_out_b) CKS(cudaMalloc((void**)&p.d_out_b, bytes));
+    st = fem2d_assemble_device(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, slot_begin, slot_end, p.d_out_a, p.d_out_b, nullptr);
+    if (st != FEM2D_OK) return st;
+    // D2H of the slice of both value arrays (outputs are indexed from slot_begin); the pattern rides along when requested
+    const uint64_t n = slot_end - slot_begin;
+    CKS(cudaMemcpyAsync(a_vals, p.d_out_a + slot_begin, n * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+    CKS(cudaMemcpyAsync(b_vals, p.d_out_b + slot_begin, n * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+    if (rows) CKS(cudaMemcpyAsync(rows, p.d_rows + slot_begin, n * 4, cudaMemcpyDeviceToHost, nullptr));
+    if (cols) CKS(cudaMemcpyAsync(cols, p.d_cols + slot_begin, n * 4, cudaMemcpyDeviceToHost, nullptr));
+    CKS(cudaStreamSynchronize(nullptr));
     return FEM2D_OK;
 }
 
 int fem2d_assemble(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w, uint32_t nu,
                    const double* v_pts, const double* v_w, uint32_t nv, uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals) {
-    int st = check_numeric_args(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv);
-    if (st != FEM2D_OK) return st;
-    if (!a_vals || !b_vals) return fail(FEM2D_ERR_BAD_ARGUMENT, "null output pointer");
-    fem2d::Plan& p = plan->p;
-    CKS(cudaSetDevice(p.device));
-    const size_t bytes = std::max<uint64_t>(p.nnz, 1) * sizeof(double);
-    if (!p.d_out_a) CKS(cudaMalloc((void**)&p.d_out_a, bytes));
-    if (!p.d_out_b) CKS(cudaMalloc((void**)&p.d_out_b, bytes));
-    st = fem2d_assemble_device(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, 0, UINT64_MAX, p.d_out_a, p.d_out_b, nullptr);
-    if (st != FEM2D_OK) return st;
-    // D2H of both value arrays; the pattern copies ride along when requested
-    CKS(cudaMemcpyAsync(a_vals, p.d_out_a, p.nnz * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
-    CKS(cudaMemcpyAsync(b_vals, p.d_out_b, p.nnz * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
-    if (rows) CKS(cudaMemcpyAsync(rows, p.d_rows, p.nnz * 4, cudaMemcpyDeviceToHost, nullptr));
-    if (cols) CKS(cudaMemcpyAsync(cols, p.d_cols, p.nnz * 4, cudaMemcpyDeviceToHost, nullptr));
-    CKS(cudaStreamSynchronize(nullptr));
-    return FEM2D_OK;
+    return fem2d_assemble_range(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, 0, UINT64_MAX, rows, cols, a_vals, b_vals);
 }
 
 int fem2d_galerkin_sample_gep_hcurl(const fem2d_domain_view* view, int device, int basis_kind, int a_kind, int b_kind, int mode,

@@ -175,7 +175,7 @@ int device_symbolic(Plan& P, std::string& err) {
     CKC(cudaDeviceSynchronize());
     cleanup();
 #undef CKC
-    for (int k = 0; k < 4; k++) CK(cudaEventCreate(&P.ev[k]));
+    for (int r = 0; r < Plan::RING; r++) for (int k = 0; k < 4; k++) CK(cudaEventCreate(&P.ev[r][k]));
     CK(cudaMalloc((void**)&P.d_glq, 4 * 128 * sizeof(double)));
     return FEM2D_OK;
 }
@@ -198,7 +198,7 @@ void device_plan_release(Plan& P) {
     cudaFree(P.d_classes); cudaFree(P.d_lists); cudaFree(P.d_spec_i); cudaFree(P.d_spec_j); cudaFree(P.d_tables); cudaFree(P.d_items);
     cudaFree(P.d_rows); cudaFree(P.d_cols); cudaFree(P.d_src1); cudaFree(P.d_extra_slot); cudaFree(P.d_extra_src);
     cudaFree(P.d_V); cudaFree(P.d_tabs); cudaFree(P.d_glq); cudaFree(P.d_gram); cudaFree(P.d_out_a); cudaFree(P.d_out_b);
-    for (int k = 0; k < 4; k++) if (P.ev[k]) cudaEventDestroy(P.ev[k]);
+    for (int r = 0; r < Plan::RING; r++) for (int k = 0; k < 4; k++) if (P.ev[r][k]) cudaEventDestroy(P.ev[r][k]);
 }
 
 }  // namespace fem2d

@@ -39,10 +39,10 @@ struct Plan {
     double* d_out_a = nullptr;  // staging for host-output calls
     double* d_out_b = nullptr;
 
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    float last_ms[4] = {0, 0, 0, 0};
+    static constexpr int RING = 64;      // event sets of the last RING numeric calls (read back without syncing in between)
+    cudaEvent_t ev[RING][4] = {};
+    uint64_t n_calls = 0;
     uint32_t last_launches[4] = {0, 0, 0, 0};
-    bool timing_pending = false;
     int max_smem_optin = 0;
     int sm_count = 0;
 };

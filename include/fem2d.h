@@ -112,8 +112,15 @@ int fem2d_assemble(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int
                    const double* v_pts, const double* v_w, uint32_t nv,
                    uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals);
 
-/* One-shot equivalent of the reference call: symbolic + numeric + copy-out.  The caller first asks for the size with
- * fem2d_galerkin_nnz (or passes capacity and reads *nnz_out).  Status 1/2/3 exactly as galerkin.rs:42-59. */
+/* Same, restricted to the row-block slice [slot_begin, slot_end): outputs hold slot_end - slot_begin entries. */
+int fem2d_assemble_range(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode,
+                         const double* u_pts, const double* u_w, uint32_t nu,
+                         const double* v_pts, const double* v_w, uint32_t nv,
+                         uint64_t slot_begin, uint64_t slot_end,
+                         uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals);
+
+/* One-shot equivalent of the reference call: symbolic + numeric + copy-out.  The caller passes its output capacity; when it is too small
+ * the call fails with FEM2D_ERR_BAD_ARGUMENT and *nnz_out holds the required size.  Status 1/2/3 exactly as galerkin.rs:42-59. */
 int fem2d_galerkin_sample_gep_hcurl(const fem2d_domain_view* view, int device, int basis_kind, int a_kind, int b_kind, int mode,
                                     const double* u_pts, const double* u_w, uint32_t nu,
                                     const double* v_pts, const double* v_w, uint32_t nv,
@@ -127,6 +134,8 @@ int fem2d_plan_row_blocks(const fem2d_plan* plan, uint32_t world, uint64_t* boun
 /* Per-phase device timings of the last numeric call in milliseconds (CUDA events on the launch stream):
  * ms[0] sampler (K1), ms[1] integrator (K2), ms[2] scatter (K3), ms[3] total; launches[0..2] kernel launch counts. */
 int fem2d_plan_last_timing(fem2d_plan* plan, float ms[4], uint32_t launches[4]);
+/* Same for the numeric call `calls_back` calls ago (0 = last; the plan keeps the events of its last 64 calls). */
+int fem2d_plan_timing(fem2d_plan* plan, uint32_t calls_back, float ms[4], uint32_t launches[4]);
 
 /* Pinned host memory for outputs (so the D2H copy of a 1 GB value array runs at PCIe speed). */
 void* fem2d_host_alloc(size_t bytes);
