@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include <string>
@@ -74,7 +75,10 @@ int fem2d_symbolic(const fem2d_domain_view* view, int device, int dedupe, fem2d_
     try {
         fem2d_plan* plan = new fem2d_plan();
         std::string err;
+        const auto t0 = std::chrono::steady_clock::now();
         int st = fem2d::build_host_plan(view, dedupe != 0, plan->p.host, err);
+        const auto t1 = std::chrono::steady_clock::now();
+        plan->p.t_host_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
         if (st != FEM2D_OK) { delete plan; return fail(st, err); }
         if (plan->p.host.n_pairs >= (1ull << 31)) { delete plan; return fail(FEM2D_ERR_UNSUPPORTED, "more than 2^31 pairs"); }
         plan->p.device = device;
@@ -91,6 +95,7 @@ int fem2d_symbolic(const fem2d_domain_view* view, int device, int dedupe, fem2d_
             st = device_available(device);
             if (st != FEM2D_OK) { delete plan; return st; }
             st = fem2d::device_symbolic(plan->p, err);
+            plan->p.t_device_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t1).count();
             if (st != FEM2D_OK) { fem2d::device_plan_release(plan->p); delete plan; return fail(st, err); }
         }
         *out = plan;
@@ -112,6 +117,7 @@ int fem2d_plan_info(const fem2d_plan* plan, uint64_t info[16]) {
     info[0] = p.nnz; info[1] = p.host.n_pairs; info[2] = p.host.blocks.size(); info[3] = p.host.classes.size();
     info[4] = p.host.n_values; info[5] = p.n_multi; info[6] = p.max_contrib; info[7] = p.host.tables.size();
     info[8] = p.host.items.size(); info[9] = p.host.n_dofs; info[10] = p.host.lists.size(); info[11] = p.n_extra;
+    info[12] = p.t_host_us; info[13] = p.t_device_us;
     return FEM2D_OK;
 }
 

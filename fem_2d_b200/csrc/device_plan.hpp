@@ -15,6 +15,7 @@ struct Plan {
     uint64_t nnz = 0, n_extra = 0;
     uint32_t max_contrib = 0;
     uint64_t n_multi = 0;
+    uint64_t t_host_us = 0, t_device_us = 0;   // wall time of the two halves of the symbolic phase
 
     // device-resident plan data
     ClassDesc* d_classes = nullptr;

@@ -130,6 +130,19 @@ __device__ __forceinline__ void contract_point(const double* __restrict__ cp, co
     }
 }
 
+// Contract `run` consecutive points of one quadrature row (n .. n+run-1 of row m) into the inner accumulators.
+template <bool SAME>
+__device__ __forceinline__ void contract_run(const double*& cp, const double*& cq, const double*& fp, const double*& fq, uint32_t strideP,
+                                             uint32_t strideQ, const double* __restrict__ vw, uint32_t run, double ratio, double maxdet,
+                                             double (&inA)[MT_P][MT_Q], double (&inB)[MT_P][MT_Q]) {
+#pragma unroll 4
+    for (uint32_t k = 0; k < run; k++) {
+        contract_point<SAME>(cp, cq, fp, fq, ratio, maxdet, vw[k], inA, inB);
+        cp += strideP; cq += strideQ;
+        if (SAME) { fp += strideP; fq += strideQ; }
+    }
+}
+
 __global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g) {
     extern __shared__ __align__(16) double smem[];
     const WorkItem it = g.items[blockIdx.x];
@@ -160,109 +173,129 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g)
     const double coefA = 1.0 / c.mu;                                        // integrals.rs:37
     const double coefB = c.eps * (c.su * c.sv) * (1.0 * 1.0);               // eps * p.glq_scale() * q.glq_scale() integrals.rs:303-305
 
-    // ---- my micro-tile
-    const bool active = threadIdx.x < it.mt_count;
-    uint32_t sub = 0, row0 = 0, col0 = 0, row_end = 0, col_end = 0, prow = 0, pcol = 0;
-    if (active) {
-        const SubBlocks sb = make_subblocks(nP, nUP, nQ, nUQ, c.local);
-        uint32_t idx = it.mt_begin + threadIdx.x;
-        while (idx >= sb.cnt[sub]) { idx -= sb.cnt[sub]; sub++; }
-        const uint32_t nct = mt_div_up(sb.cols[sub], MT_Q);
-        uint32_t rt, ct;
-        if (sb.tri[sub]) {
-            rt = 0;
-            for (;;) { const uint32_t lo = rt * MT_P / MT_Q; const uint32_t cnt = nct > lo ? nct - lo : 0; if (idx < cnt) { ct = lo + idx; break; } idx -= cnt; rt++; }
-        } else { rt = idx / nct; ct = idx - rt * nct; }
-        row0 = sb.row0[sub] + rt * MT_P; col0 = sb.col0[sub] + ct * MT_Q;
-        row_end = sb.row0[sub] + sb.rows[sub]; col_end = sb.col0[sub] + sb.cols[sub];
-        prow = (sub >= 2 ? pad4(nUP) - nUP : 0) + row0;            // slab column of canonical row index
-        pcol = ((sub & 1) ? pad4(nUQ) - nUQ : 0) + col0;
-    }
-    const bool same = (sub == 0 || sub == 3);
-    const double ratio = sub == 0 ? ratio_uv : ratio_vu;
-
     const double* tPu = g.tabs + (size_t)c.tabPu * 4 * g.NO * g.NPT;
     const double* tPv = g.tabs + (size_t)c.tabPv * 4 * g.NO * g.NPT;
     const double* tQu = g.tabs + (size_t)c.tabQu * 4 * g.NO * g.NPT;
     const double* tQv = g.tabs + (size_t)c.tabQv * 4 * g.NO * g.NPT;
     const uint32_t AS = g.NO * g.NPT;   // stride between the four arrays N, N', T, T'
-
-    double solA[MT_P][MT_Q], solB[MT_P][MT_Q], inA[MT_P][MT_Q], inB[MT_P][MT_Q];
-#pragma unroll
-    for (int r = 0; r < MT_P; r++)
-#pragma unroll
-        for (int q = 0; q < MT_Q; q++) { solA[r][q] = 0.0; solB[r][q] = 0.0; inA[r][q] = 0.0; inB[r][q] = 0.0; }
-
-    for (uint32_t pt0 = 0; pt0 < npts; pt0 += chunk) {
-        const uint32_t cn = min(chunk, npts - pt0);
-        __syncthreads();
-        // ---- stage the slabs: curl_f and val_f of every function at the chunk's points (the "sampler" applied per block)
-        for (int side = 0; side < (c.local ? 1 : 2); side++) {
-            const uint32_t stride = side ? strideQ : strideP, nF = side ? nQ : nP, nUF = side ? nUQ : nUP;
-            const ListDesc& L = side ? LQ : LP;
-            const double* tu = side ? tQu : tPu; const double* tv = side ? tQv : tPv;
-            const double jiu = side ? jiuQ : jiuP, jiv = side ? jivQ : jivP;
-            // derivative scale = the OTHER function's para_scale (integrals.rs:44,47); Q's is (1,1), P's is (su,sv)
-            const double ps0 = side ? c.su : 1.0, ps1 = side ? c.sv : 1.0;
-            double* sC = side ? s_CQ : s_CP; double* sF = side ? s_FQ : s_FP;
-            const uint32_t padU = pad4(nUF);
-            for (uint32_t k = threadIdx.x; k < cn * stride; k += blockDim.x) {
-                const uint32_t pl = k / stride, col = k - pl * stride;
-                const uint32_t pt = pt0 + pl, m = pt / nv, n = pt - m * nv;
-                double cv = 0.0, fv = 0.0;
-                if (col < nUF) {
-                    const uint32_t i = g.spec_i[L.off + col], j = g.spec_j[L.off + col];
-                    const double Ni = tu[(0 * g.NO + i) * g.NPT + m];
-                    const double Tj = tv[2 * AS + j * g.NPT + n], Tdj = tv[3 * AS + j * g.NPT + n];
-                    cv = -((jiu * (Ni * Tdj)) * ps0);
-                    fv = (jiu * Ni) * Tj;
-                } else if (col >= padU && col - padU < nF - nUF) {
-                    const uint32_t a = nUF + (col - padU);
-                    const uint32_t i = g.spec_i[L.off + a], j = g.spec_j[L.off + a];
-                    const double Ti = tu[2 * AS + i * g.NPT + m], Tdi = tu[3 * AS + i * g.NPT + m];
-                    const double Nj = tv[(0 * g.NO + j) * g.NPT + n];
-                    cv = (jiv * (Tdi * Nj)) * ps1;
-                    fv = (jiv * Ti) * Nj;
-                }
-                sC[k] = cv; sF[k] = fv;
-            }
-        }
-        __syncthreads();
-        if (active) {
-            uint32_t m = pt0 / nv, n = pt0 - m * nv;
-            const double* cp = s_CP + prow; const double* fp = s_FP + prow;
-            const double* cq = s_CQ + pcol; const double* fq = s_FQ + pcol;
-            for (uint32_t pl = 0; pl < cn; pl++) {
-                const double w = s_vw[n];
-                if (same) contract_point<true>(cp, cq, fp, fq, ratio, maxdet, w, inA, inB);
-                else contract_point<false>(cp, cq, fp, fq, ratio, maxdet, w, inA, inB);
-                cp += strideP; fp += strideP; cq += strideQ; fq += strideQ;
-                if (++n == nv) {   // end of the inner (v) loop: solution += inner_solution * u_w (glq.rs:29)
-                    const double uw = s_uw[m];
-#pragma unroll
-                    for (int r = 0; r < MT_P; r++)
-#pragma unroll
-                        for (int q = 0; q < MT_Q; q++) {
-                            solA[r][q] = solA[r][q] + inA[r][q] * uw; inA[r][q] = 0.0;
-                            solB[r][q] = solB[r][q] + inB[r][q] * uw; inB[r][q] = 0.0;
-                        }
-                    n = 0; m++;
-                }
-            }
-        }
-    }
-    if (!active) return;
+    __shared__ SubBlocks sb;
+    if (threadIdx.x == 0) sb = make_subblocks(nP, nUP, nQ, nUQ, c.local);
+    __syncthreads();
+    const bool single_chunk = chunk >= npts;
     double2* out = g.V + c.v_off;
+
+    for (uint32_t round0 = 0; round0 < it.mt_count; round0 += K2_THREADS) {
+        // ---- my micro-tile of this round
+        const bool active = round0 + threadIdx.x < it.mt_count;
+        uint32_t sub = 0, row0 = 0, col0 = 0, row_end = 0, col_end = 0, prow = 0, pcol = 0;
+        if (active) {
+            uint32_t idx = it.mt_begin + round0 + threadIdx.x;
+            while (idx >= sb.cnt[sub]) { idx -= sb.cnt[sub]; sub++; }
+            const uint32_t nct = mt_div_up(sb.cols[sub], MT_Q);
+            uint32_t rt, ct;
+            if (sb.tri[sub]) {
+                rt = 0;
+                for (;;) { const uint32_t lo = rt * MT_P / MT_Q; const uint32_t cnt = nct > lo ? nct - lo : 0; if (idx < cnt) { ct = lo + idx; break; } idx -= cnt; rt++; }
+            } else { rt = idx / nct; ct = idx - rt * nct; }
+            row0 = sb.row0[sub] + rt * MT_P; col0 = sb.col0[sub] + ct * MT_Q;
+            row_end = sb.row0[sub] + sb.rows[sub]; col_end = sb.col0[sub] + sb.cols[sub];
+            prow = (sub >= 2 ? pad4(nUP) - nUP : 0) + row0;            // slab column of the canonical row index
+            pcol = ((sub & 1) ? pad4(nUQ) - nUQ : 0) + col0;
+        }
+        const bool same = (sub == 0 || sub == 3);
+        const double ratio = sub == 0 ? ratio_uv : ratio_vu;
+
+        double solA[MT_P][MT_Q], solB[MT_P][MT_Q], inA[MT_P][MT_Q], inB[MT_P][MT_Q];
 #pragma unroll
-    for (int r = 0; r < MT_P; r++) {
-        const uint32_t a = row0 + r;
-        if (a >= row_end) continue;
+        for (int r = 0; r < MT_P; r++)
 #pragma unroll
-        for (int q = 0; q < MT_Q; q++) {
-            const uint32_t b = col0 + q;
-            if (b >= col_end) continue;
-            // cross-direction mass entries: every integrand term is a signed zero, the quadrature returns +0.0 (integrals.rs:318-339)
-            out[(size_t)a * nQ + b] = make_double2(coefA * solA[r][q], coefB * (same ? solB[r][q] : 0.0));
+            for (int q = 0; q < MT_Q; q++) { solA[r][q] = 0.0; solB[r][q] = 0.0; inA[r][q] = 0.0; inB[r][q] = 0.0; }
+
+        for (uint32_t pt0 = 0; pt0 < npts; pt0 += chunk) {
+            const uint32_t cn = min(chunk, npts - pt0);
+            if (!(single_chunk && round0 > 0)) {   // a class whose slabs cover all points is staged once for all rounds
+                __syncthreads();
+                // ---- stage the slabs: curl_f and val_f of every function at the chunk's points (the sampler applied per block).
+                // One task = (function column, quadrature row m); the n loop runs inside so N_i(m) / T_i(m) are loaded once.
+                const uint32_t m_lo = pt0 / nv, m_hi = (pt0 + cn - 1) / nv;
+                for (int side = 0; side < (c.local ? 1 : 2); side++) {
+                    const uint32_t stride = side ? strideQ : strideP, nF = side ? nQ : nP, nUF = side ? nUQ : nUP;
+                    const uint32_t loff = side ? LQ.off : LP.off;
+                    const double* tu = side ? tQu : tPu; const double* tv = side ? tQv : tPv;
+                    const double jiu = side ? jiuQ : jiuP, jiv = side ? jivQ : jivP;
+                    // derivative scale = the OTHER function's para_scale (integrals.rs:44,47); Q's is (1,1), P's is (su,sv)
+                    const double ps0 = side ? c.su : 1.0, ps1 = side ? c.sv : 1.0;
+                    double* sC = side ? s_CQ : s_CP; double* sF = side ? s_FQ : s_FP;
+                    const uint32_t padU = pad4(nUF);
+                    const uint32_t ntask = (m_hi - m_lo + 1) * stride;
+                    for (uint32_t t = threadIdx.x; t < ntask; t += blockDim.x) {
+                        const uint32_t mi = t / stride, col = t - mi * stride, m = m_lo + mi;
+                        const uint32_t n_lo = (m == m_lo) ? pt0 - m_lo * nv : 0u;
+                        const uint32_t n_hi = (m == m_hi) ? pt0 + cn - 1 - m_hi * nv : nv - 1;
+                        double* dC = sC + (size_t)(m * nv + n_lo - pt0) * stride + col;
+                        double* dF = sF + (size_t)(m * nv + n_lo - pt0) * stride + col;
+                        if (col < nUF) {
+                            const uint32_t i = g.spec_i[loff + col], j = g.spec_j[loff + col];
+                            const double Ni = tu[(0 * g.NO + i) * g.NPT + m];
+                            const double jN = jiu * Ni;
+                            const double* Tj = tv + 2 * AS + j * g.NPT; const double* Tdj = tv + 3 * AS + j * g.NPT;
+                            for (uint32_t n = n_lo; n <= n_hi; n++, dC += stride, dF += stride) {
+                                *dC = -((jiu * (Ni * Tdj[n])) * ps0);
+                                *dF = jN * Tj[n];
+                            }
+                        } else if (col >= padU && col - padU < nF - nUF) {
+                            const uint32_t a = nUF + (col - padU);
+                            const uint32_t i = g.spec_i[loff + a], j = g.spec_j[loff + a];
+                            const double Ti = tu[2 * AS + i * g.NPT + m], Tdi = tu[3 * AS + i * g.NPT + m];
+                            const double jT = jiv * Ti;
+                            const double* Nj = tv + (0 * g.NO + j) * g.NPT;
+                            for (uint32_t n = n_lo; n <= n_hi; n++, dC += stride, dF += stride) {
+                                *dC = (jiv * (Tdi * Nj[n])) * ps1;
+                                *dF = jT * Nj[n];
+                            }
+                        } else {
+                            for (uint32_t n = n_lo; n <= n_hi; n++, dC += stride, dF += stride) { *dC = 0.0; *dF = 0.0; }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            if (active) {
+                uint32_t m = pt0 / nv, n = pt0 - m * nv, pl = 0;
+                const double* cp = s_CP + prow; const double* fp = s_FP + prow;
+                const double* cq = s_CQ + pcol; const double* fq = s_FQ + pcol;
+                while (pl < cn) {
+                    const uint32_t run = min(cn - pl, nv - n);
+                    if (same) contract_run<true>(cp, cq, fp, fq, strideP, strideQ, s_vw + n, run, ratio, maxdet, inA, inB);
+                    else contract_run<false>(cp, cq, fp, fq, strideP, strideQ, s_vw + n, run, ratio, maxdet, inA, inB);
+                    pl += run; n += run;
+                    if (n == nv) {   // end of the inner (v) loop: solution += inner_solution * u_w (glq.rs:29)
+                        const double uw = s_uw[m];
+#pragma unroll
+                        for (int r = 0; r < MT_P; r++)
+#pragma unroll
+                            for (int q = 0; q < MT_Q; q++) {
+                                solA[r][q] = solA[r][q] + inA[r][q] * uw; inA[r][q] = 0.0;
+                                if (same) { solB[r][q] = solB[r][q] + inB[r][q] * uw; inB[r][q] = 0.0; }
+                            }
+                        n = 0; m++;
+                    }
+                }
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int r = 0; r < MT_P; r++) {
+                const uint32_t a = row0 + r;
+                if (a >= row_end) continue;
+#pragma unroll
+                for (int q = 0; q < MT_Q; q++) {
+                    const uint32_t b = col0 + q;
+                    if (b >= col_end) continue;
+                    // cross-direction mass entries: every integrand term is a signed zero, the quadrature returns +0.0 (integrals.rs:318-339)
+                    out[(size_t)a * nQ + b] = make_double2(coefA * solA[r][q], coefB * (same ? solB[r][q] : 0.0));
+                }
+            }
         }
     }
 }

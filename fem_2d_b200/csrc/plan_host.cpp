@@ -4,16 +4,23 @@
 #include <algorithm>
 #include <cstring>
 #include <numeric>
+#include <thread>
 #include <unordered_map>
 
 namespace fem2d {
 
 namespace {
 
+// 64-bit word-wise mixing hash (keys are memset-padded PODs whose size is a multiple of 4)
 inline uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
     const uint8_t* p = (const uint8_t*)data;
-    for (size_t k = 0; k < n; k++) { h ^= p[k]; h *= 1099511628211ull; }
-    return h;
+    size_t k = 0;
+    for (; k + 8 <= n; k += 8) {
+        uint64_t w; std::memcpy(&w, p + k, 8);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull; h ^= h >> 29;
+    }
+    for (; k < n; k++) { h ^= p[k]; h *= 1099511628211ull; }
+    return h ^ (h >> 32);
 }
 
 // Child sub-range (h_refinement.rs:247-279).
@@ -85,50 +92,100 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
         P.elem_dy[e] = (real_y_max - real_y_min) / 2.0;
     }
 
-    // ---- canonical BasisSpec lists, pooled by content
+    // ---- canonical BasisSpec lists, pooled by content.
+    // Phase A (parallel over Elems): validate, sort each Elem's specs by (dir, i, j), emit canon_dof and a content hash.
+    // Phase B (serial): pool identical lists.
     P.canon_dof.resize(nbs);
     P.elem_list.assign(ne, UINT32_MAX);
+    for (uint32_t e = 0; e < ne; e++) {
+        if (v->bs_off[e + 1] < v->bs_off[e]) { err = "bs_off must be non-decreasing"; return FEM2D_ERR_BAD_ARGUMENT; }
+        if (v->bs_off[e + 1] - v->bs_off[e] >= (1u << 11)) { err = "more than 2047 basis specs on one Elem"; return FEM2D_ERR_UNSUPPORTED; }
+    }
+    std::vector<uint32_t> canon_key(nbs);      // (dir << 16 | i << 8 | j) in canonical order, per Elem at bs_off[e]
+    std::vector<uint64_t> elem_hash(ne, 0);
+    std::vector<uint32_t> elem_nU(ne, 0);
+    const unsigned n_threads = ne < 4096 ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<int> bad(n_threads, 0);
+    auto phase_a = [&](unsigned tid) {
+        std::vector<uint32_t> order;
+        // Elems are split so that every thread owns about the same number of basis specs
+        const uint32_t* off = v->bs_off;
+        const uint32_t e0 = (uint32_t)(std::lower_bound(off, off + ne, (uint32_t)((uint64_t)nbs * tid / n_threads)) - off);
+        const uint32_t e1 = tid + 1 == n_threads ? ne : (uint32_t)(std::lower_bound(off, off + ne, (uint32_t)((uint64_t)nbs * (tid + 1) / n_threads)) - off);
+        // counting placement over the (dir, i, j) key space: O(n + 2 (i_max+1) (j_max+1)) per Elem, no comparison sort
+        const uint32_t JS = v->j_max + 1, KS = 2 * (v->i_max + 1) * JS;
+        std::vector<int32_t> slot(KS, -1);
+        for (uint32_t e = e0; e < e1; e++) {
+            const uint32_t b = v->bs_off[e], n = v->bs_off[e + 1] - b;
+            if (n == 0) continue;
+            order.resize(n);   // packed (dir, i, j, position) keys in canonical order
+            bool ok = true, dup = false;
+            for (uint32_t k = 0; k < n; k++) {
+                const uint32_t dir = v->bs_dir[b + k], i = v->bs_i[b + k], j = v->bs_j[b + k];
+                if (dir > 1) { bad[tid] = 1; ok = false; break; }
+                if (v->bs_dof[b + k] >= v->n_dofs) { bad[tid] = 2; ok = false; break; }
+                if (i > v->i_max || j > v->j_max) { bad[tid] = 3; ok = false; break; }
+                int32_t& sl = slot[(dir * (v->i_max + 1) + i) * JS + j];
+                if (sl >= 0) dup = true;
+                sl = (int32_t)k;
+            }
+            if (!ok) { std::fill(slot.begin(), slot.end(), -1); continue; }
+            if (!dup) {
+                uint32_t w = 0;
+                for (uint32_t key = 0; key < KS && w < n; key++)
+                    if (slot[key] >= 0) {
+                        const uint32_t k = (uint32_t)slot[key];
+                        order[w++] = ((uint32_t)v->bs_dir[b + k] << 16 | (uint32_t)v->bs_i[b + k] << 8 | v->bs_j[b + k]) << 11 | k;
+                        slot[key] = -1;
+                    }
+            } else {   // repeated (dir, i, j) on one Elem (never produced by Domain::from_mesh): stable comparison sort keeps all of them
+                std::fill(slot.begin(), slot.end(), -1);
+                for (uint32_t k = 0; k < n; k++)
+                    order[k] = ((uint32_t)v->bs_dir[b + k] << 16 | (uint32_t)v->bs_i[b + k] << 8 | v->bs_j[b + k]) << 11 | k;
+                std::sort(order.begin(), order.end());
+            }
+            uint32_t nU = 0;
+            uint64_t h = 1469598103934665603ull;
+            for (uint32_t k = 0; k < n; k++) {
+                const uint32_t key = order[k] >> 11;
+                P.canon_dof[b + k] = v->bs_dof[b + (order[k] & 2047u)];
+                canon_key[b + k] = key;
+                nU += (key >> 16) == 0;
+                h = (h ^ key) * 0x9E3779B97F4A7C15ull; h ^= h >> 29;
+            }
+            elem_hash[e] = h; elem_nU[e] = nU;
+        }
+    };
+    if (n_threads == 1) phase_a(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < n_threads; t++) th.emplace_back(phase_a, t);
+        for (auto& t : th) t.join();
+    }
+    for (int bcode : bad) {
+        if (bcode == 1) { err = "bs_dir must be 0 (U) or 1 (V)"; return FEM2D_ERR_BAD_ARGUMENT; }
+        if (bcode == 2) { err = "bs_dof out of range"; return FEM2D_ERR_BAD_ARGUMENT; }
+        if (bcode == 3) { err = "basis-spec order exceeds i_max/j_max"; return FEM2D_ERR_BAD_ARGUMENT; }
+    }
     std::unordered_map<uint64_t, std::vector<uint32_t>> list_pool;   // hash -> candidate list ids
-    std::vector<uint32_t> order;
-    std::vector<uint8_t> tmp;
+    std::vector<uint32_t> list_first_elem;                          // an Elem that carries the list (for content comparison)
     for (uint32_t e = 0; e < ne; e++) {
         const uint32_t b = v->bs_off[e], n = v->bs_off[e + 1] - b;
-        if (v->bs_off[e + 1] < b) { err = "bs_off must be non-decreasing"; return FEM2D_ERR_BAD_ARGUMENT; }
         if (n == 0) continue;
-        order.resize(n);
-        std::iota(order.begin(), order.end(), 0u);
-        for (uint32_t k = 0; k < n; k++) {
-            if (v->bs_dir[b + k] > 1) { err = "bs_dir must be 0 (U) or 1 (V)"; return FEM2D_ERR_BAD_ARGUMENT; }
-            if (v->bs_dof[b + k] >= v->n_dofs) { err = "bs_dof out of range"; return FEM2D_ERR_BAD_ARGUMENT; }
-            if (v->bs_i[b + k] > v->i_max || v->bs_j[b + k] > v->j_max) { err = "basis-spec order exceeds i_max/j_max"; return FEM2D_ERR_BAD_ARGUMENT; }
-        }
-        std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-            const uint32_t kx = (uint32_t)v->bs_dir[b + x] << 16 | (uint32_t)v->bs_i[b + x] << 8 | v->bs_j[b + x];
-            const uint32_t ky = (uint32_t)v->bs_dir[b + y] << 16 | (uint32_t)v->bs_i[b + y] << 8 | v->bs_j[b + y];
-            return kx < ky;
-        });
-        tmp.resize(3 * (size_t)n);
-        uint32_t nU = 0;
-        for (uint32_t k = 0; k < n; k++) {
-            const uint32_t s = b + order[k];
-            P.canon_dof[b + k] = v->bs_dof[s];
-            tmp[3 * k] = v->bs_dir[s]; tmp[3 * k + 1] = v->bs_i[s]; tmp[3 * k + 2] = v->bs_j[s];
-            nU += v->bs_dir[s] == 0;
-        }
-        const uint64_t h = fnv1a(tmp.data(), tmp.size());
+        const uint32_t nU = elem_nU[e];
         uint32_t id = UINT32_MAX;
-        for (uint32_t cand : list_pool[h]) {
+        auto& cands = list_pool[elem_hash[e]];
+        for (uint32_t cand : cands) {
             const ListDesc& L = P.lists[cand];
             if (L.n != n || L.nU != nU) continue;
-            bool same = true;
-            for (uint32_t k = 0; k < n && same; k++) same = P.spec_i[L.off + k] == tmp[3 * k + 1] && P.spec_j[L.off + k] == tmp[3 * k + 2];
-            if (same) { id = cand; break; }
+            if (std::memcmp(&canon_key[v->bs_off[list_first_elem[cand]]], &canon_key[b], (size_t)n * 4) == 0) { id = cand; break; }
         }
         if (id == UINT32_MAX) {
             id = (uint32_t)P.lists.size();
             P.lists.push_back(ListDesc{(uint32_t)P.spec_i.size(), n, nU, 0});
-            for (uint32_t k = 0; k < n; k++) { P.spec_i.push_back(tmp[3 * k + 1]); P.spec_j.push_back(tmp[3 * k + 2]); }
-            list_pool[h].push_back(id);
+            list_first_elem.push_back(e);
+            for (uint32_t k = 0; k < n; k++) { P.spec_i.push_back((uint8_t)(canon_key[b + k] >> 8)); P.spec_j.push_back((uint8_t)canon_key[b + k]); }
+            cands.push_back(id);
         }
         P.elem_list[e] = id;
         P.max_list_n = std::max(P.max_list_n, n);
@@ -206,13 +263,18 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
     }
     if (P.n_values >= (1ull << 31) || P.n_pairs >= (1ull << 32)) { err = "domain too large for 32-bit source indices"; return FEM2D_ERR_UNSUPPORTED; }
 
-    // ---- work items: <= K2_THREADS micro-tiles each; largest classes first (longest-processing-time order)
+    // ---- work items: <= K2_ROUNDS * K2_THREADS micro-tiles each (balanced split); largest classes first (longest-processing-time order)
     std::vector<uint32_t> cls_order(P.classes.size());
     std::iota(cls_order.begin(), cls_order.end(), 0u);
     std::stable_sort(cls_order.begin(), cls_order.end(), [&](uint32_t a, uint32_t b) { return P.classes[a].n_mt > P.classes[b].n_mt; });
-    for (uint32_t c : cls_order)
-        for (uint32_t b = 0; b < P.classes[c].n_mt; b += K2_THREADS)
-            P.items.push_back(WorkItem{c, b, std::min<uint32_t>(K2_THREADS, P.classes[c].n_mt - b), 0});
+    for (uint32_t c : cls_order) {
+        const uint32_t n_mt = P.classes[c].n_mt, cap = K2_ROUNDS * K2_THREADS;
+        const uint32_t n_items = (n_mt + cap - 1) / cap;
+        for (uint32_t k = 0; k < n_items; k++) {   // equal shares, rounded up to whole warps
+            const uint32_t b = (uint32_t)((uint64_t)n_mt * k / n_items), e = (uint32_t)((uint64_t)n_mt * (k + 1) / n_items);
+            if (e > b) P.items.push_back(WorkItem{c, b, e - b, 0});
+        }
+    }
     return FEM2D_OK;
 }
 

@@ -17,6 +17,7 @@ namespace fem2d {
 constexpr int MT_P = 4;   // micro-tile: P functions (rows) per thread
 constexpr int MT_Q = 2;   // micro-tile: Q functions (cols) per thread
 constexpr int K2_THREADS = 256;
+constexpr int K2_ROUNDS = 2;    // a work item covers up to K2_ROUNDS * K2_THREADS micro-tiles of one class (slabs staged once)
 
 struct ClassDesc {
     double dxP, dyP, dxQ, dyQ;   // dx_du, dy_dv (element.rs:46-47) of P's Elem and of Q's Elem
@@ -45,7 +46,7 @@ struct TableDesc {
 struct WorkItem {
     uint32_t cls;
     uint32_t mt_begin;   // first micro-tile handled by this item
-    uint32_t mt_count;   // <= K2_THREADS
+    uint32_t mt_count;   // <= K2_ROUNDS * K2_THREADS
     uint32_t pad;
 };
 

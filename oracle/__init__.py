@@ -48,11 +48,11 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         L.orc_last_error.restype = C.c_char_p
         for name in ("orc_mesh_from_arrays", "orc_mesh_unit", "orc_mesh_clone", "orc_domain_from_mesh", "orc_domain_mesh",
-                     "orc_assemble"):
+                     "orc_assemble", "orc_assemble_elems"):
             getattr(L, name).restype = C.c_void_p
         for name in ("orc_mesh_num_elems", "orc_mesh_num_edges", "orc_mesh_num_nodes", "orc_mesh_descendant_elems",
                      "orc_mesh_ancestor_elems", "orc_domain_num_dofs", "orc_domain_num_basis_specs", "orc_gep_nnz",
-                     "orc_default_ngq", "orc_xy_fields"):
+                     "orc_default_ngq", "orc_xy_fields", "orc_elem_entries_size"):
             getattr(L, name).restype = C.c_int64
         _lib = L
     return _lib
@@ -380,6 +380,26 @@ def galerkin_sample_gep_hcurl(domain: Domain, glq_grid_dim=None, basis: int = HI
         return GEP(domain.num_dofs, rows, cols, a, b, float(t[0]), float(t[1]))
     finally:
         lib().orc_gep_free(g)
+
+
+def assemble_elems(domain: Domain, elem_ids, glq, basis: int = HIER_POLY):
+    """Per-Elem matrices (galerkin.rs:73-183 closure body) of the selected Elems, NOT merged: (elem, rows, cols, a, b)."""
+    (up, uw), (vp, vw) = glq
+    up, uw, vp, vw = [np.ascontiguousarray(x, dtype=np.float64) for x in (up, uw, vp, vw)]
+    ids = np.ascontiguousarray(elem_ids, dtype=np.int64)
+    h = lib().orc_assemble_elems(domain._h, basis, _p(up, C.c_double), _p(uw, C.c_double), C.c_int64(len(up)), _p(vp, C.c_double),
+                                 _p(vw, C.c_double), C.c_int64(len(vp)), _p(ids, C.c_int64), C.c_int64(len(ids)))
+    if not h:
+        raise OracleError(_err())
+    h = C.c_void_p(h)
+    try:
+        n = lib().orc_elem_entries_size(h)
+        el = np.zeros(n, dtype=np.int64); rows = np.zeros(n, dtype=np.uint32); cols = np.zeros(n, dtype=np.uint32)
+        a = np.zeros(n); b = np.zeros(n)
+        lib().orc_elem_entries_copy(h, _p(el, C.c_int64), _p(rows, C.c_uint32), _p(cols, C.c_uint32), _p(a, C.c_double), _p(b, C.c_double))
+        return el, rows, cols, a, b
+    finally:
+        lib().orc_elem_entries_free(h)
 
 
 def xy_fields(domain: Domain, densities, solution, basis: int = HIER_POLY):

@@ -1193,6 +1193,30 @@ static GEPResult galerkin_sample_gep_hcurl(const Domain& domain, int basis_kind,
     return res;
 }
 
+// Per-Elem matrices of selected Elems only (the closure body of galerkin.rs:73-183, not merged): used to spot-check
+// full-size GPU results without running the whole CPU assembly.
+struct ElemEntries { std::vector<int64_t> elem; std::vector<uint32_t> rows, cols; std::vector<double> a, b; };
+static ElemEntries assemble_elems(const Domain& domain, int basis_kind, const double* u_pts, const double* u_w, size_t nu, const double* v_pts,
+                                  const double* v_w, size_t nv, const int64_t* elem_ids, size_t n_ids) {
+    auto mo = domain.mesh.max_expansion_orders();
+    Sampler sampler;
+    sampler.domain = &domain; sampler.i_max = mo[0]; sampler.j_max = mo[1]; sampler.basis_kind = basis_kind;
+    sampler.u_points.assign(u_pts, u_pts + nu); sampler.v_points.assign(v_pts, v_pts + nv);
+    Integrator AI{std::vector<double>(u_w, u_w + nu), std::vector<double>(v_w, v_w + nv)};
+    Integrator BI = AI;
+    ElemEntries out;
+    for (size_t k = 0; k < n_ids; k++) {
+        SparseMatrix la{domain.n_dofs, {}}, lb{domain.n_dofs, {}};
+        elem_matrices(domain, sampler, AI, BI, domain.mesh.elems.at(elem_ids[k]), la, lb);
+        auto ib = lb.entries.begin();
+        for (auto& kv : la.entries) {
+            out.elem.push_back(elem_ids[k]); out.rows.push_back(kv.first[0]); out.cols.push_back(kv.first[1]);
+            out.a.push_back(kv.second); out.b.push_back(ib->second); ++ib;
+        }
+    }
+    return out;
+}
+
 // UniformFieldSpace::xy_fields fields.rs:63-127 (+ uniform_range :407-410)
 static void xy_fields(const Domain& domain, int basis_kind, size_t d0, size_t d1, const double* solution,
                       std::vector<int64_t>& leaf_ids, std::vector<double>& xv, std::vector<double>& yv) {
@@ -1388,6 +1412,20 @@ void orc_gep_copy(void* g, uint32_t* rows, uint32_t* cols, double* a, double* b)
     std::copy(r->a.begin(), r->a.end(), a); std::copy(r->b.begin(), r->b.end(), b);
 }
 void orc_gep_free(void* g) { delete (orc::GEPResult*)g; }
+
+void* orc_assemble_elems(void* d, int basis_kind, const double* u_pts, const double* u_w, int64_t nu, const double* v_pts, const double* v_w,
+                         int64_t nv, const int64_t* elem_ids, int64_t n_ids) {
+    ORC_TRY
+    return new orc::ElemEntries(orc::assemble_elems(*(orc::Domain*)d, basis_kind, u_pts, u_w, nu, v_pts, v_w, nv, elem_ids, n_ids));
+    ORC_CATCH(nullptr)
+}
+int64_t orc_elem_entries_size(void* e) { return ((orc::ElemEntries*)e)->rows.size(); }
+void orc_elem_entries_copy(void* e, int64_t* elem, uint32_t* rows, uint32_t* cols, double* a, double* b) {
+    auto* r = (orc::ElemEntries*)e;
+    std::copy(r->elem.begin(), r->elem.end(), elem); std::copy(r->rows.begin(), r->rows.end(), rows); std::copy(r->cols.begin(), r->cols.end(), cols);
+    std::copy(r->a.begin(), r->a.end(), a); std::copy(r->b.begin(), r->b.end(), b);
+}
+void orc_elem_entries_free(void* e) { delete (orc::ElemEntries*)e; }
 
 // xy_fields: returns number of leaves; outputs sized n_leaves * d0*d1 (caller passes capacity in leaves)
 int64_t orc_xy_fields(void* d, int basis_kind, int64_t d0, int64_t d1, const double* solution, int64_t cap_leaves, int64_t* leaf_ids,

@@ -1,0 +1,114 @@
+"""Full-size checks at BASELINE.json configs[2] (mesh_a, Orders(6,6), 6x global T: 1,178,112 DoFs), where the CPU oracle cannot
+run the whole assembly in test time: size-independent properties plus oracle spot checks of individual Elems."""
+import numpy as np
+import pytest
+
+import recipes
+
+pytestmark = pytest.mark.gpu
+
+import fem_2d_b200 as F  # noqa: E402
+import oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def full():
+    import torch
+    mf = recipes.mesh_cfg3(recipes.api("product"), levels=6, order=6)
+    df = F.Domain.from_mesh(mf)
+    glq = (F.gauss_quadrature_points(8), F.gauss_quadrature_points(8))
+    plan = F.Plan(df.view(), device=0, dedupe=True)
+    a = torch.empty(plan.nnz, dtype=torch.float64, device="cuda:0"); b = torch.empty_like(a)
+    plan.assemble_device(glq, a.data_ptr(), b.data_ptr())
+    torch.cuda.synchronize()
+    return dict(mesh=mf, domain=df, glq=glq, plan=plan, a=a, b=b)
+
+
+def test_sizes_match_closed_form(full):
+    info = full["plan"].info
+    assert full["domain"].num_dofs == 1178112            # SURVEY.md section 8 table, cfg 3
+    assert info["nnz_upper"] == 57557904 and info["n_pairs"] == 58240656
+    assert info["max_contrib"] == 2 and info["n_extra"] == 58240656 - 57557904
+
+
+def test_pattern_is_sorted_unique_upper_triangular(full):
+    rows, cols = full["plan"].pattern()
+    assert np.all(rows <= cols)
+    keys = rows.astype(np.int64) << 32 | cols.astype(np.int64)
+    assert np.all(np.diff(keys) > 0)
+    assert rows[0] == 0 and cols.max() == full["domain"].num_dofs - 1
+    # every DoF has its diagonal entry
+    assert np.count_nonzero(rows == cols) == full["domain"].num_dofs
+
+
+def test_dedupe_off_is_bit_identical(full):
+    import torch
+    plan = F.Plan(full["domain"].view(), device=0, dedupe=False)
+    assert plan.info["n_classes"] == plan.info["n_blocks"] == 16384
+    a = torch.empty_like(full["a"]); b = torch.empty_like(full["b"])
+    plan.assemble_device(full["glq"], a.data_ptr(), b.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(a.view(torch.int64), full["a"].view(torch.int64))
+    assert torch.equal(b.view(torch.int64), full["b"].view(torch.int64))
+
+
+def test_material_scaling_is_exact(full):
+    """A = (1/mu) * (...), B = eps * (...): scaling by powers of two is exact in IEEE arithmetic, whatever the mesh size."""
+    import torch
+    df = F.Domain.from_mesh(recipes.mesh_cfg3(recipes.api("product"), levels=6, order=6))
+    v = df.view()
+    v.element_eps_re *= 2.0
+    v.element_mu_re *= 4.0
+    plan = F.Plan(v, device=0)
+    a = torch.empty_like(full["a"]); b = torch.empty_like(full["b"])
+    plan.assemble_device(full["glq"], a.data_ptr(), b.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal((a * 4.0).view(torch.int64), full["a"].view(torch.int64))
+    assert torch.equal((b * 0.5).view(torch.int64), full["b"].view(torch.int64))
+
+
+def test_oracle_spot_check_of_single_elems(full):
+    """Per-Elem matrices of a few leaves (corner, edge, interior, last) from the oracle vs the GPU values at the same keys.
+    Keys between two Elem-type DoFs of one leaf receive exactly one contribution, so they must match bit for bit; all keys of
+    a leaf must match once the neighbours' contributions are added -- checked through the full sum for an interior leaf."""
+    mo = recipes.mesh_cfg3(recipes.api("oracle"), levels=6, order=6)
+    do = O.Domain.from_mesh(mo)
+    n_leaf0 = 21844 - 16384
+    ids = [n_leaf0, n_leaf0 + 1, n_leaf0 + 777, n_leaf0 + 8191, 21843]
+    el, r, c, a, b = O.assemble_elems(do, ids, full["glq"])
+    rows, cols = full["plan"].pattern()
+    keys = rows.astype(np.int64) << 32 | cols.astype(np.int64)
+    slot = np.searchsorted(keys, r.astype(np.int64) << 32 | c.astype(np.int64))
+    assert np.array_equal(keys[slot], r.astype(np.int64) << 32 | c.astype(np.int64))     # every oracle key exists in the pattern
+    ga = full["a"].cpu().numpy()[slot]; gb = full["b"].cpu().numpy()[slot]
+    n_elem_type = 16384 * 60                                                             # Elem-type DoFs are numbered first (domain.rs:83-96)
+    single = (r < n_elem_type) & (c < n_elem_type)
+    assert single.sum() == len(ids) * 60 * 61 // 2
+    assert np.array_equal(ga[single].view(np.uint64), a[single].view(np.uint64))
+    assert np.array_equal(gb[single].view(np.uint64), b[single].view(np.uint64))
+    # shared (edge-type) keys of one interior leaf: add the contributions of its four edge neighbours (<= 2 terms per key, so the
+    # order of the IEEE sum is immaterial) and compare every key of that leaf bit for bit
+    centre = n_leaf0 + 8191
+    neigh = set()
+    for e in mo.elem(centre).edges:
+        act = mo.edge(e)["active"]
+        assert centre in act
+        neigh.add(act[0] + act[1] - centre)
+    assert len(neigh) == 4
+    el, r, c, a, b = O.assemble_elems(do, [centre] + sorted(neigh), full["glq"])
+    k_all = r.astype(np.int64) << 32 | c.astype(np.int64)
+    mine = el == centre
+    tot_a, tot_b = {}, {}
+    for k, va, vb in zip(k_all[mine], a[mine], b[mine]):
+        tot_a[k] = va; tot_b[k] = vb
+    n_two = 0
+    for k, va, vb in zip(k_all[~mine], a[~mine], b[~mine]):
+        if k in tot_a:
+            tot_a[k] = tot_a[k] + va; tot_b[k] = tot_b[k] + vb; n_two += 1
+    assert n_two == 4 * 21                                                               # 6 edge functions per shared edge: 6*7/2 keys
+    kk = np.array(sorted(tot_a), dtype=np.int64)
+    slot = np.searchsorted(keys, kk)
+    assert np.array_equal(keys[slot], kk)
+    ref_a = np.array([tot_a[k] for k in kk]); ref_b = np.array([tot_b[k] for k in kk])
+    assert np.array_equal(full["a"].cpu().numpy()[slot].view(np.uint64), ref_a.view(np.uint64))
+    assert np.array_equal(full["b"].cpu().numpy()[slot].view(np.uint64), ref_b.view(np.uint64))
