@@ -109,6 +109,7 @@ int device_symbolic(Plan& P, std::string& err) {
     if ((st = upload(P.d_spec_i, H.spec_i.data(), H.spec_i.size(), err))) return st;
     if ((st = upload(P.d_spec_j, H.spec_j.data(), H.spec_j.size(), err))) return st;
     if ((st = upload(P.d_tables, H.tables.data(), H.tables.size(), err))) return st;
+    if ((st = upload(P.d_grams, H.grams.data(), H.grams.size(), err))) return st;
     if ((st = upload(P.d_items, H.items.data(), H.items.size(), err))) return st;
 
     const uint32_t np = (uint32_t)H.n_pairs;
@@ -195,9 +196,9 @@ int device_row_block_bounds(const Plan& P, uint32_t world, uint64_t* bounds, std
 void device_plan_release(Plan& P) {
     if (P.device < 0) return;
     cudaSetDevice(P.device);
-    cudaFree(P.d_classes); cudaFree(P.d_lists); cudaFree(P.d_spec_i); cudaFree(P.d_spec_j); cudaFree(P.d_tables); cudaFree(P.d_items);
+    cudaFree(P.d_classes); cudaFree(P.d_lists); cudaFree(P.d_spec_i); cudaFree(P.d_spec_j); cudaFree(P.d_tables); cudaFree(P.d_grams); cudaFree(P.d_items);
     cudaFree(P.d_rows); cudaFree(P.d_cols); cudaFree(P.d_src1); cudaFree(P.d_extra_slot); cudaFree(P.d_extra_src);
-    cudaFree(P.d_V); cudaFree(P.d_tabs); cudaFree(P.d_glq); cudaFree(P.d_gram); cudaFree(P.d_out_a); cudaFree(P.d_out_b);
+    cudaFree(P.d_V); cudaFree(P.d_tabs); cudaFree(P.d_glq); cudaFree(P.d_gram); cudaFree(P.d_dmma_items); cudaFree(P.d_out_a); cudaFree(P.d_out_b);
     for (int r = 0; r < Plan::RING; r++) for (int k = 0; k < 4; k++) if (P.ev[r][k]) cudaEventDestroy(P.ev[r][k]);
 }
 

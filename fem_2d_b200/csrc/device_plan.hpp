@@ -23,6 +23,7 @@ struct Plan {
     uint8_t* d_spec_i = nullptr;
     uint8_t* d_spec_j = nullptr;
     TableDesc* d_tables = nullptr;
+    GramDesc* d_grams = nullptr;
     WorkItem* d_items = nullptr;
     uint32_t* d_rows = nullptr;
     uint32_t* d_cols = nullptr;
@@ -36,6 +37,8 @@ struct Plan {
     size_t tabs_capacity = 0;   // doubles
     double* d_glq = nullptr;    // u_pts[64] u_w[64] v_pts[64] v_w[64]
     double* d_gram = nullptr;   // fast modes scratch
+    void* d_dmma_items = nullptr;   // tile work items of the DMMA integrator (built on first use)
+    uint32_t n_dmma_items = 0;
     size_t gram_capacity = 0;
     double* d_out_a = nullptr;  // staging for host-output calls
     double* d_out_b = nullptr;

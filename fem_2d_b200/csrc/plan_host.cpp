@@ -206,6 +206,17 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
     table_id(1.0, 0.0, 0, 1);
     table_id(1.0, 0.0, 1, 1);
 
+    std::unordered_map<uint64_t, uint32_t> gram_pool;
+    auto gram_id = [&](uint32_t tp, uint32_t tq, uint32_t axis) {
+        const uint64_t k = (uint64_t)tp << 33 | (uint64_t)tq << 1 | axis;
+        auto it = gram_pool.find(k);
+        if (it != gram_pool.end()) return it->second;
+        const uint32_t id = (uint32_t)P.grams.size();
+        P.grams.push_back(GramDesc{tp, tq, axis, 0});
+        gram_pool.emplace(k, id);
+        return id;
+    };
+
     // ---- blocks and classes.  Block order: for every Elem d (ascending) its local block, then its blocks with each
     // ancestor that carries functions (nearest ancestor first).
     std::unordered_map<ClassKey, uint32_t, ClassKeyHash> class_pool;
@@ -248,6 +259,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
                 c.tabPu = local ? 0u : table_id(su, ou, 0, 0);
                 c.tabPv = local ? 1u : table_id(sv, ov, 1, 0);
                 c.tabQu = 0; c.tabQv = 1;
+                c.gramU = gram_id(c.tabPu, c.tabQu, 0); c.gramV = gram_id(c.tabPv, c.tabQv, 1);
                 c.v_off = P.n_values;
                 const ListDesc& LP = P.lists[c.listP]; const ListDesc& LQ = P.lists[c.listQ];
                 P.n_values += (uint64_t)LP.n * LQ.n;

@@ -19,6 +19,7 @@ struct HostPlan {
     std::vector<ListDesc> lists;
     std::vector<uint8_t> spec_i, spec_j;
     std::vector<TableDesc> tables;
+    std::vector<GramDesc> grams;
     std::vector<ClassDesc> classes;
     std::vector<BlockDesc> blocks;
     std::vector<WorkItem> items;

@@ -28,6 +28,7 @@ struct ClassDesc {
     uint32_t tabPu, tabPv, tabQu, tabQv;
     uint32_t local;              // 1: d == e (symmetric block, only a <= b is consumed)
     uint32_t n_mt;               // micro-tiles in this class
+    uint32_t gramU, gramV;       // ids of the (tabPu,tabQu) / (tabPv,tabQv) 1-D Gram sets (re-ordered modes only)
 };
 
 struct ListDesc {
@@ -41,6 +42,11 @@ struct TableDesc {
     double s, o;        // point map x' = x*s + o (glq.rs:238-249)
     uint32_t axis;      // 0: u (orders up to i_max, nu points), 1: v (j_max, nv points)
     uint32_t identity;  // 1: unscaled points (no arithmetic applied, basis.rs:375,392)
+};
+
+struct GramDesc {
+    uint32_t tabP, tabQ;   // tables of the P side and of the Q side on one axis
+    uint32_t axis, pad;
 };
 
 struct WorkItem {

@@ -88,12 +88,14 @@ def test_oracle_spot_check_of_single_elems(full):
     assert np.array_equal(gb[single].view(np.uint64), b[single].view(np.uint64))
     # shared (edge-type) keys of one interior leaf: add the contributions of its four edge neighbours (<= 2 terms per key, so the
     # order of the IEEE sum is immaterial) and compare every key of that leaf bit for bit
-    centre = n_leaf0 + 8191
-    neigh = set()
-    for e in mo.elem(centre).edges:
-        act = mo.edge(e)["active"]
-        assert centre in act
-        neigh.add(act[0] + act[1] - centre)
+    centre = None
+    for cand in range(n_leaf0 + 8191, 21844):      # first leaf from the middle of the id range whose four edges are all interior
+        acts = [mo.edge(e)["active"] for e in mo.elem(cand).edges]
+        if all(cand in a for a in acts):
+            centre = cand
+            break
+    assert centre is not None
+    neigh = {a[0] + a[1] - centre for a in acts}
     assert len(neigh) == 4
     el, r, c, a, b = O.assemble_elems(do, [centre] + sorted(neigh), full["glq"])
     k_all = r.astype(np.int64) << 32 | c.astype(np.int64)
