@@ -690,3 +690,52 @@ def host_alloc(nbytes: int) -> int:
 
 def host_free(ptr: int) -> None:
     _L.fem2d_host_free(C.c_void_p(ptr))
+
+
+# ---- caller-side "next" row: field evaluation (fields.rs) ------------------------------------------------------------------------------
+class UniformFieldError(Exception):
+    """fields.rs:412-433"""
+
+
+class UniformFieldSpace:
+    """Mirror of UniformFieldSpace (fields.rs:17-22): field quantities on a uniform grid over every leaf Elem.
+    `xy_fields` runs on the GPU (fem2d_xy_fields); quantities are dicts {leaf elem id: ndarray[d][d]}."""
+
+    def __init__(self, domain: Domain, densities):
+        if densities[0] != densities[1]:
+            # the reference allocates [densities[1]][densities[0]] but indexes [m < d0][n < d1] (fields.rs:83-84,102-112)
+            raise UniformFieldError("non-square densities index out of bounds in the reference; only square grids are supported")
+        self.domain = domain
+        self.densities = list(densities)
+        self.quantities = {}
+
+    def xy_fields(self, vector_name: str, solution, basis=HierPoly, device: int = 0):
+        """fields.rs:63-127: returns [f"{vector_name}_x", f"{vector_name}_y"]."""
+        sol = np.ascontiguousarray(solution, dtype=np.float64)
+        if len(sol) != self.domain.num_dofs:
+            raise UniformFieldError(f"Domain size ({self.domain.num_dofs}) does not match solution size ({len(sol)})!")
+        d = self.densities[0]
+        cap = self.domain.mesh.num_elems
+        ids = np.zeros(cap, dtype=np.uint32)
+        x = np.zeros((cap, d, d)); y = np.zeros((cap, d, d))
+        n = C.c_uint64()
+        _ck(_L.fem2d_xy_fields(C.byref(self.domain.view().c), int(device), basis.kind, C.c_uint32(d), _p(sol, C.c_double), C.c_uint64(cap),
+                               C.byref(n), _p(ids, C.c_uint32), _p(x, C.c_double), _p(y, C.c_double)))
+        n = n.value
+        xn, yn = f"{vector_name}_x", f"{vector_name}_y"
+        self.quantities[xn] = {int(ids[k]): x[k] for k in range(n)}
+        self.quantities[yn] = {int(ids[k]): y[k] for k in range(n)}
+        return [xn, yn]
+
+    def map_to_quantity(self, name: str, result_name: str, operator) -> None:           # fields.rs:256-279
+        if name not in self.quantities:
+            raise UniformFieldError(f"Missing quantity '{name}', Cannot apply operation!")
+        self.quantities[result_name] = {e: np.vectorize(operator)(v) for e, v in self.quantities[name].items()}
+
+    def expression_2arg(self, operand_names, result_name: str, expression) -> None:      # fields.rs:301-339
+        a, b = operand_names
+        for nm in (a, b):
+            if nm not in self.quantities:
+                raise UniformFieldError(f"Missing quantity '{nm}', Cannot apply operation!")
+        qa, qb = self.quantities[a], self.quantities[b]
+        self.quantities[result_name] = {e: np.vectorize(expression)(qa[e], qb[e]) for e in qa}

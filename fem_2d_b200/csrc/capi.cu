@@ -175,16 +175,21 @@ int fem2d_assemble_device(fem2d_plan* plan, int basis_kind, int a_kind, int b_ki
     std::memset(h_glq, 0, sizeof(h_glq));
     std::copy(u_pts, u_pts + nu, h_glq); std::copy(u_w, u_w + nu, h_glq + 128);
     std::copy(v_pts, v_pts + nv, h_glq + 256); std::copy(v_w, v_w + nv, h_glq + 384);
-    CKS(cudaMemcpyAsync(p.d_glq, h_glq, sizeof(h_glq), cudaMemcpyHostToDevice, s));
+    // the nodes/weights stay resident on the device: re-upload only when the caller passes different values
+    if (!p.glq_valid || std::memcmp(p.h_glq, h_glq, sizeof(h_glq)) != 0) {
+        std::memcpy(p.h_glq, h_glq, sizeof(h_glq));
+        CKS(cudaMemcpyAsync(p.d_glq, p.h_glq, sizeof(h_glq), cudaMemcpyHostToDevice, s));
+        p.glq_valid = true;
+    }
     const uint32_t NO = std::max(p.host.i_max, p.host.j_max) + 1, NPT = std::max(nu, nv);
     const size_t tabs_need = p.host.tables.size() * 4 * (size_t)NO * NPT;
     if (tabs_need > p.tabs_capacity) {
         CKS(cudaStreamSynchronize(s));
-        cudaFree(p.d_tabs); p.d_tabs = nullptr; p.tabs_capacity = 0;
-        CKS(cudaMalloc((void**)&p.d_tabs, tabs_need * sizeof(double)));
+        fem2d::dev_free(p.d_tabs, s); p.d_tabs = nullptr; p.tabs_capacity = 0;
+        CKS(fem2d::dev_malloc((void**)&p.d_tabs, tabs_need * sizeof(double), s));
         p.tabs_capacity = tabs_need;
     }
-    if (!p.d_V) CKS(cudaMalloc((void**)&p.d_V, std::max<uint64_t>(p.host.n_values, 1) * sizeof(double2)));
+    if (!p.d_V) CKS(fem2d::dev_malloc((void**)&p.d_V, std::max<uint64_t>(p.host.n_values, 1) * sizeof(double2), s));
     for (int k = 0; k < 4; k++) p.last_launches[k] = 0;
     cudaEvent_t* ev = p.ev[p.n_calls % fem2d::Plan::RING];
     CKS(cudaEventRecord(ev[0], s));
@@ -230,8 +235,8 @@ int fem2d_assemble_range(fem2d_plan* plan, int basis_kind, int a_kind, int b_kin
     if (slot_begin > slot_end) return fail(FEM2D_ERR_BAD_ARGUMENT, "slot_begin > slot_end");
     CKS(cudaSetDevice(p.device));
     const size_t bytes = std::max<uint64_t>(p.nnz, 1) * sizeof(double);
-    if (!p.d_out_a) CKS(cudaMalloc((void**)&p.d_out_a, bytes));
-    if (!p.d_out_b) CKS(cudaMalloc((void**)&p.d_out_b, bytes));
+    if (!p.d_out_a) CKS(fem2d::dev_malloc((void**)&p.d_out_a, bytes));
+    if (!p.d_out_b) CKS(fem2d::dev_malloc((void**)&p.d_out_b, bytes));
     st = fem2d_assemble_device(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, slot_begin, slot_end, p.d_out_a, p.d_out_b, nullptr);
     if (st != FEM2D_OK) return st;
     // D2H of the slice of both value arrays (outputs are indexed from slot_begin); the pattern rides along when requested

@@ -50,14 +50,18 @@ __global__ void head_flags_kernel(const unsigned long long* __restrict__ keys, u
 __global__ void emit_pattern_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ srcs,
                                     const uint32_t* __restrict__ head, const uint32_t* __restrict__ scan, uint32_t n,
                                     uint32_t* __restrict__ rows, uint32_t* __restrict__ cols, uint32_t* __restrict__ src1,
-                                    uint32_t* __restrict__ extra_slot, uint32_t* __restrict__ extra_src) {
+                                    uint32_t* __restrict__ extra_slot, uint32_t* __restrict__ extra_src, uint32_t* __restrict__ extra_first) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t slot = scan[i] - 1;
     if (head[i]) {
         rows[slot] = (uint32_t)(keys[i] >> 32);
         cols[slot] = (uint32_t)keys[i];
-        src1[slot] = srcs[i];
+        if (i + 1 < n && !head[i + 1]) {   // key with more than one contribution: point at its run in the extras arrays
+            const uint32_t k = i - slot;   // rank of element i+1 among the non-heads
+            src1[slot] = 0x80000000u | k;
+            extra_first[k] = srcs[i];
+        } else src1[slot] = srcs[i];
     } else {
         const uint32_t k = i - slot - 1;
         extra_slot[k] = slot;
@@ -91,16 +95,28 @@ template <class T>
 int upload(T*& dst, const T* src, size_t n, std::string& err) {
     dst = nullptr;
     if (n == 0) n = 1;
-    CK(cudaMalloc((void**)&dst, n * sizeof(T)));
+    CK(fem2d::dev_malloc((void**)&dst, n * sizeof(T)));
     if (src) CK(cudaMemcpy(dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
     return FEM2D_OK;
 }
 
 }  // namespace
 
+void dev_pool_init(int device) {
+    static bool done[64] = {};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[device] = true;
+}
+
 int device_symbolic(Plan& P, std::string& err) {
     const HostPlan& H = P.host;
     CK(cudaSetDevice(P.device));
+    dev_pool_init(P.device);
     CK(cudaDeviceGetAttribute(&P.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, P.device));
     CK(cudaDeviceGetAttribute(&P.sm_count, cudaDevAttrMultiProcessorCount, P.device));
     int st;
@@ -124,14 +140,14 @@ int device_symbolic(Plan& P, std::string& err) {
     uint32_t *d_srcs = nullptr, *d_srcs2 = nullptr, *d_head = nullptr, *d_scan = nullptr, *d_stats = nullptr;
     void* d_temp = nullptr;
     auto cleanup = [&]() {
-        cudaFree(d_blocks); cudaFree(d_canon); cudaFree(d_keys); cudaFree(d_keys2); cudaFree(d_srcs); cudaFree(d_srcs2);
-        cudaFree(d_head); cudaFree(d_scan); cudaFree(d_stats); cudaFree(d_temp);
+        fem2d::dev_free(d_blocks); fem2d::dev_free(d_canon); fem2d::dev_free(d_keys); fem2d::dev_free(d_keys2); fem2d::dev_free(d_srcs); fem2d::dev_free(d_srcs2);
+        fem2d::dev_free(d_head); fem2d::dev_free(d_scan); fem2d::dev_free(d_stats); fem2d::dev_free(d_temp);
     };
 #define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); cleanup(); return FEM2D_ERR_CUDA; } } while (0)
     if ((st = upload(d_blocks, hb.data(), hb.size(), err))) { cleanup(); return st; }
     if ((st = upload(d_canon, H.canon_dof.data(), H.canon_dof.size(), err))) { cleanup(); return st; }
-    CKC(cudaMalloc((void**)&d_keys, (size_t)np * 8)); CKC(cudaMalloc((void**)&d_keys2, (size_t)np * 8));
-    CKC(cudaMalloc((void**)&d_srcs, (size_t)np * 4)); CKC(cudaMalloc((void**)&d_srcs2, (size_t)np * 4));
+    CKC(fem2d::dev_malloc((void**)&d_keys, (size_t)np * 8)); CKC(fem2d::dev_malloc((void**)&d_keys2, (size_t)np * 8));
+    CKC(fem2d::dev_malloc((void**)&d_srcs, (size_t)np * 4)); CKC(fem2d::dev_malloc((void**)&d_srcs2, (size_t)np * 4));
     keygen_kernel<<<(unsigned)hb.size(), 256>>>(d_blocks, d_canon, d_keys, d_srcs);
     CKC(cudaGetLastError());
 
@@ -144,14 +160,14 @@ int device_symbolic(Plan& P, std::string& err) {
     size_t scan_bytes = 0;
     CKC(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, d_head, d_scan, (int)np));
     temp_bytes = std::max(temp_bytes, scan_bytes);
-    CKC(cudaMalloc(&d_temp, temp_bytes ? temp_bytes : 1));
+    CKC(fem2d::dev_malloc(&d_temp, temp_bytes ? temp_bytes : 1));
     // keys use [row << 32 | col]: sort low 'bits' of col, then low 'bits' of row.  Two passes keep the bit count minimal.
     CKC(cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, kb, vb, (int)np, 0, bits));
     CKC(cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, kb, vb, (int)np, 32, 32 + bits));
     const unsigned long long* keys_sorted = kb.Current();
     const uint32_t* srcs_sorted = vb.Current();
 
-    CKC(cudaMalloc((void**)&d_head, (size_t)np * 4)); CKC(cudaMalloc((void**)&d_scan, (size_t)np * 4));
+    CKC(fem2d::dev_malloc((void**)&d_head, (size_t)np * 4)); CKC(fem2d::dev_malloc((void**)&d_scan, (size_t)np * 4));
     const unsigned gb = (np + 255) / 256;
     head_flags_kernel<<<gb, 256>>>(keys_sorted, np, d_head);
     CKC(cudaGetLastError());
@@ -159,13 +175,14 @@ int device_symbolic(Plan& P, std::string& err) {
     uint32_t nnz32 = 0;
     CKC(cudaMemcpy(&nnz32, d_scan + (np - 1), 4, cudaMemcpyDeviceToHost));
     P.nnz = nnz32; P.n_extra = (uint64_t)np - nnz32;
-    CKC(cudaMalloc((void**)&P.d_rows, (size_t)nnz32 * 4)); CKC(cudaMalloc((void**)&P.d_cols, (size_t)nnz32 * 4));
-    CKC(cudaMalloc((void**)&P.d_src1, (size_t)nnz32 * 4));
-    CKC(cudaMalloc((void**)&P.d_extra_slot, (P.n_extra ? P.n_extra : 1) * 4)); CKC(cudaMalloc((void**)&P.d_extra_src, (P.n_extra ? P.n_extra : 1) * 4));
-    emit_pattern_kernel<<<gb, 256>>>(keys_sorted, srcs_sorted, d_head, d_scan, np, P.d_rows, P.d_cols, P.d_src1, P.d_extra_slot, P.d_extra_src);
+    CKC(fem2d::dev_malloc((void**)&P.d_rows, (size_t)nnz32 * 4)); CKC(fem2d::dev_malloc((void**)&P.d_cols, (size_t)nnz32 * 4));
+    CKC(fem2d::dev_malloc((void**)&P.d_src1, (size_t)nnz32 * 4));
+    CKC(fem2d::dev_malloc((void**)&P.d_extra_slot, (P.n_extra ? P.n_extra : 1) * 4)); CKC(fem2d::dev_malloc((void**)&P.d_extra_src, (P.n_extra ? P.n_extra : 1) * 4));
+    CKC(fem2d::dev_malloc((void**)&P.d_extra_first, (P.n_extra ? P.n_extra : 1) * 4));
+    emit_pattern_kernel<<<gb, 256>>>(keys_sorted, srcs_sorted, d_head, d_scan, np, P.d_rows, P.d_cols, P.d_src1, P.d_extra_slot, P.d_extra_src, P.d_extra_first);
     CKC(cudaGetLastError());
     uint32_t stats[2] = {1, 0};
-    CKC(cudaMalloc((void**)&d_stats, 8));
+    CKC(fem2d::dev_malloc((void**)&d_stats, 8));
     CKC(cudaMemcpy(d_stats, stats, 8, cudaMemcpyHostToDevice));
     if (P.n_extra) {
         contrib_stats_kernel<<<(unsigned)((P.n_extra + 255) / 256), 256>>>(P.d_extra_slot, (uint32_t)P.n_extra, d_stats);
@@ -177,7 +194,7 @@ int device_symbolic(Plan& P, std::string& err) {
     cleanup();
 #undef CKC
     for (int r = 0; r < Plan::RING; r++) for (int k = 0; k < 4; k++) CK(cudaEventCreate(&P.ev[r][k]));
-    CK(cudaMalloc((void**)&P.d_glq, 4 * 128 * sizeof(double)));
+    CK(fem2d::dev_malloc((void**)&P.d_glq, 4 * 128 * sizeof(double)));
     return FEM2D_OK;
 }
 
@@ -185,10 +202,10 @@ int device_row_block_bounds(const Plan& P, uint32_t world, uint64_t* bounds, std
     if (world == 0 || world > 1023) { err = "world out of range"; return FEM2D_ERR_BAD_ARGUMENT; }
     CK(cudaSetDevice(P.device));
     unsigned long long* d_b = nullptr;
-    CK(cudaMalloc((void**)&d_b, (world + 1) * 8));
+    CK(fem2d::dev_malloc((void**)&d_b, (world + 1) * 8));
     row_bounds_kernel<<<1, 1024>>>(P.d_rows, P.nnz, world, d_b);
     cudaError_t e = cudaMemcpy(bounds, d_b, (world + 1) * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d_b);
+    fem2d::dev_free(d_b);
     if (e != cudaSuccess) { err = cudaGetErrorString(e); return FEM2D_ERR_CUDA; }
     return FEM2D_OK;
 }
@@ -196,9 +213,10 @@ int device_row_block_bounds(const Plan& P, uint32_t world, uint64_t* bounds, std
 void device_plan_release(Plan& P) {
     if (P.device < 0) return;
     cudaSetDevice(P.device);
-    cudaFree(P.d_classes); cudaFree(P.d_lists); cudaFree(P.d_spec_i); cudaFree(P.d_spec_j); cudaFree(P.d_tables); cudaFree(P.d_grams); cudaFree(P.d_items);
-    cudaFree(P.d_rows); cudaFree(P.d_cols); cudaFree(P.d_src1); cudaFree(P.d_extra_slot); cudaFree(P.d_extra_src);
-    cudaFree(P.d_V); cudaFree(P.d_tabs); cudaFree(P.d_glq); cudaFree(P.d_gram); cudaFree(P.d_dmma_items); cudaFree(P.d_out_a); cudaFree(P.d_out_b);
+    cudaDeviceSynchronize();   // numeric work may still be in flight on a caller stream
+    fem2d::dev_free(P.d_classes); fem2d::dev_free(P.d_lists); fem2d::dev_free(P.d_spec_i); fem2d::dev_free(P.d_spec_j); fem2d::dev_free(P.d_tables); fem2d::dev_free(P.d_grams); fem2d::dev_free(P.d_items);
+    fem2d::dev_free(P.d_rows); fem2d::dev_free(P.d_cols); fem2d::dev_free(P.d_src1); fem2d::dev_free(P.d_extra_slot); fem2d::dev_free(P.d_extra_src); fem2d::dev_free(P.d_extra_first);
+    fem2d::dev_free(P.d_V); fem2d::dev_free(P.d_tabs); fem2d::dev_free(P.d_glq); fem2d::dev_free(P.d_gram); fem2d::dev_free(P.d_dmma_items); fem2d::dev_free(P.d_out_a); fem2d::dev_free(P.d_out_b);
     for (int r = 0; r < Plan::RING; r++) for (int k = 0; k < 4; k++) if (P.ev[r][k]) cudaEventDestroy(P.ev[r][k]);
 }
 

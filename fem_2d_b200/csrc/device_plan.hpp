@@ -30,12 +30,15 @@ struct Plan {
     uint32_t* d_src1 = nullptr;
     uint32_t* d_extra_slot = nullptr;
     uint32_t* d_extra_src = nullptr;
+    uint32_t* d_extra_first = nullptr;   // first contribution of a multi-contribution slot, stored at the head of its extras run
 
     // numeric scratch (allocated lazily, reused across calls)
     double2* d_V = nullptr;
     double* d_tabs = nullptr;
     size_t tabs_capacity = 0;   // doubles
-    double* d_glq = nullptr;    // u_pts[64] u_w[64] v_pts[64] v_w[64]
+    double* d_glq = nullptr;    // u_pts[128] u_w[128] v_pts[128] v_w[128]
+    double h_glq[512] = {};     // host copy of what d_glq holds (skips the upload when the caller passes the same nodes again)
+    bool glq_valid = false;
     double* d_gram = nullptr;   // fast modes scratch
     void* d_dmma_items = nullptr;   // tile work items of the DMMA integrator (built on first use)
     uint32_t n_dmma_items = 0;
@@ -50,6 +53,12 @@ struct Plan {
     int max_smem_optin = 0;
     int sm_count = 0;
 };
+
+// Device memory comes from the stream-ordered pool of the device (cudaMallocAsync) with an unlimited release threshold, so the
+// symbolic phase of a repeated one-shot call re-uses its ~1.5 GB of scratch instead of paying cudaMalloc / cudaFree every time.
+inline cudaError_t dev_malloc(void** p, size_t bytes, cudaStream_t st = nullptr) { return cudaMallocAsync(p, bytes ? bytes : 1, st); }
+inline void dev_free(void* p, cudaStream_t st = nullptr) { if (p) cudaFreeAsync(p, st); }
+void dev_pool_init(int device);
 
 constexpr uint32_t MAX_GLQ = 128;   // default_ngq(20) = 128 (basis.rs:172-177)
 

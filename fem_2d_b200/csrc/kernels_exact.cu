@@ -17,6 +17,7 @@
 // contracts a 4 x 2 register tile of pairs over the points in strict (m outer, n inner) order.
 #include <cuda_runtime.h>
 
+#include "basis_device.cuh"
 #include "device_plan.hpp"
 
 namespace fem2d {
@@ -24,15 +25,6 @@ namespace fem2d {
 namespace {
 
 // ---------------------------------------------------------------------------------------------------------------- K1
-// HierMaxOrtho constants, verbatim incl. apparent typos (hierarchical_basis_fns.rs:206-225).
-__constant__ double c_euc_norm[12] = {0.968246, 2.561738, 0.838525, 4.248161, 0.816397, 5.882766, 0.808509, 1.0, 1.0, 1.0, 1.0, 1.0};
-__constant__ int c_q_num[12][14] = {
-    {-1, 0, 1}, {0, -3, 0, 3}, {-1, 0, -5, 0, 6}, {0, -3, 0, -7, 0, 10}, {-1, 0, -5, 0, -9, 0, 15},
-    {0, -3, 0, -7, 0, -11, 0, 21}, {-1, 0, -5, 0, -9, 0, -13, 0, 28}, {0, -3, 0, -7, 0, -11, 0, -15, 0, 36},
-    {-1, 0, -5, 0, -9, 0, -13, 0, -17, 0, 40}, {0, -3, 0, -7, 0, -11, 0, -15, 0, -19, 0, 55},
-    {-1, 0, -5, 0, -9, 0, -13, 0, -17, 0, -21, 0, 66}, {0, -3, 0, -7, 0, -11, 0, -15, 0, -19, 0, -23, 0, 72}};
-__constant__ int c_q_den[12] = {1, 3, 6, 10, 15, 21, 28, 36, 40, 55, 66, 72};
-
 // One CTA per table, one thread per point.  Output layout: out[((arr * NO) + order) * NPT + point], arr: 0 N, 1 N', 2 T, 3 T'.
 __global__ void k1_tables_kernel(const TableDesc* __restrict__ tabs, double* __restrict__ out, uint32_t NO, uint32_t NPT,
                                  const double* __restrict__ glq, uint32_t nu, uint32_t nv, uint32_t i_max, uint32_t j_max, int basis) {
@@ -43,51 +35,7 @@ __global__ void k1_tables_kernel(const TableDesc* __restrict__ tabs, double* __r
     for (uint32_t p = threadIdx.x; p < np; p += blockDim.x) {
         // RBS ancestor -> descendant point map (basis.rs:372-393, glq.rs:238-249)
         const double x = t.identity ? pts[p] : pts[p] * t.s + t.o;
-        auto N = [&](uint32_t n) -> double& { return o[(0 * NO + n) * NPT + p]; };
-        auto Nd = [&](uint32_t n) -> double& { return o[(1 * NO + n) * NPT + p]; };
-        auto T = [&](uint32_t n) -> double& { return o[(2 * NO + n) * NPT + p]; };
-        auto Td = [&](uint32_t n) -> double& { return o[(3 * NO + n) * NPT + p]; };
-        if (basis == FEM2D_BASIS_HIER_POLY) {   // HierPoly::new_without_d2, hierarchical_basis_fns.rs:102-162
-            double pw_prev = 1.0;
-            for (uint32_t n = 0; n <= nmax; n++) {
-                if (n == 0) { T(0) = 1.0 - x; Td(0) = -1.0; N(0) = 1.0; Nd(0) = 0.0; pw_prev = 1.0; }
-                else if (n == 1) { T(1) = 1.0 + x; Td(1) = 1.0; N(1) = x; Nd(1) = 1.0; pw_prev = x; }
-                else {
-                    const double pw = pw_prev * x;
-                    const double d1 = (double)n * pw_prev;
-                    N(n) = pw; Nd(n) = d1;
-                    if (n % 2 == 0) { T(n) = pw - 1.0; Td(n) = d1; }
-                    else { T(n) = pw - x; Td(n) = d1 - 1.0; }
-                    pw_prev = pw;
-                }
-            }
-        } else {   // HierMaxOrtho: LegendrePoly (:425-463) + QFunction (:316-352, :593-621)
-            double L[21], Ld[21];
-            for (uint32_t i = 0; i <= nmax; i++) {
-                const double i_f = (double)i;
-                if (i == 0) { L[0] = 1.0; Ld[0] = 0.0; }
-                else if (i == 1) { L[1] = x; Ld[1] = 1.0; }
-                else {
-                    L[i] = ((2.0 * i_f - 1.0) * x * L[i - 1] - (i_f - 1.0) * L[i - 2]) / i_f;
-                    Ld[i] = i_f * L[i - 1] + x * Ld[i - 1];
-                }
-                N(i) = L[i]; Nd(i) = Ld[i];
-            }
-            for (uint32_t i = 0; i <= nmax; i++) {
-                if (i == 0) { T(0) = 1.0 - x; Td(0) = -1.0; }
-                else if (i == 1) { T(1) = 1.0 + x; Td(1) = 1.0; }
-                else {
-                    double sv = 0.0, sp = 0.0;
-                    for (uint32_t k = 0; k <= i; k++) {
-                        const double w = ((double)c_q_num[i - 2][k]) / ((double)c_q_den[i - 2]);
-                        sv += w * L[k];
-                        sp += w * Ld[k];
-                    }
-                    T(i) = sv * c_euc_norm[i - 2];
-                    Td(i) = sp * c_euc_norm[i - 2];
-                }
-            }
-        }
+        basis_at_point(basis, nmax, x, [&](int arr, uint32_t n, double val) { o[((size_t)arr * NO + n) * NPT + p] = val; });
     }
 }
 
@@ -327,14 +275,7 @@ cudaError_t launch_k1_tables(const Plan& P, int basis_kind, uint32_t nu, uint32_
 cudaError_t launch_k2_exact(const Plan& P, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches) {
     if (P.host.items.empty()) return cudaSuccess;
     // shared memory: 256 doubles of weights + chunk * (C and F slabs of both sides).  Prefer <= ~100 KB so two CTAs share an SM.
-    uint32_t max_stride = 0;
-    for (const ClassDesc& c : P.host.classes) {
-        const ListDesc& LP = P.host.lists[c.listP]; const ListDesc& LQ = P.host.lists[c.listQ];
-        auto p4 = [](uint32_t x) { return (x + 3u) & ~3u; };
-        uint32_t s = p4(LP.nU) + p4(LP.n - LP.nU);
-        if (!c.local) s += p4(LQ.nU) + p4(LQ.n - LQ.nU);
-        max_stride = std::max(max_stride, s);
-    }
+    const uint32_t max_stride = P.host.max_slab_stride;   // widest class: pad4(U) + pad4(V) functions of P (+ of Q unless local)
     const size_t per_pt = (size_t)max_stride * 2 * sizeof(double);
     const size_t fixed = 256 * sizeof(double);
     const size_t soft = 100 * 1024, hard = (size_t)P.max_smem_optin - 1024;
@@ -343,8 +284,12 @@ cudaError_t launch_k2_exact(const Plan& P, uint32_t nu, uint32_t nv, uint32_t NO
     if (chunk < std::min<uint32_t>(npts, nv)) chunk = (uint32_t)std::min<size_t>(npts, (hard - fixed) / per_pt);   // at least one row if possible
     if (chunk == 0) return cudaErrorInvalidConfiguration;
     const size_t smem = fixed + (size_t)chunk * per_pt;
-    cudaError_t e = cudaFuncSetAttribute(k2_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    static thread_local size_t smem_set[64] = {};   // per device: largest dynamic shared memory size already opted in
+    if (P.device >= 0 && P.device < 64 && smem > smem_set[P.device]) {
+        cudaError_t e = cudaFuncSetAttribute(k2_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set[P.device] = smem;
+    }
     K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, P.d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, chunk};
     k2_exact_kernel<<<(unsigned)P.host.items.size(), K2_THREADS, smem, st>>>(g);
     if (launches) (*launches)++;

@@ -96,11 +96,11 @@ __global__ void __launch_bounds__(256) k2_sumfact_kernel(const SFArgs g) {
     }
 }
 
-cudaError_t ensure_gram(Plan& P, uint32_t NO) {
+cudaError_t ensure_gram(Plan& P, uint32_t NO, cudaStream_t st) {
     const size_t need = std::max<size_t>(P.host.grams.size(), 1) * G_KINDS * NO * NO;
     if (need > P.gram_capacity) {
-        cudaFree(P.d_gram); P.d_gram = nullptr; P.gram_capacity = 0;
-        cudaError_t e = cudaMalloc((void**)&P.d_gram, need * sizeof(double));
+        fem2d::dev_free(P.d_gram, st); P.d_gram = nullptr; P.gram_capacity = 0;
+        cudaError_t e = fem2d::dev_malloc((void**)&P.d_gram, need * sizeof(double), st);
         if (e != cudaSuccess) return e;
         P.gram_capacity = need;
     }
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(DM_WARPS * 32) k2_dmma_kernel(const DMArgs g) 
 
 cudaError_t launch_k2_sumfact(Plan& P, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches) {
     if (P.host.classes.empty()) return cudaSuccess;
-    cudaError_t e = ensure_gram(P, NO);
+    cudaError_t e = ensure_gram(P, NO, st);
     if (e != cudaSuccess) return e;
     gram_kernel<<<(unsigned)P.host.grams.size(), 128, 0, st>>>(P.d_grams, P.d_tabs, P.d_glq, P.d_gram, NO, NPT, nu, nv);
     if (launches) (*launches)++;
@@ -282,7 +282,7 @@ cudaError_t launch_k2_dmma(Plan& P, uint32_t nu, uint32_t nv, uint32_t NO, uint3
             }
         }
         P.n_dmma_items = (uint32_t)items.size();
-        cudaError_t e = cudaMalloc((void**)&P.d_dmma_items, std::max<size_t>(items.size(), 1) * sizeof(DmmaItem));
+        cudaError_t e = fem2d::dev_malloc((void**)&P.d_dmma_items, std::max<size_t>(items.size(), 1) * sizeof(DmmaItem), st);
         if (e != cudaSuccess) return e;
         e = cudaMemcpyAsync(P.d_dmma_items, items.data(), items.size() * sizeof(DmmaItem), cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess) return e;

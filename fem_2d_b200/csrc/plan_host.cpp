@@ -54,24 +54,12 @@ struct TabKeyHash { size_t operator()(const TabKey& k) const { return (size_t)fn
 
 }  // namespace
 
-int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::string& err) {
-    if (!v) { err = "null view"; return FEM2D_ERR_BAD_ARGUMENT; }
-    // Reference error order: continuity condition, then empty DoF set (galerkin.rs:42-50).
-    if (v->continuity != FEM2D_CC_HCURL) { err = "Wrong Continuity Condition on Domain (required: H(Curl))"; return FEM2D_ERR_WRONG_CONTINUITY; }
-    if (v->n_dofs == 0) { err = "No Degrees-of-Freedom Defined over Domain"; return FEM2D_ERR_EMPTY_DOF_SET; }
+// Per-Elem constant Jacobian: parametric range of the Elem inside its Element (elem.rs:191-197) mapped to real space
+// (element.rs:33-50): diag(dx_du, dy_dv).
+int elem_geometry(const fem2d_domain_view* v, std::vector<double>& dx, std::vector<double>& dy, std::string& err) {
     const uint32_t ne = v->n_elems;
-    if (!v->elem_element || !v->elem_parent || !v->elem_loc || !v->element_p0 || !v->element_p3 || !v->element_eps_re ||
-        !v->element_mu_re || !v->bs_off) { err = "null array in view"; return FEM2D_ERR_BAD_ARGUMENT; }
-    const uint32_t nbs = v->bs_off[ne];
-    if (nbs && (!v->bs_i || !v->bs_j || !v->bs_dir || !v->bs_dof)) { err = "null basis-spec array in view"; return FEM2D_ERR_BAD_ARGUMENT; }
-    if (v->i_max > 20 || v->j_max > 20) { err = "expansion order exceeds MAX_POLYNOMIAL_ORDER (20)"; return FEM2D_ERR_UNSUPPORTED; }
-    P = HostPlan();
-    P.n_elems = ne; P.n_dofs = v->n_dofs; P.i_max = v->i_max; P.j_max = v->j_max;
-    P.bs_off.assign(v->bs_off, v->bs_off + ne + 1);
-
-    // ---- per-Elem geometry: parametric range (elem.rs:191-197) then the constant Jacobian diag(dx_du, dy_dv) (element.rs:33-50)
     std::vector<double> range(4 * (size_t)ne);
-    P.elem_dx.resize(ne); P.elem_dy.resize(ne);
+    dx.resize(ne); dy.resize(ne);
     for (uint32_t e = 0; e < ne; e++) {
         const int32_t par = v->elem_parent[e];
         if (par >= (int32_t)e) { err = "elem_parent must precede its children"; return FEM2D_ERR_BAD_ARGUMENT; }
@@ -88,9 +76,29 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
         const double real_x_max = map_range(r[1], -1.0, 1.0, p0[0], p3[0]);
         const double real_y_min = map_range(r[2], -1.0, 1.0, p0[1], p3[1]);
         const double real_y_max = map_range(r[3], -1.0, 1.0, p0[1], p3[1]);
-        P.elem_dx[e] = (real_x_max - real_x_min) / 2.0;
-        P.elem_dy[e] = (real_y_max - real_y_min) / 2.0;
+        dx[e] = (real_x_max - real_x_min) / 2.0;
+        dy[e] = (real_y_max - real_y_min) / 2.0;
     }
+    return FEM2D_OK;
+}
+
+int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::string& err) {
+    if (!v) { err = "null view"; return FEM2D_ERR_BAD_ARGUMENT; }
+    // Reference error order: continuity condition, then empty DoF set (galerkin.rs:42-50).
+    if (v->continuity != FEM2D_CC_HCURL) { err = "Wrong Continuity Condition on Domain (required: H(Curl))"; return FEM2D_ERR_WRONG_CONTINUITY; }
+    if (v->n_dofs == 0) { err = "No Degrees-of-Freedom Defined over Domain"; return FEM2D_ERR_EMPTY_DOF_SET; }
+    const uint32_t ne = v->n_elems;
+    if (!v->elem_element || !v->elem_parent || !v->elem_loc || !v->element_p0 || !v->element_p3 || !v->element_eps_re ||
+        !v->element_mu_re || !v->bs_off) { err = "null array in view"; return FEM2D_ERR_BAD_ARGUMENT; }
+    const uint32_t nbs = v->bs_off[ne];
+    if (nbs && (!v->bs_i || !v->bs_j || !v->bs_dir || !v->bs_dof)) { err = "null basis-spec array in view"; return FEM2D_ERR_BAD_ARGUMENT; }
+    if (v->i_max > 20 || v->j_max > 20) { err = "expansion order exceeds MAX_POLYNOMIAL_ORDER (20)"; return FEM2D_ERR_UNSUPPORTED; }
+    P = HostPlan();
+    P.n_elems = ne; P.n_dofs = v->n_dofs; P.i_max = v->i_max; P.j_max = v->j_max;
+    P.bs_off.assign(v->bs_off, v->bs_off + ne + 1);
+
+    // ---- per-Elem geometry
+    if (int st = elem_geometry(v, P.elem_dx, P.elem_dy, err)) return st;
 
     // ---- canonical BasisSpec lists, pooled by content.
     // Phase A (parallel over Elems): validate, sort each Elem's specs by (dir, i, j), emit canon_dof and a content hash.
@@ -279,10 +287,25 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
     std::vector<uint32_t> cls_order(P.classes.size());
     std::iota(cls_order.begin(), cls_order.end(), 0u);
     std::stable_sort(cls_order.begin(), cls_order.end(), [&](uint32_t a, uint32_t b) { return P.classes[a].n_mt > P.classes[b].n_mt; });
+    for (const ClassDesc& c : P.classes) {
+        const ListDesc& LP = P.lists[c.listP]; const ListDesc& LQ = P.lists[c.listQ];
+        auto p4 = [](uint32_t x) { return (x + 3u) & ~3u; };
+        uint32_t s = p4(LP.nU) + p4(LP.n - LP.nU);
+        if (!c.local) s += p4(LQ.nU) + p4(LQ.n - LQ.nU);
+        P.max_slab_stride = std::max(P.max_slab_stride, s);
+    }
+    // Few, heavily deduplicated classes would leave most of the 148 SMs idle: shrink the item size until there are about two
+    // CTAs per SM (each item re-stages its class's slabs, which is cheap next to an idle machine).
+    uint32_t cap = K2_ROUNDS * K2_THREADS;
+    for (; cap > 64; cap /= 2) {
+        uint64_t n = 0;
+        for (const ClassDesc& c : P.classes) n += (c.n_mt + cap - 1) / cap;
+        if (n >= 2 * 148) break;
+    }
     for (uint32_t c : cls_order) {
-        const uint32_t n_mt = P.classes[c].n_mt, cap = K2_ROUNDS * K2_THREADS;
+        const uint32_t n_mt = P.classes[c].n_mt;
         const uint32_t n_items = (n_mt + cap - 1) / cap;
-        for (uint32_t k = 0; k < n_items; k++) {   // equal shares, rounded up to whole warps
+        for (uint32_t k = 0; k < n_items; k++) {   // equal shares
             const uint32_t b = (uint32_t)((uint64_t)n_mt * k / n_items), e = (uint32_t)((uint64_t)n_mt * (k + 1) / n_items);
             if (e > b) P.items.push_back(WorkItem{c, b, e - b, 0});
         }

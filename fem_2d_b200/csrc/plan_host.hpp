@@ -27,7 +27,11 @@ struct HostPlan {
     uint64_t n_pairs = 0;    // == number of (p,q) integrations the reference performs (x2 for A and B)
     uint64_t n_values = 0;   // entries of V
     uint32_t max_list_n = 0;
+    uint32_t max_slab_stride = 0;   // max over classes of pad4(nU)+pad4(nV) of P (+ the same of Q for non-local classes)
 };
+
+// dx_du, dy_dv of every Elem (element.rs:33-50), in the reference's operation order.
+int elem_geometry(const fem2d_domain_view* view, std::vector<double>& dx, std::vector<double>& dy, std::string& err);
 
 // Returns FEM2D_OK or a status from include/fem2d.h; err receives a detail message.
 int build_host_plan(const fem2d_domain_view* view, bool dedupe, HostPlan& plan, std::string& err);
