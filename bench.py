@@ -209,6 +209,9 @@ def run_ours(args):
     nnz = plan.nnz
     bounds = plan.row_blocks(world)
     s0, s1 = int(bounds[rank]), int(bounds[rank + 1])
+    if args.emulate_world > 1:   # tuning aid: time one rank's row block of an N-rank run on a single GPU
+        eb = plan.row_blocks(args.emulate_world)
+        s0, s1 = int(eb[args.emulate_rank]), int(eb[args.emulate_rank + 1])
     stream = torch.cuda.current_stream()
     d_a = torch.empty(nnz, dtype=torch.float64, device=dev)
     d_b = torch.empty(nnz, dtype=torch.float64, device=dev)
@@ -248,6 +251,8 @@ def run_ours(args):
     peaks, peak_kind = _peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     n_slots = s1 - s0
+    # K3 algorithmic bytes: 16 B written per slot (A and B) + the 4 B source index it reads (SURVEY.md 8d budgets 4 B per pair
+    # for a push scatter; the gather form reads one index per slot)
     alg_bytes_k3 = 16.0 * n_slots + 4.0 * n_slots
     k3_gbs = alg_bytes_k3 / (k3_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k3_gather_kernel (DoF scatter)", "achieved": k3_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k3_gbs / hbm_peak,
@@ -303,7 +308,7 @@ def run_ours(args):
                        if workload == "cfg3" else workload,
                        "mode": args.mode, "dedupe": int(args.dedupe), "n_dofs": info["n_dofs"], "nnz_upper_per_matrix": nnz, "n_pairs": info["n_pairs"],
                        "n_classes": info["n_classes"], "nnz_counted": "2 x nnz_upper (A and B)",
-                       "l2_policy": "no flush: each step streams 1.15 GB (source map + A/B value arrays) > 126 MB L2",
+                       "l2_policy": "no flush: each step streams > 0.92 GB (A/B value arrays + source map) >> 126 MB L2",
                        "parallelism": f"row-block x{world}" if world > 1 else "single GPU"},
             "phases_ms": {"sampler_k1": float(k1_ms), "integrator_k2": float(k2_ms), "scatter_k3": float(k3_ms), "sum": float(tot_ms)},
             "roofline": roofline,
@@ -389,6 +394,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--emulate-world", type=int, default=1)
+    ap.add_argument("--emulate-rank", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -568,7 +568,7 @@ def nalgebra_solve_gep(gep: GEP, target_eigenvalue: float) -> EigenPair:
 
 # ---- plan + assembly --------------------------------------------------------------------------------------------------------------
 INFO_KEYS = ["nnz_upper", "n_pairs", "n_blocks", "n_classes", "n_values", "n_multi", "max_contrib", "n_tables", "n_work_items",
-             "n_dofs", "n_lists", "n_extra", "symbolic_host_us", "symbolic_device_us"]
+             "n_dofs", "n_lists", "n_extra", "symbolic_host_us", "symbolic_device_us", "tile_p"]
 
 
 class Plan:

@@ -16,7 +16,7 @@ LIB = os.path.join(HERE, "libfem2d_b200.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall"] + os.environ.get("FEM2D_NVCC_FLAGS", "").split()
 
 # (source, extra flags)
 UNITS = [

@@ -117,7 +117,7 @@ int fem2d_plan_info(const fem2d_plan* plan, uint64_t info[16]) {
     info[0] = p.nnz; info[1] = p.host.n_pairs; info[2] = p.host.blocks.size(); info[3] = p.host.classes.size();
     info[4] = p.host.n_values; info[5] = p.n_multi; info[6] = p.max_contrib; info[7] = p.host.tables.size();
     info[8] = p.host.items.size(); info[9] = p.host.n_dofs; info[10] = p.host.lists.size(); info[11] = p.n_extra;
-    info[12] = p.t_host_us; info[13] = p.t_device_us;
+    info[12] = p.t_host_us; info[13] = p.t_device_us; info[14] = p.host.tile_p;
     return FEM2D_OK;
 }
 

@@ -190,6 +190,7 @@ int device_symbolic(Plan& P, std::string& err) {
     }
     CKC(cudaMemcpy(stats, d_stats, 8, cudaMemcpyDeviceToHost));
     P.max_contrib = stats[0]; P.n_multi = stats[1];
+
     CKC(cudaDeviceSynchronize());
     cleanup();
 #undef CKC

@@ -48,15 +48,20 @@ struct K2Args {
 
 __device__ __forceinline__ uint32_t pad4(uint32_t x) { return (x + 3u) & ~3u; }
 
-template <bool SAME>
+template <bool SAME, int TP>
 __device__ __forceinline__ void contract_point(const double* __restrict__ cp, const double* __restrict__ cq,
                                                const double* __restrict__ fp, const double* __restrict__ fq, double ratio, double maxdet,
-                                               double w, double (&inA)[MT_P][MT_Q], double (&inB)[MT_P][MT_Q]) {
-    const double2 c01 = *reinterpret_cast<const double2*>(cp), c23 = *reinterpret_cast<const double2*>(cp + 2);
-    const double2 q01 = *reinterpret_cast<const double2*>(cq);
-    const double pc[4] = {c01.x, c01.y, c23.x, c23.y}, qc[2] = {q01.x, q01.y};
+                                               double w, double (&inA)[TP][MT_Q], double (&inB)[TP][MT_Q]) {
+    double pc[TP], qc[MT_Q];
+    if (TP == 1) pc[0] = cp[0];
+    else {
 #pragma unroll
-    for (int r = 0; r < MT_P; r++)
+        for (int r = 0; r + 1 < TP; r += 2) { const double2 t = *reinterpret_cast<const double2*>(cp + r); pc[r] = t.x; pc[r + 1] = t.y; }
+    }
+#pragma unroll
+    for (int c = 0; c < MT_Q; c += 2) { const double2 t = *reinterpret_cast<const double2*>(cq + c); qc[c] = t.x; qc[c + 1] = t.y; }
+#pragma unroll
+    for (int r = 0; r < TP; r++)
 #pragma unroll
         for (int c = 0; c < MT_Q; c++) {
             double t = pc[r] * qc[c];              // p_curl * q_curl
@@ -64,11 +69,16 @@ __device__ __forceinline__ void contract_point(const double* __restrict__ cp, co
             inA[r][c] = inA[r][c] + t * w;         // inner_solution += integrand * v_w (glq.rs:27)
         }
     if (SAME) {
-        const double2 f01 = *reinterpret_cast<const double2*>(fp), f23 = *reinterpret_cast<const double2*>(fp + 2);
-        const double2 g01 = *reinterpret_cast<const double2*>(fq);
-        const double pf[4] = {f01.x, f01.y, f23.x, f23.y}, qf[2] = {g01.x, g01.y};
+        double pf[TP], qf[MT_Q];
+        if (TP == 1) pf[0] = fp[0];
+        else {
 #pragma unroll
-        for (int r = 0; r < MT_P; r++)
+            for (int r = 0; r + 1 < TP; r += 2) { const double2 t = *reinterpret_cast<const double2*>(fp + r); pf[r] = t.x; pf[r + 1] = t.y; }
+        }
+#pragma unroll
+        for (int c = 0; c < MT_Q; c += 2) { const double2 t = *reinterpret_cast<const double2*>(fq + c); qf[c] = t.x; qf[c + 1] = t.y; }
+#pragma unroll
+        for (int r = 0; r < TP; r++)
 #pragma unroll
             for (int c = 0; c < MT_Q; c++) {
                 double t = pf[r] * qf[c];          // V2D::dot(f_p, f_q): the second product is a signed zero
@@ -79,18 +89,19 @@ __device__ __forceinline__ void contract_point(const double* __restrict__ cp, co
 }
 
 // Contract `run` consecutive points of one quadrature row (n .. n+run-1 of row m) into the inner accumulators.
-template <bool SAME>
+template <bool SAME, int TP>
 __device__ __forceinline__ void contract_run(const double*& cp, const double*& cq, const double*& fp, const double*& fq, uint32_t strideP,
                                              uint32_t strideQ, const double* __restrict__ vw, uint32_t run, double ratio, double maxdet,
-                                             double (&inA)[MT_P][MT_Q], double (&inB)[MT_P][MT_Q]) {
+                                             double (&inA)[TP][MT_Q], double (&inB)[TP][MT_Q]) {
 #pragma unroll 4
     for (uint32_t k = 0; k < run; k++) {
-        contract_point<SAME>(cp, cq, fp, fq, ratio, maxdet, vw[k], inA, inB);
+        contract_point<SAME, TP>(cp, cq, fp, fq, ratio, maxdet, vw[k], inA, inB);
         cp += strideP; cq += strideQ;
         if (SAME) { fp += strideP; fq += strideQ; }
     }
 }
 
+template <int TP>
 __global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g) {
     extern __shared__ __align__(16) double smem[];
     const WorkItem it = g.items[blockIdx.x];
@@ -127,7 +138,7 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g)
     const double* tQv = g.tabs + (size_t)c.tabQv * 4 * g.NO * g.NPT;
     const uint32_t AS = g.NO * g.NPT;   // stride between the four arrays N, N', T, T'
     __shared__ SubBlocks sb;
-    if (threadIdx.x == 0) sb = make_subblocks(nP, nUP, nQ, nUQ, c.local);
+    if (threadIdx.x == 0) sb = make_subblocks(nP, nUP, nQ, nUQ, c.local, TP);
     __syncthreads();
     const bool single_chunk = chunk >= npts;
     double2* out = g.V + c.v_off;
@@ -143,9 +154,9 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g)
             uint32_t rt, ct;
             if (sb.tri[sub]) {
                 rt = 0;
-                for (;;) { const uint32_t lo = rt * MT_P / MT_Q; const uint32_t cnt = nct > lo ? nct - lo : 0; if (idx < cnt) { ct = lo + idx; break; } idx -= cnt; rt++; }
+                for (;;) { const uint32_t lo = rt * TP / MT_Q; const uint32_t cnt = nct > lo ? nct - lo : 0; if (idx < cnt) { ct = lo + idx; break; } idx -= cnt; rt++; }
             } else { rt = idx / nct; ct = idx - rt * nct; }
-            row0 = sb.row0[sub] + rt * MT_P; col0 = sb.col0[sub] + ct * MT_Q;
+            row0 = sb.row0[sub] + rt * TP; col0 = sb.col0[sub] + ct * MT_Q;
             row_end = sb.row0[sub] + sb.rows[sub]; col_end = sb.col0[sub] + sb.cols[sub];
             prow = (sub >= 2 ? pad4(nUP) - nUP : 0) + row0;            // slab column of the canonical row index
             pcol = ((sub & 1) ? pad4(nUQ) - nUQ : 0) + col0;
@@ -153,9 +164,9 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g)
         const bool same = (sub == 0 || sub == 3);
         const double ratio = sub == 0 ? ratio_uv : ratio_vu;
 
-        double solA[MT_P][MT_Q], solB[MT_P][MT_Q], inA[MT_P][MT_Q], inB[MT_P][MT_Q];
+        double solA[TP][MT_Q], solB[TP][MT_Q], inA[TP][MT_Q], inB[TP][MT_Q];
 #pragma unroll
-        for (int r = 0; r < MT_P; r++)
+        for (int r = 0; r < TP; r++)
 #pragma unroll
             for (int q = 0; q < MT_Q; q++) { solA[r][q] = 0.0; solB[r][q] = 0.0; inA[r][q] = 0.0; inB[r][q] = 0.0; }
 
@@ -214,13 +225,13 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g)
                 const double* cq = s_CQ + pcol; const double* fq = s_FQ + pcol;
                 while (pl < cn) {
                     const uint32_t run = min(cn - pl, nv - n);
-                    if (same) contract_run<true>(cp, cq, fp, fq, strideP, strideQ, s_vw + n, run, ratio, maxdet, inA, inB);
-                    else contract_run<false>(cp, cq, fp, fq, strideP, strideQ, s_vw + n, run, ratio, maxdet, inA, inB);
+                    if (same) contract_run<true, TP>(cp, cq, fp, fq, strideP, strideQ, s_vw + n, run, ratio, maxdet, inA, inB);
+                    else contract_run<false, TP>(cp, cq, fp, fq, strideP, strideQ, s_vw + n, run, ratio, maxdet, inA, inB);
                     pl += run; n += run;
                     if (n == nv) {   // end of the inner (v) loop: solution += inner_solution * u_w (glq.rs:29)
                         const double uw = s_uw[m];
 #pragma unroll
-                        for (int r = 0; r < MT_P; r++)
+                        for (int r = 0; r < TP; r++)
 #pragma unroll
                             for (int q = 0; q < MT_Q; q++) {
                                 solA[r][q] = solA[r][q] + inA[r][q] * uw; inA[r][q] = 0.0;
@@ -233,7 +244,7 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g)
         }
         if (active) {
 #pragma unroll
-            for (int r = 0; r < MT_P; r++) {
+            for (int r = 0; r < TP; r++) {
                 const uint32_t a = row0 + r;
                 if (a >= row_end) continue;
 #pragma unroll
@@ -286,12 +297,14 @@ cudaError_t launch_k2_exact(const Plan& P, uint32_t nu, uint32_t nv, uint32_t NO
     const size_t smem = fixed + (size_t)chunk * per_pt;
     static thread_local size_t smem_set[64] = {};   // per device: largest dynamic shared memory size already opted in
     if (P.device >= 0 && P.device < 64 && smem > smem_set[P.device]) {
-        cudaError_t e = cudaFuncSetAttribute(k2_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k2_exact_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         smem_set[P.device] = smem;
     }
     K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, P.d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, chunk};
-    k2_exact_kernel<<<(unsigned)P.host.items.size(), K2_THREADS, smem, st>>>(g);
+    if (P.host.tile_p == 1) k2_exact_kernel<1><<<(unsigned)P.host.items.size(), K2_THREADS, smem, st>>>(g);
+    else k2_exact_kernel<4><<<(unsigned)P.host.items.size(), K2_THREADS, smem, st>>>(g);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

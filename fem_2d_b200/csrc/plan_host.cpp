@@ -112,6 +112,25 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
     std::vector<uint32_t> canon_key(nbs);      // (dir << 16 | i << 8 | j) in canonical order, per Elem at bs_off[e]
     std::vector<uint64_t> elem_hash(ne, 0);
     std::vector<uint32_t> elem_nU(ne, 0);
+    // Canonical order of an Elem's functions: U-directed first, then V-directed; inside a direction the Elem-type functions
+    // (U: j >= 2, V: i >= 2; basis_spec.rs:49-63) in (i, j) order, then the edge-type functions edge by edge (U: j = 0, j = 1,
+    // each by i; V: i = 0, i = 1, each by j).  This follows the reference's DoF numbering (Elem-type DoFs of a leaf are
+    // consecutive in generation order, the DoFs of an edge are consecutive: domain.rs:83-149), so consecutive slots of a pattern
+    // row read consecutive entries of V (long source runs), and the pairs feeding edge-DoF rows form contiguous micro-tile ranges.
+    const uint32_t JSg = v->j_max + 1, KSg = 2 * (v->i_max + 1) * JSg;
+    std::vector<uint32_t> rank_cell(KSg), cell_rank(KSg);
+    {
+        std::vector<std::pair<uint32_t, uint32_t>> keyed;   // (sort key, cell)
+        for (uint32_t dir = 0; dir < 2; dir++)
+            for (uint32_t i = 0; i <= v->i_max; i++)
+                for (uint32_t j = 0; j <= v->j_max; j++) {
+                    const uint32_t across = dir == 0 ? j : i;                 // order across the function's tangential edge pair
+                    const uint32_t group = across >= 2 ? 0u : 1u + across;   // 0: Elem-type, 1 / 2: the two edges
+                    keyed.push_back({dir << 20 | group << 16 | i << 8 | j, (dir * (v->i_max + 1) + i) * JSg + j});
+                }
+        std::sort(keyed.begin(), keyed.end());
+        for (uint32_t r = 0; r < KSg; r++) { rank_cell[r] = keyed[r].second; cell_rank[keyed[r].second] = r; }
+    }
     const unsigned n_threads = ne < 4096 ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     std::vector<int> bad(n_threads, 0);
     auto phase_a = [&](unsigned tid) {
@@ -140,23 +159,23 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
             if (!ok) { std::fill(slot.begin(), slot.end(), -1); continue; }
             if (!dup) {
                 uint32_t w = 0;
-                for (uint32_t key = 0; key < KS && w < n; key++)
-                    if (slot[key] >= 0) {
-                        const uint32_t k = (uint32_t)slot[key];
-                        order[w++] = ((uint32_t)v->bs_dir[b + k] << 16 | (uint32_t)v->bs_i[b + k] << 8 | v->bs_j[b + k]) << 11 | k;
-                        slot[key] = -1;
-                    }
+                for (uint32_t r = 0; r < KS && w < n; r++) {
+                    const uint32_t cell = rank_cell[r];
+                    if (slot[cell] >= 0) { order[w++] = (uint32_t)slot[cell]; slot[cell] = -1; }
+                }
             } else {   // repeated (dir, i, j) on one Elem (never produced by Domain::from_mesh): stable comparison sort keeps all of them
                 std::fill(slot.begin(), slot.end(), -1);
                 for (uint32_t k = 0; k < n; k++)
-                    order[k] = ((uint32_t)v->bs_dir[b + k] << 16 | (uint32_t)v->bs_i[b + k] << 8 | v->bs_j[b + k]) << 11 | k;
+                    order[k] = cell_rank[((uint32_t)v->bs_dir[b + k] * (v->i_max + 1) + v->bs_i[b + k]) * JS + v->bs_j[b + k]] << 11 | k;
                 std::sort(order.begin(), order.end());
+                for (uint32_t k = 0; k < n; k++) order[k] &= 2047u;
             }
             uint32_t nU = 0;
             uint64_t h = 1469598103934665603ull;
             for (uint32_t k = 0; k < n; k++) {
-                const uint32_t key = order[k] >> 11;
-                P.canon_dof[b + k] = v->bs_dof[b + (order[k] & 2047u)];
+                const uint32_t src = b + order[k];
+                const uint32_t key = (uint32_t)v->bs_dir[src] << 16 | (uint32_t)v->bs_i[src] << 8 | v->bs_j[src];
+                P.canon_dof[b + k] = v->bs_dof[src];
                 canon_key[b + k] = key;
                 nU += (key >> 16) == 0;
                 h = (h ^ key) * 0x9E3779B97F4A7C15ull; h ^= h >> 29;
@@ -271,8 +290,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
                 c.v_off = P.n_values;
                 const ListDesc& LP = P.lists[c.listP]; const ListDesc& LQ = P.lists[c.listQ];
                 P.n_values += (uint64_t)LP.n * LQ.n;
-                const SubBlocks sb = make_subblocks(LP.n, LP.nU, LQ.n, LQ.nU, c.local);
-                c.n_mt = sb.cnt[0] + sb.cnt[1] + sb.cnt[2] + sb.cnt[3];
+                c.n_mt = 0;   // filled once the tile shape is chosen
                 P.classes.push_back(c);
                 class_pool.emplace(key, cls);
             }
@@ -294,10 +312,25 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
         if (!c.local) s += p4(LQ.nU) + p4(LQ.n - LQ.nU);
         P.max_slab_stride = std::max(P.max_slab_stride, s);
     }
+    // ---- tile shape: a plan whose 4 x 2 micro-tiles cannot even give every SM one full CTA is latency bound -> 1 x 2 tiles
+    auto count_mt = [&](uint32_t tp) {
+        uint64_t n = 0;
+        for (ClassDesc& c : P.classes) {
+            const ListDesc& LP = P.lists[c.listP]; const ListDesc& LQ = P.lists[c.listQ];
+            const SubBlocks sb = make_subblocks(LP.n, LP.nU, LQ.n, LQ.nU, c.local, tp);
+            c.n_mt = sb.cnt[0] + sb.cnt[1] + sb.cnt[2] + sb.cnt[3];
+            n += c.n_mt;
+        }
+        return n;
+    };
+    P.tile_p = 4;
+    if (count_mt(4) < (uint64_t)148 * K2_THREADS) { P.tile_p = 1; count_mt(1); }
+    std::stable_sort(cls_order.begin(), cls_order.end(), [&](uint32_t a, uint32_t b) { return P.classes[a].n_mt > P.classes[b].n_mt; });
     // Few, heavily deduplicated classes would leave most of the 148 SMs idle: shrink the item size until there are about two
     // CTAs per SM (each item re-stages its class's slabs, which is cheap next to an idle machine).
     uint32_t cap = K2_ROUNDS * K2_THREADS;
-    for (; cap > 64; cap /= 2) {
+    const uint32_t min_cap = P.tile_p == 1 ? 128u : 64u;
+    for (; cap > min_cap; cap /= 2) {
         uint64_t n = 0;
         for (const ClassDesc& c : P.classes) n += (c.n_mt + cap - 1) / cap;
         if (n >= 2 * 148) break;

@@ -14,9 +14,12 @@
 
 namespace fem2d {
 
-constexpr int MT_P = 4;   // micro-tile: P functions (rows) per thread
-constexpr int MT_Q = 2;   // micro-tile: Q functions (cols) per thread
+// Micro-tile of the exact integrator: TP x MT_Q pairs per thread.  TP = 4 is the throughput shape (FP64-issue bound, 16
+// independent accumulation chains per thread); TP = 1 is the latency shape used for small / heavily deduplicated plans,
+// where 4x more threads with 4x shorter instruction streams fill the machine instead.  The planner picks (HostPlan::tile_p).
+constexpr int MT_Q = 2;            // micro-tile: Q functions (cols) per thread
 constexpr int K2_THREADS = 256;
+constexpr int K2_MIN_CTAS = 2;     // CTAs per SM the integrator is compiled for
 constexpr int K2_ROUNDS = 2;    // a work item covers up to K2_ROUNDS * K2_THREADS micro-tiles of one class (slabs staged once)
 
 struct ClassDesc {
@@ -78,13 +81,13 @@ struct SubBlocks {
 #define FEM2D_HD
 #endif
 FEM2D_HD inline uint32_t mt_div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
-FEM2D_HD inline uint32_t mt_tri_count(uint32_t n) {
-    const uint32_t nrt = mt_div_up(n, MT_P), nct = mt_div_up(n, MT_Q);
+FEM2D_HD inline uint32_t mt_tri_count(uint32_t n, uint32_t tp) {
+    const uint32_t nrt = mt_div_up(n, tp), nct = mt_div_up(n, MT_Q);
     uint32_t c = 0;
-    for (uint32_t rt = 0; rt < nrt; rt++) { const uint32_t lo = rt * MT_P / MT_Q; if (nct > lo) c += nct - lo; }
+    for (uint32_t rt = 0; rt < nrt; rt++) { const uint32_t lo = rt * tp / MT_Q; if (nct > lo) c += nct - lo; }
     return c;
 }
-FEM2D_HD inline SubBlocks make_subblocks(uint32_t nP, uint32_t nUP, uint32_t nQ, uint32_t nUQ, uint32_t local) {
+FEM2D_HD inline SubBlocks make_subblocks(uint32_t nP, uint32_t nUP, uint32_t nQ, uint32_t nUQ, uint32_t local, uint32_t tp) {
     SubBlocks s;
     const uint32_t nVP = nP - nUP, nVQ = nQ - nUQ;
     const uint32_t R[4] = {nUP, nUP, nVP, nVP}, Cc[4] = {nUQ, nVQ, nUQ, nVQ};
@@ -93,8 +96,8 @@ FEM2D_HD inline SubBlocks make_subblocks(uint32_t nP, uint32_t nUP, uint32_t nQ,
         s.rows[k] = R[k]; s.cols[k] = Cc[k]; s.row0[k] = r0[k]; s.col0[k] = c0[k];
         s.tri[k] = (local && (k == 0 || k == 3)) ? 1u : 0u;
         if (local && k == 2) s.cnt[k] = 0;
-        else if (s.tri[k]) s.cnt[k] = mt_tri_count(R[k]);
-        else s.cnt[k] = mt_div_up(R[k], MT_P) * mt_div_up(Cc[k], MT_Q);
+        else if (s.tri[k]) s.cnt[k] = mt_tri_count(R[k], tp);
+        else s.cnt[k] = mt_div_up(R[k], tp) * mt_div_up(Cc[k], MT_Q);
     }
     return s;
 }

@@ -89,7 +89,8 @@ void fem2d_plan_free(fem2d_plan* plan);
 
 /* Plan queries. info[]: 0 nnz_upper, 1 n_pairs (galerkin.rs pair count), 2 n_blocks, 3 n_classes, 4 n_value_slots (V buffer
  * entries), 5 n_multi (keys with >1 contribution), 6 max contributions per key, 7 n_tables, 8 n_work_items, 9 n_dofs,
- * 10 n_lists, 11 n_extra (2nd+ contributions), 12 / 13 wall microseconds of the host / device halves of the symbolic phase */
+ * 10 n_lists, 11 n_extra (2nd+ contributions), 12 / 13 wall microseconds of the host / device halves of the symbolic phase,
+ * 14 micro-tile height chosen for the exact integrator (4: throughput shape, 1: latency shape for small plans) */
 int fem2d_plan_info(const fem2d_plan* plan, uint64_t info[16]);
 /* Copy the pattern to host: rows[k] <= cols[k], sorted by (row, col). */
 int fem2d_plan_pattern(const fem2d_plan* plan, uint32_t* rows, uint32_t* cols);
