@@ -357,14 +357,25 @@ def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz):
     h_b = torch.empty(n, dtype=torch.float64).pin_memory()
     d2h = n * (4 + 4 + 8 + 8)
 
+    trace = []
+
     def one():
+        t0 = time.perf_counter()
         plan = F.Plan(pview, device=local_rank, dedupe=bool(args.dedupe))       # symbolic phase (H2D of the view-derived arrays inside)
+        t1 = time.perf_counter()
         plan.assemble_range_into(glq, s0, s1, h_a.data_ptr(), h_b.data_ptr(), h_rows.data_ptr(), h_cols.data_ptr(), mode=mode)   # numeric + D2H, synchronous
+        t2 = time.perf_counter()
+        info = plan.info
         del plan
+        t3 = time.perf_counter()
+        trace.append({"symbolic_ms": round(1e3 * (t1 - t0), 2), "symbolic_host_ms": round(info["symbolic_host_us"] / 1e3, 2),
+                      "symbolic_device_ms": round(info["symbolic_device_us"] / 1e3, 2), "numeric_d2h_ms": round(1e3 * (t2 - t1), 2),
+                      "plan_free_ms": round(1e3 * (t3 - t2), 2)})
 
     steps = max(1, min(args.steps, args.e2e_steps))
     for _ in range(2):
         one()
+    trace.clear()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -378,7 +389,8 @@ def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t.item())
     return {"value": 2.0 * nnz * steps / sec, "unit": "nnz/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * sec / steps,
-            "steps": steps, "includes": "symbolic phase (pattern + source map) + K1/K2/K3 + D2H of rows, cols, A, B into pinned host buffers"}
+            "steps": steps, "includes": "symbolic phase (pattern + source map) + K1/K2/K3 + D2H of rows, cols, A, B into pinned host buffers",
+            "per_step_breakdown_rank0": trace}
 
 
 def main():

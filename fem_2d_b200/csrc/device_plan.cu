@@ -3,6 +3,10 @@
 // per-Elem BTreeMap inserts and serial merge (sparse_matrix.rs:68-120, linalg.rs:59-81).
 #include <cub/cub.cuh>
 
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
 #include "device_plan.hpp"
 
 namespace fem2d {
@@ -91,15 +95,6 @@ __global__ void row_bounds_kernel(const uint32_t* __restrict__ rows, unsigned lo
     bounds[r] = s;
 }
 
-template <class T>
-int upload(T*& dst, const T* src, size_t n, std::string& err) {
-    dst = nullptr;
-    if (n == 0) n = 1;
-    CK(fem2d::dev_malloc((void**)&dst, n * sizeof(T)));
-    if (src) CK(cudaMemcpy(dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
-    return FEM2D_OK;
-}
-
 }  // namespace
 
 void dev_pool_init(int device) {
@@ -113,61 +108,92 @@ void dev_pool_init(int device) {
     done[device] = true;
 }
 
+namespace {
+// Carves 256-byte aligned sub-buffers out of one allocation.
+struct Arena {
+    size_t size = 0;
+    size_t reserve(size_t bytes) { const size_t off = size; size += (bytes + 255) & ~(size_t)255; return off; }
+};
+template <class T> T* at(void* base, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<char*>(base) + off); }
+}  // namespace
+
+// Two allocations per symbolic call: the plan-owned arena (pattern, source map, descriptors) and one scratch arena (keys, sort
+// double buffers, flags, scan, cub temp) that goes back to the stream-ordered pool at the end -- repeated calls on same-sized
+// Domains re-use both blocks without touching the driver allocator.  All small host arrays travel in one staged H2D copy.
 int device_symbolic(Plan& P, std::string& err) {
     const HostPlan& H = P.host;
     CK(cudaSetDevice(P.device));
     dev_pool_init(P.device);
     CK(cudaDeviceGetAttribute(&P.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, P.device));
     CK(cudaDeviceGetAttribute(&P.sm_count, cudaDevAttrMultiProcessorCount, P.device));
-    int st;
-    if ((st = upload(P.d_classes, H.classes.data(), H.classes.size(), err))) return st;
-    if ((st = upload(P.d_lists, H.lists.data(), H.lists.size(), err))) return st;
-    if ((st = upload(P.d_spec_i, H.spec_i.data(), H.spec_i.size(), err))) return st;
-    if ((st = upload(P.d_spec_j, H.spec_j.data(), H.spec_j.size(), err))) return st;
-    if ((st = upload(P.d_tables, H.tables.data(), H.tables.size(), err))) return st;
-    if ((st = upload(P.d_grams, H.grams.data(), H.grams.size(), err))) return st;
-    if ((st = upload(P.d_items, H.items.data(), H.items.size(), err))) return st;
-
     const uint32_t np = (uint32_t)H.n_pairs;
+
+    // ---- descriptor blob (plan-owned part first, then the scratch-only part), laid out identically on host and device
     std::vector<DevBlock> hb(H.blocks.size());
     for (size_t k = 0; k < H.blocks.size(); k++) {
         const BlockDesc& b = H.blocks[k];
         const ClassDesc& c = H.classes[b.cls];
         hb[k] = DevBlock{b.pair_off, c.v_off, H.bs_off[b.elemP], H.bs_off[b.elemQ], H.lists[c.listP].n, H.lists[c.listQ].n, c.local, 0};
     }
-    DevBlock* d_blocks = nullptr; uint32_t* d_canon = nullptr;
-    unsigned long long *d_keys = nullptr, *d_keys2 = nullptr;
-    uint32_t *d_srcs = nullptr, *d_srcs2 = nullptr, *d_head = nullptr, *d_scan = nullptr, *d_stats = nullptr;
-    void* d_temp = nullptr;
-    auto cleanup = [&]() {
-        fem2d::dev_free(d_blocks); fem2d::dev_free(d_canon); fem2d::dev_free(d_keys); fem2d::dev_free(d_keys2); fem2d::dev_free(d_srcs); fem2d::dev_free(d_srcs2);
-        fem2d::dev_free(d_head); fem2d::dev_free(d_scan); fem2d::dev_free(d_stats); fem2d::dev_free(d_temp);
-    };
-#define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); cleanup(); return FEM2D_ERR_CUDA; } } while (0)
-    if ((st = upload(d_blocks, hb.data(), hb.size(), err))) { cleanup(); return st; }
-    if ((st = upload(d_canon, H.canon_dof.data(), H.canon_dof.size(), err))) { cleanup(); return st; }
-    CKC(fem2d::dev_malloc((void**)&d_keys, (size_t)np * 8)); CKC(fem2d::dev_malloc((void**)&d_keys2, (size_t)np * 8));
-    CKC(fem2d::dev_malloc((void**)&d_srcs, (size_t)np * 4)); CKC(fem2d::dev_malloc((void**)&d_srcs2, (size_t)np * 4));
+    Arena desc;
+    const size_t o_classes = desc.reserve(H.classes.size() * sizeof(ClassDesc)), o_lists = desc.reserve(H.lists.size() * sizeof(ListDesc));
+    const size_t o_si = desc.reserve(H.spec_i.size()), o_sj = desc.reserve(H.spec_j.size());
+    const size_t o_tabs = desc.reserve(H.tables.size() * sizeof(TableDesc)), o_grams = desc.reserve(H.grams.size() * sizeof(GramDesc));
+    const size_t o_items = desc.reserve(H.items.size() * sizeof(WorkItem));
+    const size_t o_glq = desc.reserve(4 * 128 * sizeof(double));
+    const size_t desc_plan_bytes = desc.size;                     // everything above lives as long as the plan
+    const size_t o_blocks = desc.reserve(hb.size() * sizeof(DevBlock)), o_canon = desc.reserve(H.canon_dof.size() * 4);
+    std::vector<unsigned char> blob(desc.size, 0);
+    auto put = [&](size_t off, const void* src, size_t n) { if (n) std::memcpy(blob.data() + off, src, n); };
+    put(o_classes, H.classes.data(), H.classes.size() * sizeof(ClassDesc)); put(o_lists, H.lists.data(), H.lists.size() * sizeof(ListDesc));
+    put(o_si, H.spec_i.data(), H.spec_i.size()); put(o_sj, H.spec_j.data(), H.spec_j.size());
+    put(o_tabs, H.tables.data(), H.tables.size() * sizeof(TableDesc)); put(o_grams, H.grams.data(), H.grams.size() * sizeof(GramDesc));
+    put(o_items, H.items.data(), H.items.size() * sizeof(WorkItem));
+    put(o_blocks, hb.data(), hb.size() * sizeof(DevBlock)); put(o_canon, H.canon_dof.data(), H.canon_dof.size() * 4);
+
+    // ---- scratch arena
+    int bits = 1; while ((1ull << bits) < (unsigned long long)H.n_dofs) bits++;
+    size_t temp_bytes = 0, scan_bytes = 0;
+    {
+        cub::DoubleBuffer<unsigned long long> kq(nullptr, nullptr);
+        cub::DoubleBuffer<uint32_t> vq(nullptr, nullptr);
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, kq, vq, (int)np, 0, 32 + bits));
+        CK(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)np));
+        temp_bytes = std::max(temp_bytes, scan_bytes);
+    }
+    Arena sc;
+    const size_t s_desc = sc.reserve(desc.size - desc_plan_bytes);
+    const size_t s_keys = sc.reserve((size_t)np * 8), s_keys2 = sc.reserve((size_t)np * 8);
+    const size_t s_srcs = sc.reserve((size_t)np * 4), s_srcs2 = sc.reserve((size_t)np * 4);
+    const size_t s_head = sc.reserve((size_t)np * 4), s_scan = sc.reserve((size_t)np * 4);
+    const size_t s_temp = sc.reserve(temp_bytes), s_stats = sc.reserve(8);
+    void* scratch = nullptr;
+    CK(dev_malloc(&scratch, sc.size));
+#define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); dev_free(scratch); return FEM2D_ERR_CUDA; } } while (0)
+    // descriptors: the plan-owned part goes to a first small plan allocation, the rest into the scratch arena
+    CKC(dev_malloc(&P.d_desc_arena, desc_plan_bytes));
+    CKC(cudaMemcpyAsync(P.d_desc_arena, blob.data(), desc_plan_bytes, cudaMemcpyHostToDevice, nullptr));
+    CKC(cudaMemcpyAsync(at<char>(scratch, s_desc), blob.data() + desc_plan_bytes, desc.size - desc_plan_bytes, cudaMemcpyHostToDevice, nullptr));
+    P.d_classes = at<ClassDesc>(P.d_desc_arena, o_classes); P.d_lists = at<ListDesc>(P.d_desc_arena, o_lists);
+    P.d_spec_i = at<uint8_t>(P.d_desc_arena, o_si); P.d_spec_j = at<uint8_t>(P.d_desc_arena, o_sj);
+    P.d_tables = at<TableDesc>(P.d_desc_arena, o_tabs); P.d_grams = at<GramDesc>(P.d_desc_arena, o_grams);
+    P.d_items = at<WorkItem>(P.d_desc_arena, o_items); P.d_glq = at<double>(P.d_desc_arena, o_glq);
+    DevBlock* d_blocks = at<DevBlock>(scratch, s_desc + (o_blocks - desc_plan_bytes));
+    uint32_t* d_canon = at<uint32_t>(scratch, s_desc + (o_canon - desc_plan_bytes));
+    unsigned long long *d_keys = at<unsigned long long>(scratch, s_keys), *d_keys2 = at<unsigned long long>(scratch, s_keys2);
+    uint32_t *d_srcs = at<uint32_t>(scratch, s_srcs), *d_srcs2 = at<uint32_t>(scratch, s_srcs2);
+    uint32_t *d_head = at<uint32_t>(scratch, s_head), *d_scan = at<uint32_t>(scratch, s_scan), *d_stats = at<uint32_t>(scratch, s_stats);
+    void* d_temp = at<char>(scratch, s_temp);
+
     keygen_kernel<<<(unsigned)hb.size(), 256>>>(d_blocks, d_canon, d_keys, d_srcs);
     CKC(cudaGetLastError());
-
-    // stable LSD radix sort on the significant key bits only: [row | col] with bits(n_dofs) each
-    int bits = 1; while ((1ull << bits) < (unsigned long long)H.n_dofs) bits++;
+    // stable LSD radix sort on the significant key bits only ([row << 32 | col], bits(n_dofs) each): low bits of col, then of row
     cub::DoubleBuffer<unsigned long long> kb(d_keys, d_keys2);
     cub::DoubleBuffer<uint32_t> vb(d_srcs, d_srcs2);
-    size_t temp_bytes = 0;
-    CKC(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, kb, vb, (int)np, 0, 32 + bits));
-    size_t scan_bytes = 0;
-    CKC(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, d_head, d_scan, (int)np));
-    temp_bytes = std::max(temp_bytes, scan_bytes);
-    CKC(fem2d::dev_malloc(&d_temp, temp_bytes ? temp_bytes : 1));
-    // keys use [row << 32 | col]: sort low 'bits' of col, then low 'bits' of row.  Two passes keep the bit count minimal.
     CKC(cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, kb, vb, (int)np, 0, bits));
     CKC(cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, kb, vb, (int)np, 32, 32 + bits));
     const unsigned long long* keys_sorted = kb.Current();
     const uint32_t* srcs_sorted = vb.Current();
-
-    CKC(fem2d::dev_malloc((void**)&d_head, (size_t)np * 4)); CKC(fem2d::dev_malloc((void**)&d_scan, (size_t)np * 4));
     const unsigned gb = (np + 255) / 256;
     head_flags_kernel<<<gb, 256>>>(keys_sorted, np, d_head);
     CKC(cudaGetLastError());
@@ -175,27 +201,27 @@ int device_symbolic(Plan& P, std::string& err) {
     uint32_t nnz32 = 0;
     CKC(cudaMemcpy(&nnz32, d_scan + (np - 1), 4, cudaMemcpyDeviceToHost));
     P.nnz = nnz32; P.n_extra = (uint64_t)np - nnz32;
-    CKC(fem2d::dev_malloc((void**)&P.d_rows, (size_t)nnz32 * 4)); CKC(fem2d::dev_malloc((void**)&P.d_cols, (size_t)nnz32 * 4));
-    CKC(fem2d::dev_malloc((void**)&P.d_src1, (size_t)nnz32 * 4));
-    CKC(fem2d::dev_malloc((void**)&P.d_extra_slot, (P.n_extra ? P.n_extra : 1) * 4)); CKC(fem2d::dev_malloc((void**)&P.d_extra_src, (P.n_extra ? P.n_extra : 1) * 4));
-    CKC(fem2d::dev_malloc((void**)&P.d_extra_first, (P.n_extra ? P.n_extra : 1) * 4));
+
+    // ---- plan-owned pattern arena
+    Arena pa;
+    const size_t p_rows = pa.reserve((size_t)nnz32 * 4), p_cols = pa.reserve((size_t)nnz32 * 4), p_src1 = pa.reserve((size_t)nnz32 * 4);
+    const size_t p_es = pa.reserve(P.n_extra * 4), p_ex = pa.reserve(P.n_extra * 4), p_ef = pa.reserve(P.n_extra * 4);
+    CKC(dev_malloc(&P.d_pattern_arena, pa.size));
+    P.d_rows = at<uint32_t>(P.d_pattern_arena, p_rows); P.d_cols = at<uint32_t>(P.d_pattern_arena, p_cols); P.d_src1 = at<uint32_t>(P.d_pattern_arena, p_src1);
+    P.d_extra_slot = at<uint32_t>(P.d_pattern_arena, p_es); P.d_extra_src = at<uint32_t>(P.d_pattern_arena, p_ex); P.d_extra_first = at<uint32_t>(P.d_pattern_arena, p_ef);
     emit_pattern_kernel<<<gb, 256>>>(keys_sorted, srcs_sorted, d_head, d_scan, np, P.d_rows, P.d_cols, P.d_src1, P.d_extra_slot, P.d_extra_src, P.d_extra_first);
     CKC(cudaGetLastError());
     uint32_t stats[2] = {1, 0};
-    CKC(fem2d::dev_malloc((void**)&d_stats, 8));
-    CKC(cudaMemcpy(d_stats, stats, 8, cudaMemcpyHostToDevice));
+    CKC(cudaMemcpyAsync(d_stats, stats, 8, cudaMemcpyHostToDevice, nullptr));
     if (P.n_extra) {
         contrib_stats_kernel<<<(unsigned)((P.n_extra + 255) / 256), 256>>>(P.d_extra_slot, (uint32_t)P.n_extra, d_stats);
         CKC(cudaGetLastError());
     }
-    CKC(cudaMemcpy(stats, d_stats, 8, cudaMemcpyDeviceToHost));
+    CKC(cudaMemcpy(stats, d_stats, 8, cudaMemcpyDeviceToHost));   // synchronises the null stream: everything above is done
     P.max_contrib = stats[0]; P.n_multi = stats[1];
-
-    CKC(cudaDeviceSynchronize());
-    cleanup();
+    dev_free(scratch);
 #undef CKC
     for (int r = 0; r < Plan::RING; r++) for (int k = 0; k < 4; k++) CK(cudaEventCreate(&P.ev[r][k]));
-    CK(fem2d::dev_malloc((void**)&P.d_glq, 4 * 128 * sizeof(double)));
     return FEM2D_OK;
 }
 
@@ -215,9 +241,8 @@ void device_plan_release(Plan& P) {
     if (P.device < 0) return;
     cudaSetDevice(P.device);
     cudaDeviceSynchronize();   // numeric work may still be in flight on a caller stream
-    fem2d::dev_free(P.d_classes); fem2d::dev_free(P.d_lists); fem2d::dev_free(P.d_spec_i); fem2d::dev_free(P.d_spec_j); fem2d::dev_free(P.d_tables); fem2d::dev_free(P.d_grams); fem2d::dev_free(P.d_items);
-    fem2d::dev_free(P.d_rows); fem2d::dev_free(P.d_cols); fem2d::dev_free(P.d_src1); fem2d::dev_free(P.d_extra_slot); fem2d::dev_free(P.d_extra_src); fem2d::dev_free(P.d_extra_first);
-    fem2d::dev_free(P.d_V); fem2d::dev_free(P.d_tabs); fem2d::dev_free(P.d_glq); fem2d::dev_free(P.d_gram); fem2d::dev_free(P.d_dmma_items); fem2d::dev_free(P.d_out_a); fem2d::dev_free(P.d_out_b);
+    dev_free(P.d_desc_arena); dev_free(P.d_pattern_arena);   // descriptors, GLQ buffer, pattern, source map
+    dev_free(P.d_V); dev_free(P.d_tabs); dev_free(P.d_gram); dev_free(P.d_dmma_items); dev_free(P.d_out_a); dev_free(P.d_out_b);
     for (int r = 0; r < Plan::RING; r++) for (int k = 0; k < 4; k++) if (P.ev[r][k]) cudaEventDestroy(P.ev[r][k]);
 }
 

@@ -17,7 +17,9 @@ struct Plan {
     uint64_t n_multi = 0;
     uint64_t t_host_us = 0, t_device_us = 0;   // wall time of the two halves of the symbolic phase
 
-    // device-resident plan data
+    // device-resident plan data (sub-buffers of the two arenas below)
+    void* d_desc_arena = nullptr;
+    void* d_pattern_arena = nullptr;
     ClassDesc* d_classes = nullptr;
     ListDesc* d_lists = nullptr;
     uint8_t* d_spec_i = nullptr;
