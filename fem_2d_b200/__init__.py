@@ -568,7 +568,7 @@ def nalgebra_solve_gep(gep: GEP, target_eigenvalue: float) -> EigenPair:
 
 # ---- plan + assembly --------------------------------------------------------------------------------------------------------------
 INFO_KEYS = ["nnz_upper", "n_pairs", "n_blocks", "n_classes", "n_values", "n_multi", "max_contrib", "n_tables", "n_work_items",
-             "n_dofs", "n_lists", "n_extra", "symbolic_host_us", "symbolic_device_us", "tile_p"]
+             "n_dofs", "n_lists", "n_extra", "symbolic_host_us", "symbolic_device_us", "tile_p", "range_tiles_needed"]
 
 
 class Plan:
@@ -590,6 +590,12 @@ class Plan:
         if getattr(self, "_h", None):
             _L.fem2d_plan_free(self._h)
             self._h = None
+
+    def refresh_info(self) -> dict:
+        info = (C.c_uint64 * 16)()
+        _ck(_L.fem2d_plan_info(self._h, info))
+        self.info = {k: int(info[i]) for i, k in enumerate(INFO_KEYS)}
+        return self.info
 
     def pattern(self):
         rows = np.zeros(self.nnz, dtype=np.uint32); cols = np.zeros(self.nnz, dtype=np.uint32)

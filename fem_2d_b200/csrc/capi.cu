@@ -117,7 +117,7 @@ int fem2d_plan_info(const fem2d_plan* plan, uint64_t info[16]) {
     info[0] = p.nnz; info[1] = p.host.n_pairs; info[2] = p.host.blocks.size(); info[3] = p.host.classes.size();
     info[4] = p.host.n_values; info[5] = p.n_multi; info[6] = p.max_contrib; info[7] = p.host.tables.size();
     info[8] = p.host.items.size(); info[9] = p.host.n_dofs; info[10] = p.host.lists.size(); info[11] = p.n_extra;
-    info[12] = p.t_host_us; info[13] = p.t_device_us; info[14] = p.host.tile_p;
+    info[12] = p.t_host_us; info[13] = p.t_device_us; info[14] = p.host.tile_p; info[15] = p.range_mt_needed;
     return FEM2D_OK;
 }
 
@@ -196,7 +196,13 @@ int fem2d_assemble_device(fem2d_plan* plan, int basis_kind, int a_kind, int b_ki
     CKS(fem2d::launch_k1_tables(p, basis_kind, nu, nv, NO, NPT, s));
     p.last_launches[0] = 1;
     CKS(cudaEventRecord(ev[1], s));
-    if (mode == FEM2D_MODE_EXACT) CKS(fem2d::launch_k2_exact(p, nu, nv, NO, NPT, s, &p.last_launches[1]));
+    if (mode == FEM2D_MODE_EXACT) {
+        const fem2d::WorkItem* items = nullptr; uint32_t n_items = 0;
+        std::string ierr;
+        const int ist = fem2d::device_range_items(p, slot_begin, std::min<uint64_t>(slot_end, p.nnz), &items, &n_items, ierr);
+        if (ist != FEM2D_OK) return fail(ist, ierr);
+        CKS(fem2d::launch_k2_exact(p, items, n_items, nu, nv, NO, NPT, s, &p.last_launches[1]));
+    }
     else if (mode == FEM2D_MODE_SUMFACT) CKS(fem2d::launch_k2_sumfact(p, nu, nv, NO, NPT, s, &p.last_launches[1]));
     else CKS(fem2d::launch_k2_dmma(p, nu, nv, NO, NPT, s, &p.last_launches[1]));
     CKS(cudaEventRecord(ev[2], s));

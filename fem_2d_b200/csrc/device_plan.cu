@@ -141,6 +141,15 @@ int device_symbolic(Plan& P, std::string& err) {
     const size_t o_tabs = desc.reserve(H.tables.size() * sizeof(TableDesc)), o_grams = desc.reserve(H.grams.size() * sizeof(GramDesc));
     const size_t o_items = desc.reserve(H.items.size() * sizeof(WorkItem));
     const size_t o_glq = desc.reserve(4 * 128 * sizeof(double));
+    std::vector<uint32_t> h_voff(H.classes.size() + 1), h_mtoff(H.classes.size() + 1);
+    {
+        uint64_t mt = 0;
+        for (size_t c = 0; c < H.classes.size(); c++) { h_voff[c] = (uint32_t)H.classes[c].v_off; h_mtoff[c] = (uint32_t)mt; mt += H.classes[c].n_mt; }
+        h_voff[H.classes.size()] = (uint32_t)H.n_values; h_mtoff[H.classes.size()] = (uint32_t)mt;
+        P.total_mt = mt;
+        if (mt >= (1ull << 32)) { err = "too many micro-tiles"; return FEM2D_ERR_UNSUPPORTED; }
+    }
+    const size_t o_voff = desc.reserve(h_voff.size() * 4), o_mtoff = desc.reserve(h_mtoff.size() * 4);
     const size_t desc_plan_bytes = desc.size;                     // everything above lives as long as the plan
     const size_t o_blocks = desc.reserve(hb.size() * sizeof(DevBlock)), o_canon = desc.reserve(H.canon_dof.size() * 4);
     std::vector<unsigned char> blob(desc.size, 0);
@@ -149,6 +158,7 @@ int device_symbolic(Plan& P, std::string& err) {
     put(o_si, H.spec_i.data(), H.spec_i.size()); put(o_sj, H.spec_j.data(), H.spec_j.size());
     put(o_tabs, H.tables.data(), H.tables.size() * sizeof(TableDesc)); put(o_grams, H.grams.data(), H.grams.size() * sizeof(GramDesc));
     put(o_items, H.items.data(), H.items.size() * sizeof(WorkItem));
+    put(o_voff, h_voff.data(), h_voff.size() * 4); put(o_mtoff, h_mtoff.data(), h_mtoff.size() * 4);
     put(o_blocks, hb.data(), hb.size() * sizeof(DevBlock)); put(o_canon, H.canon_dof.data(), H.canon_dof.size() * 4);
 
     // ---- scratch arena
@@ -178,6 +188,7 @@ int device_symbolic(Plan& P, std::string& err) {
     P.d_spec_i = at<uint8_t>(P.d_desc_arena, o_si); P.d_spec_j = at<uint8_t>(P.d_desc_arena, o_sj);
     P.d_tables = at<TableDesc>(P.d_desc_arena, o_tabs); P.d_grams = at<GramDesc>(P.d_desc_arena, o_grams);
     P.d_items = at<WorkItem>(P.d_desc_arena, o_items); P.d_glq = at<double>(P.d_desc_arena, o_glq);
+    P.d_class_voff = at<uint32_t>(P.d_desc_arena, o_voff); P.d_class_mtoff = at<uint32_t>(P.d_desc_arena, o_mtoff);
     DevBlock* d_blocks = at<DevBlock>(scratch, s_desc + (o_blocks - desc_plan_bytes));
     uint32_t* d_canon = at<uint32_t>(scratch, s_desc + (o_canon - desc_plan_bytes));
     unsigned long long *d_keys = at<unsigned long long>(scratch, s_keys), *d_keys2 = at<unsigned long long>(scratch, s_keys2);
@@ -225,6 +236,114 @@ int device_symbolic(Plan& P, std::string& err) {
     return FEM2D_OK;
 }
 
+namespace {
+// Marks the micro-tile that produces V[v]: inverse of the integrator's tile enumeration (plan_types.h make_subblocks).
+__device__ void mark_source(uint32_t v, const ClassDesc* classes, const ListDesc* lists, const uint32_t* voff, const uint32_t* mtoff, uint32_t n_classes,
+                            uint32_t tp, unsigned char* flags) {
+    uint32_t lo = 0, hi = n_classes;                      // last class with voff <= v
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (voff[mid] <= v) lo = mid; else hi = mid; }
+    const ClassDesc& c = classes[lo];
+    const uint32_t nP = lists[c.listP].n, nUP = lists[c.listP].nU, nQ = lists[c.listQ].n, nUQ = lists[c.listQ].nU;
+    const uint32_t t = v - voff[lo], a = t / nQ, b = t - a * nQ;
+    const SubBlocks sb = make_subblocks(nP, nUP, nQ, nUQ, c.local, tp);
+    const uint32_t sub = (a < nUP ? 0u : 2u) + (b < nUQ ? 0u : 1u);
+    uint32_t idx = 0;
+    for (uint32_t k = 0; k < sub; k++) idx += sb.cnt[k];
+    const uint32_t rt = (a - sb.row0[sub]) / tp, ct = (b - sb.col0[sub]) / MT_Q, nct = mt_div_up(sb.cols[sub], MT_Q);
+    if (sb.tri[sub]) {
+        for (uint32_t q = 0; q < rt; q++) { const uint32_t l0 = q * tp / MT_Q; if (nct > l0) idx += nct - l0; }
+        idx += ct - rt * tp / MT_Q;
+    } else idx += rt * nct + ct;
+    flags[mtoff[lo] + idx] = 1;
+}
+
+__global__ void mark_tiles_kernel(const uint32_t* __restrict__ src1, const uint32_t* __restrict__ extra_slot, const uint32_t* __restrict__ extra_src,
+                                  const uint32_t* __restrict__ extra_first, unsigned long long n_extra, unsigned long long begin, unsigned long long end,
+                                  const ClassDesc* classes, const ListDesc* lists, const uint32_t* voff, const uint32_t* mtoff, uint32_t n_classes,
+                                  uint32_t tp, unsigned char* flags) {
+    const unsigned long long slot = begin + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (slot >= end) return;
+    const uint32_t s = src1[slot];
+    if (!(s & 0x80000000u)) { mark_source(s, classes, lists, voff, mtoff, n_classes, tp, flags); return; }
+    unsigned long long k = s & 0x7fffffffu;
+    mark_source(extra_first[k], classes, lists, voff, mtoff, n_classes, tp, flags);
+    do { mark_source(extra_src[k], classes, lists, voff, mtoff, n_classes, tp, flags); k++; } while (k < n_extra && extra_slot[k] == slot);
+}
+}  // namespace
+
+int device_range_items(Plan& P, uint64_t begin, uint64_t end, const WorkItem** d_items, uint32_t* n_items, std::string& err) {
+    const bool full = begin == 0 && end >= P.nnz;
+    // restricting is pointless when the whole integrator is a single wave of CTAs anyway
+    if (full || P.total_mt < (uint64_t)4 * 148 * K2_THREADS) { *d_items = P.d_items; *n_items = (uint32_t)P.host.items.size(); return FEM2D_OK; }
+    if (P.d_range_items && begin == P.range_begin && end == P.range_end) { *d_items = P.d_range_items; *n_items = P.n_range_items; return FEM2D_OK; }
+    CK(cudaSetDevice(P.device));
+    unsigned char* d_flags = nullptr;
+    CK(dev_malloc((void**)&d_flags, P.total_mt));
+    CK(cudaMemsetAsync(d_flags, 0, P.total_mt, nullptr));
+    if (end > begin) {
+        mark_tiles_kernel<<<(unsigned)((end - begin + 255) / 256), 256>>>(P.d_src1, P.d_extra_slot, P.d_extra_src, P.d_extra_first, P.n_extra, begin, end,
+                                                                           P.d_classes, P.d_lists, P.d_class_voff, P.d_class_mtoff,
+                                                                           (uint32_t)P.host.classes.size(), P.host.tile_p, d_flags);
+    }
+    std::vector<unsigned char> flags(P.total_mt);
+    cudaError_t e = cudaMemcpy(flags.data(), d_flags, P.total_mt, cudaMemcpyDeviceToHost);
+    dev_free(d_flags);
+    if (e != cudaSuccess) { err = cudaGetErrorString(e); return FEM2D_ERR_CUDA; }
+    // items: per class, the runs of needed tiles (gaps of up to 2 tiles are bridged) packed into CTAs of <= ITEM_MAX_RANGES runs and
+    // <= 2 * K2_THREADS tiles; every item records which function columns its tiles touch so it stages only those.
+    std::vector<WorkItem> items;
+    const uint32_t cap = 2 * K2_THREADS, gap = 2, tp = P.host.tile_p;
+    uint64_t needed = 0, off = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> runs, cur;
+    for (uint32_t c = 0; c < P.host.classes.size(); c++) {
+        const ClassDesc& cd = P.host.classes[c];
+        const uint32_t n = cd.n_mt;
+        const unsigned char* f = flags.data() + off;
+        off += n;
+        runs.clear();
+        for (uint32_t k = 0; k < n;) {
+            if (!f[k]) { k++; continue; }
+            uint32_t b = k, last = k;
+            while (k < n && k - b < cap && (f[k] || k - last <= gap)) { if (f[k]) last = k; k++; }
+            runs.push_back({b, last - b + 1});
+            k = last + 1;
+        }
+        if (runs.empty()) continue;
+        const ListDesc& LP = P.host.lists[cd.listP]; const ListDesc& LQ = P.host.lists[cd.listQ];
+        const SubBlocks sb = make_subblocks(LP.n, LP.nU, LQ.n, LQ.nU, cd.local, tp);
+        auto flush = [&]() {
+            if (cur.empty()) return;
+            uint32_t cols[2][2][2] = {{{UINT32_MAX, 0}, {UINT32_MAX, 0}}, {{UINT32_MAX, 0}, {UINT32_MAX, 0}}};
+            for (auto& r : cur)
+                for (uint32_t t = r.first; t < r.first + r.second; t++) {
+                    uint32_t sub, rt, ct;
+                    decode_tile(sb, t, tp, sub, rt, ct);
+                    const uint32_t r0 = rt * tp, r1 = std::min(r0 + tp, sb.rows[sub]), c0 = ct * MT_Q, c1 = std::min<uint32_t>(c0 + MT_Q, sb.cols[sub]);
+                    uint32_t* pr = cols[0][sub >= 2]; uint32_t* qc = cols[1][sub & 1];
+                    pr[0] = std::min(pr[0], r0); pr[1] = std::max(pr[1], r1);
+                    qc[0] = std::min(qc[0], c0); qc[1] = std::max(qc[1], c1);
+                }
+            for (auto& sd : cols) for (auto& g : sd) if (g[0] == UINT32_MAX) g[0] = g[1] = 0;
+            items.push_back(make_item(P.host, c, cur, cols));
+            needed += items.back().mt_count;
+            cur.clear();
+        };
+        uint32_t cnt = 0;
+        for (auto& r : runs) {
+            if (cur.size() == ITEM_MAX_RANGES || cnt + r.second > cap) { flush(); cnt = 0; }
+            cur.push_back(r); cnt += r.second;
+        }
+        flush();
+    }
+    std::stable_sort(items.begin(), items.end(), [](const WorkItem& x, const WorkItem& y) { return x.mt_count > y.mt_count; });
+    dev_free(P.d_range_items); P.d_range_items = nullptr;
+    CK(dev_malloc((void**)&P.d_range_items, std::max<size_t>(items.size(), 1) * sizeof(WorkItem)));
+    CK(cudaMemcpy(P.d_range_items, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+    P.n_range_items = (uint32_t)items.size(); P.range_begin = begin; P.range_end = end; P.range_mt_needed = needed;
+    *d_items = P.d_range_items; *n_items = P.n_range_items;
+    return FEM2D_OK;
+}
+
 int device_row_block_bounds(const Plan& P, uint32_t world, uint64_t* bounds, std::string& err) {
     if (world == 0 || world > 1023) { err = "world out of range"; return FEM2D_ERR_BAD_ARGUMENT; }
     CK(cudaSetDevice(P.device));
@@ -242,6 +361,7 @@ void device_plan_release(Plan& P) {
     cudaSetDevice(P.device);
     cudaDeviceSynchronize();   // numeric work may still be in flight on a caller stream
     dev_free(P.d_desc_arena); dev_free(P.d_pattern_arena);   // descriptors, GLQ buffer, pattern, source map
+    dev_free(P.d_range_items);
     dev_free(P.d_V); dev_free(P.d_tabs); dev_free(P.d_gram); dev_free(P.d_dmma_items); dev_free(P.d_out_a); dev_free(P.d_out_b);
     for (int r = 0; r < Plan::RING; r++) for (int k = 0; k < 4; k++) if (P.ev[r][k]) cudaEventDestroy(P.ev[r][k]);
 }

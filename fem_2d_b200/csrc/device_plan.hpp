@@ -42,6 +42,14 @@ struct Plan {
     double h_glq[512] = {};     // host copy of what d_glq holds (skips the upload when the caller passes the same nodes again)
     bool glq_valid = false;
     double* d_gram = nullptr;   // fast modes scratch
+    uint32_t* d_class_voff = nullptr;    // [n_classes + 1] first V entry of each class (desc arena)
+    uint32_t* d_class_mtoff = nullptr;   // [n_classes + 1] first micro-tile of each class in the plan-wide tile numbering
+    uint64_t total_mt = 0;
+    // row-block restricted item list (multi-GPU sharding of the integrator), valid for [range_begin, range_end)
+    uint64_t range_begin = 0, range_end = 0;
+    WorkItem* d_range_items = nullptr;
+    uint32_t n_range_items = 0;
+    uint64_t range_mt_needed = 0;
     void* d_dmma_items = nullptr;   // tile work items of the DMMA integrator (built on first use)
     uint32_t n_dmma_items = 0;
     size_t gram_capacity = 0;
@@ -67,11 +75,14 @@ constexpr uint32_t MAX_GLQ = 128;   // default_ngq(20) = 128 (basis.rs:172-177)
 // device_plan.cu
 int device_symbolic(Plan& plan, std::string& err);
 int device_row_block_bounds(const Plan& plan, uint32_t world, uint64_t* bounds, std::string& err);
+// Work items of the exact integrator restricted to the micro-tiles that the slots [begin, end) read (cached per plan for the last
+// range; the full item list is returned for the full range and for plans too small to be worth restricting).
+int device_range_items(Plan& plan, uint64_t begin, uint64_t end, const WorkItem** d_items, uint32_t* n_items, std::string& err);
 void device_plan_release(Plan& plan);
 
 // kernels_exact.cu  (compiled with -fmad=false)
 cudaError_t launch_k1_tables(const Plan& plan, int basis_kind, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st);
-cudaError_t launch_k2_exact(const Plan& plan, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches);
+cudaError_t launch_k2_exact(const Plan& plan, const WorkItem* d_items, uint32_t n_items, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches);
 cudaError_t fp64_peak(int kind, double* gflops);
 
 // kernels_fast.cu

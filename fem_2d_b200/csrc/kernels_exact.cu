@@ -148,14 +148,10 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g)
         const bool active = round0 + threadIdx.x < it.mt_count;
         uint32_t sub = 0, row0 = 0, col0 = 0, row_end = 0, col_end = 0, prow = 0, pcol = 0;
         if (active) {
-            uint32_t idx = it.mt_begin + round0 + threadIdx.x;
-            while (idx >= sb.cnt[sub]) { idx -= sb.cnt[sub]; sub++; }
-            const uint32_t nct = mt_div_up(sb.cols[sub], MT_Q);
+            uint32_t li = round0 + threadIdx.x, r = 0;
+            while (li >= it.rcount[r]) { li -= it.rcount[r]; r++; }        // which of the item's tile ranges
             uint32_t rt, ct;
-            if (sb.tri[sub]) {
-                rt = 0;
-                for (;;) { const uint32_t lo = rt * TP / MT_Q; const uint32_t cnt = nct > lo ? nct - lo : 0; if (idx < cnt) { ct = lo + idx; break; } idx -= cnt; rt++; }
-            } else { rt = idx / nct; ct = idx - rt * nct; }
+            decode_tile(sb, it.rbegin[r] + li, TP, sub, rt, ct);
             row0 = sb.row0[sub] + rt * TP; col0 = sb.col0[sub] + ct * MT_Q;
             row_end = sb.row0[sub] + sb.rows[sub]; col_end = sb.col0[sub] + sb.cols[sub];
             prow = (sub >= 2 ? pad4(nUP) - nUP : 0) + row0;            // slab column of the canonical row index
@@ -186,9 +182,11 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g)
                     const double ps0 = side ? c.su : 1.0, ps1 = side ? c.sv : 1.0;
                     double* sC = side ? s_CQ : s_CP; double* sF = side ? s_FQ : s_FP;
                     const uint32_t padU = pad4(nUF);
-                    const uint32_t ntask = (m_hi - m_lo + 1) * stride;
+                    for (int grp = 0; grp < 2; grp++) {
+                    const uint32_t c_lo = it.stage[side][grp][0], c_w = it.stage[side][grp][1] - c_lo;   // only the functions this item's tiles touch
+                    const uint32_t ntask = (m_hi - m_lo + 1) * c_w;
                     for (uint32_t t = threadIdx.x; t < ntask; t += blockDim.x) {
-                        const uint32_t mi = t / stride, col = t - mi * stride, m = m_lo + mi;
+                        const uint32_t mi = t / c_w, col = c_lo + (t - mi * c_w), m = m_lo + mi;
                         const uint32_t n_lo = (m == m_lo) ? pt0 - m_lo * nv : 0u;
                         const uint32_t n_hi = (m == m_hi) ? pt0 + cn - 1 - m_hi * nv : nv - 1;
                         double* dC = sC + (size_t)(m * nv + n_lo - pt0) * stride + col;
@@ -215,6 +213,7 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g)
                         } else {
                             for (uint32_t n = n_lo; n <= n_hi; n++, dC += stride, dF += stride) { *dC = 0.0; *dF = 0.0; }
                         }
+                    }
                     }
                 }
                 __syncthreads();
@@ -283,8 +282,8 @@ cudaError_t launch_k1_tables(const Plan& P, int basis_kind, uint32_t nu, uint32_
     return cudaGetLastError();
 }
 
-cudaError_t launch_k2_exact(const Plan& P, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches) {
-    if (P.host.items.empty()) return cudaSuccess;
+cudaError_t launch_k2_exact(const Plan& P, const WorkItem* d_items, uint32_t n_items, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches) {
+    if (n_items == 0) return cudaSuccess;
     // shared memory: 256 doubles of weights + chunk * (C and F slabs of both sides).  Prefer <= ~100 KB so two CTAs share an SM.
     const uint32_t max_stride = P.host.max_slab_stride;   // widest class: pad4(U) + pad4(V) functions of P (+ of Q unless local)
     const size_t per_pt = (size_t)max_stride * 2 * sizeof(double);
@@ -302,9 +301,9 @@ cudaError_t launch_k2_exact(const Plan& P, uint32_t nu, uint32_t nv, uint32_t NO
         if (e != cudaSuccess) return e;
         smem_set[P.device] = smem;
     }
-    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, P.d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, chunk};
-    if (P.host.tile_p == 1) k2_exact_kernel<1><<<(unsigned)P.host.items.size(), K2_THREADS, smem, st>>>(g);
-    else k2_exact_kernel<4><<<(unsigned)P.host.items.size(), K2_THREADS, smem, st>>>(g);
+    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, chunk};
+    if (P.host.tile_p == 1) k2_exact_kernel<1><<<n_items, K2_THREADS, smem, st>>>(g);
+    else k2_exact_kernel<4><<<n_items, K2_THREADS, smem, st>>>(g);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

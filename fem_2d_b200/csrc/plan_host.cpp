@@ -82,6 +82,32 @@ int elem_geometry(const fem2d_domain_view* v, std::vector<double>& dx, std::vect
     return FEM2D_OK;
 }
 
+// Builds a work item from runs of micro-tiles.  `cols` (optional): [side][group][min col, max col + 1) in canonical function
+// indices actually touched; nullptr = stage everything.
+WorkItem make_item(const HostPlan& P, uint32_t cls, const std::vector<std::pair<uint32_t, uint32_t>>& ranges, const uint32_t (*cols)[2][2]) {
+    WorkItem it; std::memset(&it, 0, sizeof(it));
+    it.cls = cls; it.n_ranges = (uint32_t)ranges.size();
+    for (size_t k = 0; k < ranges.size(); k++) { it.rbegin[k] = ranges[k].first; it.rcount[k] = (uint16_t)ranges[k].second; it.mt_count += ranges[k].second; }
+    const ClassDesc& c = P.classes[cls];
+    const ListDesc* L[2] = {&P.lists[c.listP], &P.lists[c.listQ]};
+    for (int side = 0; side < 2; side++) {
+        const uint32_t nU = L[side]->nU, nV = L[side]->n - nU, padU = slab_pad4(nU);
+        uint32_t ub = 0, ue = nU, vb = 0, ve = nV;                      // function ranges inside each direction group
+        if (cols) { ub = cols[side][0][0]; ue = cols[side][0][1]; vb = cols[side][1][0]; ve = cols[side][1][1]; }
+        // slab columns, rounded outwards to the 4-wide tile rows (the padding columns are staged as zeros)
+        it.stage[side][0][0] = (uint16_t)(ue > ub ? (ub & ~3u) : 0); it.stage[side][0][1] = (uint16_t)(ue > ub ? std::min(slab_pad4(ue), padU) : 0);
+        it.stage[side][1][0] = (uint16_t)(ve > vb ? padU + (vb & ~3u) : 0); it.stage[side][1][1] = (uint16_t)(ve > vb ? padU + std::min(slab_pad4(ve), slab_pad4(nV)) : 0);
+    }
+    if (c.local) {   // P and Q share one slab pair: stage the union through the P side
+        for (int g = 0; g < 2; g++) {
+            const uint16_t pb = it.stage[0][g][0], pe = it.stage[0][g][1], qb = it.stage[1][g][0], qe = it.stage[1][g][1];
+            if (qe > qb) { it.stage[0][g][0] = pe > pb ? std::min(pb, qb) : qb; it.stage[0][g][1] = pe > pb ? std::max(pe, qe) : qe; }
+            it.stage[1][g][0] = it.stage[1][g][1] = 0;
+        }
+    }
+    return it;
+}
+
 int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::string& err) {
     if (!v) { err = "null view"; return FEM2D_ERR_BAD_ARGUMENT; }
     // Reference error order: continuity condition, then empty DoF set (galerkin.rs:42-50).
@@ -340,7 +366,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
         const uint32_t n_items = (n_mt + cap - 1) / cap;
         for (uint32_t k = 0; k < n_items; k++) {   // equal shares
             const uint32_t b = (uint32_t)((uint64_t)n_mt * k / n_items), e = (uint32_t)((uint64_t)n_mt * (k + 1) / n_items);
-            if (e > b) P.items.push_back(WorkItem{c, b, e - b, 0});
+            if (e > b) P.items.push_back(make_item(P, c, {{b, e - b}}, nullptr));
         }
     }
     return FEM2D_OK;

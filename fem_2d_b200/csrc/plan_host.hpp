@@ -34,6 +34,8 @@ struct HostPlan {
 // dx_du, dy_dv of every Elem (element.rs:33-50), in the reference's operation order.
 int elem_geometry(const fem2d_domain_view* view, std::vector<double>& dx, std::vector<double>& dy, std::string& err);
 
+WorkItem make_item(const HostPlan& plan, uint32_t cls, const std::vector<std::pair<uint32_t, uint32_t>>& ranges, const uint32_t (*cols)[2][2]);
+
 // Returns FEM2D_OK or a status from include/fem2d.h; err receives a detail message.
 int build_host_plan(const fem2d_domain_view* view, bool dedupe, HostPlan& plan, std::string& err);
 

@@ -52,11 +52,17 @@ struct GramDesc {
     uint32_t axis, pad;
 };
 
+// One CTA of the exact integrator: up to ITEM_MAX_RANGES runs of consecutive micro-tiles of one class, plus the slab columns
+// (functions) those tiles touch, so that a CTA working on a corner of a class stages only that corner's functions.
+constexpr int ITEM_MAX_RANGES = 6;
 struct WorkItem {
     uint32_t cls;
-    uint32_t mt_begin;   // first micro-tile handled by this item
-    uint32_t mt_count;   // <= K2_ROUNDS * K2_THREADS
+    uint32_t mt_count;                    // tiles of all ranges together, <= K2_ROUNDS * K2_THREADS
+    uint32_t n_ranges;
     uint32_t pad;
+    uint32_t rbegin[ITEM_MAX_RANGES];     // first micro-tile of each range (class-local numbering)
+    uint16_t rcount[ITEM_MAX_RANGES];
+    uint16_t stage[2][2][2];              // [side: P, Q][direction group: U, V][begin, end): slab columns to stage
 };
 
 struct BlockDesc {
@@ -101,5 +107,17 @@ FEM2D_HD inline SubBlocks make_subblocks(uint32_t nP, uint32_t nUP, uint32_t nQ,
     }
     return s;
 }
+
+// micro-tile index (class-local) -> sub-block, row tile, column tile
+FEM2D_HD inline void decode_tile(const SubBlocks& sb, uint32_t idx, uint32_t tp, uint32_t& sub, uint32_t& rt, uint32_t& ct) {
+    sub = 0;
+    while (sub < 3 && idx >= sb.cnt[sub]) { idx -= sb.cnt[sub]; sub++; }
+    const uint32_t nct = mt_div_up(sb.cols[sub], MT_Q);
+    if (sb.tri[sub]) {
+        rt = 0;
+        for (;;) { const uint32_t lo = rt * tp / MT_Q; const uint32_t cnt = nct > lo ? nct - lo : 0; if (idx < cnt) { ct = lo + idx; break; } idx -= cnt; rt++; }
+    } else { rt = idx / nct; ct = idx - rt * nct; }
+}
+FEM2D_HD inline uint32_t slab_pad4(uint32_t x) { return (x + 3u) & ~3u; }
 
 }  // namespace fem2d
