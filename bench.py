@@ -207,17 +207,15 @@ def run_ours(args):
     glq = (F.gauss_quadrature_points(w["glq"]), F.gauss_quadrature_points(w["glq"]))
     plan = F.Plan(view, device=local_rank, dedupe=bool(args.dedupe))
     nnz = plan.nnz
-    bounds = plan.row_blocks(world)
-    s0, s1 = int(bounds[rank]), int(bounds[rank + 1])
-    if args.emulate_world > 1:   # tuning aid: time one rank's row block of an N-rank run on a single GPU
-        eb = plan.row_blocks(args.emulate_world)
-        s0, s1 = int(eb[args.emulate_rank]), int(eb[args.emulate_rank + 1])
+    ranges = rank_ranges(plan, world, rank)
+    if args.emulate_world > 1:   # tuning aid: time one rank's share of an N-rank run on a single GPU
+        ranges = rank_ranges(plan, args.emulate_world, args.emulate_rank)
     stream = torch.cuda.current_stream()
     d_a = torch.empty(nnz, dtype=torch.float64, device=dev)
     d_b = torch.empty(nnz, dtype=torch.float64, device=dev)
 
     def step():
-        plan.assemble_device(glq, d_a.data_ptr(), d_b.data_ptr(), mode=mode, slot_begin=s0, slot_end=s1, stream=stream.cuda_stream)
+        plan.assemble_device_ranges(glq, d_a.data_ptr(), d_b.data_ptr(), ranges, mode=mode, stream=stream.cuda_stream)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -250,7 +248,7 @@ def run_ours(args):
 
     peaks, peak_kind = _peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    n_slots = s1 - s0
+    n_slots = sum(e - b for b, e in ranges)
     # K3 algorithmic bytes: 16 B written per slot (A and B) + the 4 B source index it reads (SURVEY.md 8d budgets 4 B per pair
     # for a push scatter; the gather form reads one index per slot)
     alg_bytes_k3 = 16.0 * n_slots + 4.0 * n_slots
@@ -309,7 +307,7 @@ def run_ours(args):
                        "mode": args.mode, "dedupe": int(args.dedupe), "n_dofs": info["n_dofs"], "nnz_upper_per_matrix": nnz, "n_pairs": info["n_pairs"],
                        "n_classes": info["n_classes"], "nnz_counted": "2 x nnz_upper (A and B)",
                        "l2_policy": "no flush: each step streams > 0.92 GB (A/B value arrays + source map) >> 126 MB L2",
-                       "parallelism": f"row-block x{world}" if world > 1 else "single GPU"},
+                       "parallelism": f"row blocks x{world} (Elem-type rows + edge-type rows per rank), no collective" if world > 1 else "single GPU"},
             "phases_ms": {"sampler_k1": float(k1_ms), "integrator_k2": float(k2_ms), "scatter_k3": float(k3_ms), "sum": float(tot_ms)},
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
@@ -322,6 +320,15 @@ def run_ours(args):
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def rank_ranges(plan, world, rank):
+    """Slot ranges owned by `rank`: everything for one rank; otherwise its block of the single-Elem (Elem-type) rows and its block of
+    the shared (edge-type) rows (fem2d_plan_row_blocks_split)."""
+    if world == 1:
+        return [(0, plan.nnz)]
+    b1, b2 = plan.row_blocks_split(world)
+    return [(int(b1[rank]), int(b1[rank + 1])), (int(b2[rank]), int(b2[rank + 1]))]
 
 
 def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz):
@@ -347,10 +354,9 @@ def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz):
     pview = F.DomainView(cv, keepalive=pinned)
     # probe sizes once (not timed)
     p0 = F.Plan(pview, device=local_rank, dedupe=bool(args.dedupe))
-    bounds = p0.row_blocks(world)
-    s0, s1 = int(bounds[rank]), int(bounds[rank + 1])
+    ranges = rank_ranges(p0, world, rank)
     del p0
-    n = s1 - s0
+    n = sum(e - b for b, e in ranges)
     h_rows = torch.empty(n, dtype=torch.int32).pin_memory()
     h_cols = torch.empty(n, dtype=torch.int32).pin_memory()
     h_a = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -363,7 +369,7 @@ def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz):
         t0 = time.perf_counter()
         plan = F.Plan(pview, device=local_rank, dedupe=bool(args.dedupe))       # symbolic phase (H2D of the view-derived arrays inside)
         t1 = time.perf_counter()
-        plan.assemble_range_into(glq, s0, s1, h_a.data_ptr(), h_b.data_ptr(), h_rows.data_ptr(), h_cols.data_ptr(), mode=mode)   # numeric + D2H, synchronous
+        plan.assemble_ranges_into(glq, ranges, h_a.data_ptr(), h_b.data_ptr(), h_rows.data_ptr(), h_cols.data_ptr(), mode=mode)   # numeric + D2H, synchronous
         t2 = time.perf_counter()
         info = plan.info
         del plan

@@ -73,7 +73,7 @@ class _View(C.Structure):
 # Every symbol declared in include/fem2d.h and include/fem2d_host.h (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "fem2d_symbolic", "fem2d_plan_free", "fem2d_plan_info", "fem2d_plan_pattern", "fem2d_plan_pattern_device",
-    "fem2d_assemble_device", "fem2d_assemble", "fem2d_galerkin_sample_gep_hcurl", "fem2d_plan_row_blocks",
+    "fem2d_assemble_device", "fem2d_assemble_device_ranges", "fem2d_plan_row_blocks_split", "fem2d_assemble_ranges", "fem2d_assemble", "fem2d_galerkin_sample_gep_hcurl", "fem2d_plan_row_blocks",
     "fem2d_plan_last_timing", "fem2d_plan_timing", "fem2d_assemble_range", "fem2d_host_alloc", "fem2d_host_free", "fem2d_xy_fields", "fem2d_fp64_peak",
     "fem2d_device_count", "fem2d_status_string", "fem2d_last_error", "fem2d_version",
 ]
@@ -607,6 +607,20 @@ class Plan:
         _ck(_L.fem2d_plan_row_blocks(self._h, C.c_uint32(world), _p(b, C.c_uint64)))
         return b
 
+    def row_blocks_split(self, world: int):
+        """(bounds of the single-Elem rows, bounds of the shared/edge-type rows), see fem2d_plan_row_blocks_split."""
+        b1 = np.zeros(world + 1, dtype=np.uint64); b2 = np.zeros(world + 1, dtype=np.uint64)
+        _ck(_L.fem2d_plan_row_blocks_split(self._h, C.c_uint32(world), _p(b1, C.c_uint64), _p(b2, C.c_uint64)))
+        return b1, b2
+
+    def assemble_device_ranges(self, glq, d_a: int, d_b: int, ranges, basis=HierPoly, a=CurlCurl, b=L2Inner, mode: int = MODE_EXACT, stream: int = 0):
+        """fem2d_assemble_device_ranges: `ranges` = up to 4 (slot_begin, slot_end) pairs handled by one integrator + one scatter launch."""
+        up, uw, vp, vw = self._glq_args(glq)
+        bg = np.array([r[0] for r in ranges], dtype=np.uint64); en = np.array([r[1] for r in ranges], dtype=np.uint64)
+        _ck(_L.fem2d_assemble_device_ranges(self._h, basis.kind, a.kind, b.kind, int(mode), _p(up, C.c_double), _p(uw, C.c_double), C.c_uint32(len(up)),
+                                            _p(vp, C.c_double), _p(vw, C.c_double), C.c_uint32(len(vp)), C.c_uint32(len(ranges)),
+                                            _p(bg, C.c_uint64), _p(en, C.c_uint64), C.c_void_p(d_a), C.c_void_p(d_b), C.c_void_p(stream or None)))
+
     @staticmethod
     def _glq_args(glq):
         (up, uw), (vp, vw) = glq
@@ -648,6 +662,15 @@ class Plan:
         _ck(_L.fem2d_assemble_range(self._h, basis.kind, a.kind, b.kind, int(mode), _p(up, C.c_double), _p(uw, C.c_double), C.c_uint32(len(up)),
                                     _p(vp, C.c_double), _p(vw, C.c_double), C.c_uint32(len(vp)), C.c_uint64(slot_begin), C.c_uint64(slot_end),
                                     C.c_void_p(rows_ptr or None), C.c_void_p(cols_ptr or None), C.c_void_p(a_ptr), C.c_void_p(b_ptr)))
+
+    def assemble_ranges_into(self, glq, ranges, a_ptr: int, b_ptr: int, rows_ptr: int = 0, cols_ptr: int = 0, basis=HierPoly, a=CurlCurl, b=L2Inner,
+                             mode: int = MODE_EXACT):
+        """fem2d_assemble_ranges with raw HOST pointers: numeric phase + D2H of the ranges, back to back."""
+        up, uw, vp, vw = self._glq_args(glq)
+        bg = np.array([r[0] for r in ranges], dtype=np.uint64); en = np.array([r[1] for r in ranges], dtype=np.uint64)
+        _ck(_L.fem2d_assemble_ranges(self._h, basis.kind, a.kind, b.kind, int(mode), _p(up, C.c_double), _p(uw, C.c_double), C.c_uint32(len(up)),
+                                     _p(vp, C.c_double), _p(vw, C.c_double), C.c_uint32(len(vp)), C.c_uint32(len(ranges)), _p(bg, C.c_uint64),
+                                     _p(en, C.c_uint64), C.c_void_p(rows_ptr or None), C.c_void_p(cols_ptr or None), C.c_void_p(a_ptr), C.c_void_p(b_ptr)))
 
     def last_timing(self, calls_back: int = 0):
         ms = (C.c_float * 4)(); ln = (C.c_uint32 * 4)()

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/fem2d.h"
 #include "device_plan.hpp"
@@ -161,12 +162,48 @@ int fem2d_plan_row_blocks(const fem2d_plan* plan, uint32_t world, uint64_t* boun
     return st == FEM2D_OK ? st : fail(st, err);
 }
 
+int fem2d_plan_row_blocks_split(const fem2d_plan* plan, uint32_t world, uint64_t* bounds_single, uint64_t* bounds_shared) {
+    if (!plan || !bounds_single || !bounds_shared || world == 0) return fail(FEM2D_ERR_BAD_ARGUMENT, "bad argument");
+    const fem2d::Plan& p = plan->p;
+    // first DoF carried by more than one Elem: the reference numbers all single-Elem (Elem-type) DoFs first (domain.rs:83-96)
+    std::vector<unsigned char> seen(p.host.n_dofs, 0);
+    uint32_t first_shared = p.host.n_dofs;
+    for (uint32_t d : p.host.canon_dof) { if (seen[d]) first_shared = std::min(first_shared, d); seen[d] = 1; }
+    uint64_t split = p.nnz;
+    if (p.device < 0) {
+        const auto& rows = p.host_pattern.rows;
+        split = std::lower_bound(rows.begin(), rows.end(), first_shared) - rows.begin();
+        auto part = [&](uint64_t lo, uint64_t hi, uint64_t* b) {
+            b[0] = lo; b[world] = hi;
+            for (uint32_t r = 1; r < world; r++) {
+                uint64_t s = lo + (hi - lo) * r / world;
+                while (s < hi && s > lo && rows[s] == rows[s - 1]) s++;
+                b[r] = s;
+            }
+        };
+        part(0, split, bounds_single); part(split, p.nnz, bounds_shared);
+        return FEM2D_OK;
+    }
+    std::string err;
+    int st = fem2d::device_first_slot_of_row(p, first_shared, &split, err);
+    if (st == FEM2D_OK) st = fem2d::device_row_block_bounds_range(p, 0, split, world, bounds_single, err);
+    if (st == FEM2D_OK) st = fem2d::device_row_block_bounds_range(p, split, p.nnz, world, bounds_shared, err);
+    return st == FEM2D_OK ? st : fail(st, err);
+}
+
 int fem2d_assemble_device(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w, uint32_t nu,
                           const double* v_pts, const double* v_w, uint32_t nv, uint64_t slot_begin, uint64_t slot_end, double* d_a, double* d_b,
                           void* stream) {
+    return fem2d_assemble_device_ranges(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, 1, &slot_begin, &slot_end, d_a, d_b, stream);
+}
+
+int fem2d_assemble_device_ranges(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w, uint32_t nu,
+                                 const double* v_pts, const double* v_w, uint32_t nv, uint32_t n_ranges, const uint64_t* slot_begins,
+                                 const uint64_t* slot_ends, double* d_a, double* d_b, void* stream) {
     int st = check_numeric_args(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv);
     if (st != FEM2D_OK) return st;
     if (!d_a || !d_b) return fail(FEM2D_ERR_BAD_ARGUMENT, "null output pointer");
+    if (n_ranges == 0 || n_ranges > fem2d::MAX_SLOT_RANGES || !slot_begins || !slot_ends) return fail(FEM2D_ERR_BAD_ARGUMENT, "1..4 slot ranges expected");
     fem2d::Plan& p = plan->p;
     cudaStream_t s = (cudaStream_t)stream;
     CKS(cudaSetDevice(p.device));
@@ -199,14 +236,14 @@ int fem2d_assemble_device(fem2d_plan* plan, int basis_kind, int a_kind, int b_ki
     if (mode == FEM2D_MODE_EXACT) {
         const fem2d::WorkItem* items = nullptr; uint32_t n_items = 0;
         std::string ierr;
-        const int ist = fem2d::device_range_items(p, slot_begin, std::min<uint64_t>(slot_end, p.nnz), &items, &n_items, ierr);
+        const int ist = fem2d::device_range_items(p, n_ranges, slot_begins, slot_ends, &items, &n_items, ierr);
         if (ist != FEM2D_OK) return fail(ist, ierr);
         CKS(fem2d::launch_k2_exact(p, items, n_items, nu, nv, NO, NPT, s, &p.last_launches[1]));
     }
     else if (mode == FEM2D_MODE_SUMFACT) CKS(fem2d::launch_k2_sumfact(p, nu, nv, NO, NPT, s, &p.last_launches[1]));
     else CKS(fem2d::launch_k2_dmma(p, nu, nv, NO, NPT, s, &p.last_launches[1]));
     CKS(cudaEventRecord(ev[2], s));
-    CKS(fem2d::launch_k3_scatter(p, slot_begin, slot_end, d_a, d_b, a_kind == FEM2D_INTEGRAL_L2_INNER, b_kind == FEM2D_INTEGRAL_L2_INNER, s, &p.last_launches[2]));
+    CKS(fem2d::launch_k3_scatter(p, n_ranges, slot_begins, slot_ends, d_a, d_b, a_kind == FEM2D_INTEGRAL_L2_INNER, b_kind == FEM2D_INTEGRAL_L2_INNER, s, &p.last_launches[2]));
     CKS(cudaEventRecord(ev[3], s));
     p.last_launches[3] = p.last_launches[0] + p.last_launches[1] + p.last_launches[2];
     p.n_calls++;
@@ -230,29 +267,44 @@ int fem2d_plan_timing(fem2d_plan* plan, uint32_t calls_back, float ms[4], uint32
 }
 int fem2d_plan_last_timing(fem2d_plan* plan, float ms[4], uint32_t launches[4]) { return fem2d_plan_timing(plan, 0, ms, launches); }
 
-int fem2d_assemble_range(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w, uint32_t nu,
-                         const double* v_pts, const double* v_w, uint32_t nv, uint64_t slot_begin, uint64_t slot_end,
-                         uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals) {
+int fem2d_assemble_ranges(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w, uint32_t nu,
+                          const double* v_pts, const double* v_w, uint32_t nv, uint32_t n_ranges, const uint64_t* slot_begins, const uint64_t* slot_ends,
+                          uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals) {
     int st = check_numeric_args(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv);
     if (st != FEM2D_OK) return st;
     if (!a_vals || !b_vals) return fail(FEM2D_ERR_BAD_ARGUMENT, "null output pointer");
+    if (n_ranges == 0 || n_ranges > fem2d::MAX_SLOT_RANGES || !slot_begins || !slot_ends) return fail(FEM2D_ERR_BAD_ARGUMENT, "1..4 slot ranges expected");
     fem2d::Plan& p = plan->p;
-    if (slot_end > p.nnz) slot_end = p.nnz;
-    if (slot_begin > slot_end) return fail(FEM2D_ERR_BAD_ARGUMENT, "slot_begin > slot_end");
+    uint64_t b[fem2d::MAX_SLOT_RANGES], e[fem2d::MAX_SLOT_RANGES];
+    for (uint32_t k = 0; k < n_ranges; k++) {
+        b[k] = slot_begins[k]; e[k] = std::min<uint64_t>(slot_ends[k], p.nnz);
+        if (b[k] > e[k]) return fail(FEM2D_ERR_BAD_ARGUMENT, "slot_begin > slot_end");
+    }
     CKS(cudaSetDevice(p.device));
     const size_t bytes = std::max<uint64_t>(p.nnz, 1) * sizeof(double);
     if (!p.d_out_a) CKS(fem2d::dev_malloc((void**)&p.d_out_a, bytes));
     if (!p.d_out_b) CKS(fem2d::dev_malloc((void**)&p.d_out_b, bytes));
-    st = fem2d_assemble_device(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, slot_begin, slot_end, p.d_out_a, p.d_out_b, nullptr);
+    st = fem2d_assemble_device_ranges(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, n_ranges, b, e, p.d_out_a, p.d_out_b, nullptr);
     if (st != FEM2D_OK) return st;
-    // D2H of the slice of both value arrays (outputs are indexed from slot_begin); the pattern rides along when requested
-    const uint64_t n = slot_end - slot_begin;
-    CKS(cudaMemcpyAsync(a_vals, p.d_out_a + slot_begin, n * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
-    CKS(cudaMemcpyAsync(b_vals, p.d_out_b + slot_begin, n * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
-    if (rows) CKS(cudaMemcpyAsync(rows, p.d_rows + slot_begin, n * 4, cudaMemcpyDeviceToHost, nullptr));
-    if (cols) CKS(cudaMemcpyAsync(cols, p.d_cols + slot_begin, n * 4, cudaMemcpyDeviceToHost, nullptr));
+    // D2H of the value slices (outputs hold the ranges back to back); the pattern rides along when requested
+    uint64_t off = 0;
+    for (uint32_t k = 0; k < n_ranges; k++) {
+        const uint64_t n = e[k] - b[k];
+        if (n == 0) continue;
+        CKS(cudaMemcpyAsync(a_vals + off, p.d_out_a + b[k], n * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+        CKS(cudaMemcpyAsync(b_vals + off, p.d_out_b + b[k], n * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+        if (rows) CKS(cudaMemcpyAsync(rows + off, p.d_rows + b[k], n * 4, cudaMemcpyDeviceToHost, nullptr));
+        if (cols) CKS(cudaMemcpyAsync(cols + off, p.d_cols + b[k], n * 4, cudaMemcpyDeviceToHost, nullptr));
+        off += n;
+    }
     CKS(cudaStreamSynchronize(nullptr));
     return FEM2D_OK;
+}
+
+int fem2d_assemble_range(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w, uint32_t nu,
+                         const double* v_pts, const double* v_w, uint32_t nv, uint64_t slot_begin, uint64_t slot_end,
+                         uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals) {
+    return fem2d_assemble_ranges(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, 1, &slot_begin, &slot_end, rows, cols, a_vals, b_vals);
 }
 
 int fem2d_assemble(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w, uint32_t nu,

@@ -85,14 +85,20 @@ __global__ void contrib_stats_kernel(const uint32_t* __restrict__ extra_slot, ui
     }
 }
 
-__global__ void row_bounds_kernel(const uint32_t* __restrict__ rows, unsigned long long nnz, uint32_t world, unsigned long long* bounds) {
+// nnz-balanced split of the slot interval [lo, hi) into `world` row-aligned blocks
+__global__ void row_bounds_kernel(const uint32_t* __restrict__ rows, unsigned long long lo, unsigned long long hi, uint32_t world, unsigned long long* bounds) {
     const uint32_t r = threadIdx.x;
     if (r > world) return;
-    if (r == 0) { bounds[0] = 0; return; }
-    if (r == world) { bounds[world] = nnz; return; }
-    unsigned long long s = nnz * r / world;
-    while (s < nnz && s > 0 && rows[s] == rows[s - 1]) s++;   // advance to the next row start
+    if (r == 0) { bounds[0] = lo; return; }
+    if (r == world) { bounds[world] = hi; return; }
+    unsigned long long s = lo + (hi - lo) * r / world;
+    while (s < hi && s > lo && rows[s] == rows[s - 1]) s++;   // advance to the next row start
     bounds[r] = s;
+}
+__global__ void first_slot_of_row_kernel(const uint32_t* __restrict__ rows, unsigned long long nnz, uint32_t row, unsigned long long* out) {
+    unsigned long long lo = 0, hi = nnz;   // first slot with rows[slot] >= row
+    while (lo < hi) { const unsigned long long mid = (lo + hi) >> 1; if (rows[mid] < row) lo = mid + 1; else hi = mid; }
+    *out = lo;
 }
 
 }  // namespace
@@ -271,16 +277,21 @@ __global__ void mark_tiles_kernel(const uint32_t* __restrict__ src1, const uint3
 }
 }  // namespace
 
-int device_range_items(Plan& P, uint64_t begin, uint64_t end, const WorkItem** d_items, uint32_t* n_items, std::string& err) {
-    const bool full = begin == 0 && end >= P.nnz;
+int device_range_items(Plan& P, uint32_t n_ranges, const uint64_t* begins, const uint64_t* ends, const WorkItem** d_items, uint32_t* n_items, std::string& err) {
+    if (n_ranges > MAX_SLOT_RANGES) { err = "too many slot ranges"; return FEM2D_ERR_BAD_ARGUMENT; }
+    const bool full = n_ranges == 1 && begins[0] == 0 && ends[0] >= P.nnz;
     // restricting is pointless when the whole integrator is a single wave of CTAs anyway
     if (full || P.total_mt < (uint64_t)4 * 148 * K2_THREADS) { *d_items = P.d_items; *n_items = (uint32_t)P.host.items.size(); return FEM2D_OK; }
-    if (P.d_range_items && begin == P.range_begin && end == P.range_end) { *d_items = P.d_range_items; *n_items = P.n_range_items; return FEM2D_OK; }
+    bool same = P.d_range_items && n_ranges == P.range_n;
+    for (uint32_t k = 0; same && k < n_ranges; k++) same = begins[k] == P.range_begin[k] && ends[k] == P.range_end[k];
+    if (same) { *d_items = P.d_range_items; *n_items = P.n_range_items; return FEM2D_OK; }
     CK(cudaSetDevice(P.device));
     unsigned char* d_flags = nullptr;
     CK(dev_malloc((void**)&d_flags, P.total_mt));
     CK(cudaMemsetAsync(d_flags, 0, P.total_mt, nullptr));
-    if (end > begin) {
+    for (uint32_t k = 0; k < n_ranges; k++) {
+        const uint64_t begin = begins[k], end = std::min<uint64_t>(ends[k], P.nnz);
+        if (end <= begin) continue;
         mark_tiles_kernel<<<(unsigned)((end - begin + 255) / 256), 256>>>(P.d_src1, P.d_extra_slot, P.d_extra_src, P.d_extra_first, P.n_extra, begin, end,
                                                                            P.d_classes, P.d_lists, P.d_class_voff, P.d_class_mtoff,
                                                                            (uint32_t)P.host.classes.size(), P.host.tile_p, d_flags);
@@ -339,17 +350,33 @@ int device_range_items(Plan& P, uint64_t begin, uint64_t end, const WorkItem** d
     dev_free(P.d_range_items); P.d_range_items = nullptr;
     CK(dev_malloc((void**)&P.d_range_items, std::max<size_t>(items.size(), 1) * sizeof(WorkItem)));
     CK(cudaMemcpy(P.d_range_items, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
-    P.n_range_items = (uint32_t)items.size(); P.range_begin = begin; P.range_end = end; P.range_mt_needed = needed;
+    P.n_range_items = (uint32_t)items.size(); P.range_n = n_ranges; P.range_mt_needed = needed;
+    for (uint32_t k = 0; k < n_ranges; k++) { P.range_begin[k] = begins[k]; P.range_end[k] = ends[k]; }
     *d_items = P.d_range_items; *n_items = P.n_range_items;
     return FEM2D_OK;
 }
 
-int device_row_block_bounds(const Plan& P, uint32_t world, uint64_t* bounds, std::string& err) {
+int device_first_slot_of_row(const Plan& P, uint32_t row, uint64_t* slot, std::string& err) {
+    CK(cudaSetDevice(P.device));
+    unsigned long long* d = nullptr;
+    CK(dev_malloc((void**)&d, 8));
+    first_slot_of_row_kernel<<<1, 1>>>(P.d_rows, P.nnz, row, d);
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    dev_free(d);
+    if (e != cudaSuccess) { err = cudaGetErrorString(e); return FEM2D_ERR_CUDA; }
+    *slot = h;
+    return FEM2D_OK;
+}
+
+int device_row_block_bounds(const Plan& P, uint32_t world, uint64_t* bounds, std::string& err) { return device_row_block_bounds_range(P, 0, P.nnz, world, bounds, err); }
+
+int device_row_block_bounds_range(const Plan& P, uint64_t lo, uint64_t hi, uint32_t world, uint64_t* bounds, std::string& err) {
     if (world == 0 || world > 1023) { err = "world out of range"; return FEM2D_ERR_BAD_ARGUMENT; }
     CK(cudaSetDevice(P.device));
     unsigned long long* d_b = nullptr;
     CK(fem2d::dev_malloc((void**)&d_b, (world + 1) * 8));
-    row_bounds_kernel<<<1, 1024>>>(P.d_rows, P.nnz, world, d_b);
+    row_bounds_kernel<<<1, 1024>>>(P.d_rows, lo, hi, world, d_b);
     cudaError_t e = cudaMemcpy(bounds, d_b, (world + 1) * 8, cudaMemcpyDeviceToHost);
     fem2d::dev_free(d_b);
     if (e != cudaSuccess) { err = cudaGetErrorString(e); return FEM2D_ERR_CUDA; }

@@ -46,7 +46,8 @@ struct Plan {
     uint32_t* d_class_mtoff = nullptr;   // [n_classes + 1] first micro-tile of each class in the plan-wide tile numbering
     uint64_t total_mt = 0;
     // row-block restricted item list (multi-GPU sharding of the integrator), valid for [range_begin, range_end)
-    uint64_t range_begin = 0, range_end = 0;
+    uint32_t range_n = 0;
+    uint64_t range_begin[4] = {0, 0, 0, 0}, range_end[4] = {0, 0, 0, 0};
     WorkItem* d_range_items = nullptr;
     uint32_t n_range_items = 0;
     uint64_t range_mt_needed = 0;
@@ -70,6 +71,7 @@ inline cudaError_t dev_malloc(void** p, size_t bytes, cudaStream_t st = nullptr)
 inline void dev_free(void* p, cudaStream_t st = nullptr) { if (p) cudaFreeAsync(p, st); }
 void dev_pool_init(int device);
 
+constexpr uint32_t MAX_SLOT_RANGES = 4;   // slot ranges one numeric call can cover (multi-GPU: a rank's Elem-type rows + its edge-type rows)
 constexpr uint32_t MAX_GLQ = 128;   // default_ngq(20) = 128 (basis.rs:172-177)
 
 // device_plan.cu
@@ -77,7 +79,10 @@ int device_symbolic(Plan& plan, std::string& err);
 int device_row_block_bounds(const Plan& plan, uint32_t world, uint64_t* bounds, std::string& err);
 // Work items of the exact integrator restricted to the micro-tiles that the slots [begin, end) read (cached per plan for the last
 // range; the full item list is returned for the full range and for plans too small to be worth restricting).
-int device_range_items(Plan& plan, uint64_t begin, uint64_t end, const WorkItem** d_items, uint32_t* n_items, std::string& err);
+int device_range_items(Plan& plan, uint32_t n_ranges, const uint64_t* begins, const uint64_t* ends, const WorkItem** d_items, uint32_t* n_items, std::string& err);
+// First slot whose row is >= `row` (binary search over the device pattern).
+int device_first_slot_of_row(const Plan& plan, uint32_t row, uint64_t* slot, std::string& err);
+int device_row_block_bounds_range(const Plan& plan, uint64_t lo, uint64_t hi, uint32_t world, uint64_t* bounds, std::string& err);
 void device_plan_release(Plan& plan);
 
 // kernels_exact.cu  (compiled with -fmad=false)
@@ -90,6 +95,7 @@ cudaError_t launch_k2_sumfact(Plan& plan, uint32_t nu, uint32_t nv, uint32_t NO,
 cudaError_t launch_k2_dmma(Plan& plan, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches);
 
 // kernels_scatter.cu
-cudaError_t launch_k3_scatter(const Plan& plan, uint64_t slot_begin, uint64_t slot_end, double* d_a, double* d_b, int selA, int selB, cudaStream_t st, uint32_t* launches);
+cudaError_t launch_k3_scatter(const Plan& plan, uint32_t n_ranges, const uint64_t* begins, const uint64_t* ends, double* d_a, double* d_b, int selA, int selB,
+                              cudaStream_t st, uint32_t* launches);
 
 }  // namespace fem2d

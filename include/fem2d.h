@@ -108,6 +108,15 @@ int fem2d_assemble_device(fem2d_plan* plan, int basis_kind, int a_kind, int b_ki
                           uint64_t slot_begin, uint64_t slot_end,
                           double* d_a, double* d_b, void* stream);
 
+/* Same for up to 4 disjoint slot ranges in one call (one integrator launch restricted to what those slots read, one scatter
+ * launch).  Multi-GPU use: a rank passes its block of the single-Elem rows and its block of the shared (edge-type) rows, see
+ * fem2d_plan_row_blocks_split. */
+int fem2d_assemble_device_ranges(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode,
+                                 const double* u_pts, const double* u_w, uint32_t nu,
+                                 const double* v_pts, const double* v_w, uint32_t nv,
+                                 uint32_t n_ranges, const uint64_t* slot_begins, const uint64_t* slot_ends,
+                                 double* d_a, double* d_b, void* stream);
+
 /* Numeric phase with HOST outputs (a_vals / b_vals: nnz_upper doubles each; rows / cols may be NULL). Synchronous. */
 int fem2d_assemble(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode,
                    const double* u_pts, const double* u_w, uint32_t nu,
@@ -121,6 +130,13 @@ int fem2d_assemble_range(fem2d_plan* plan, int basis_kind, int a_kind, int b_kin
                          uint64_t slot_begin, uint64_t slot_end,
                          uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals);
 
+/* Same for up to 4 slot ranges; the outputs hold the ranges back to back. */
+int fem2d_assemble_ranges(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode,
+                          const double* u_pts, const double* u_w, uint32_t nu,
+                          const double* v_pts, const double* v_w, uint32_t nv,
+                          uint32_t n_ranges, const uint64_t* slot_begins, const uint64_t* slot_ends,
+                          uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals);
+
 /* One-shot equivalent of the reference call: symbolic + numeric + copy-out.  The caller passes its output capacity; when it is too small
  * the call fails with FEM2D_ERR_BAD_ARGUMENT and *nnz_out holds the required size.  Status 1/2/3 exactly as galerkin.rs:42-59. */
 int fem2d_galerkin_sample_gep_hcurl(const fem2d_domain_view* view, int device, int basis_kind, int a_kind, int b_kind, int mode,
@@ -132,6 +148,13 @@ int fem2d_galerkin_sample_gep_hcurl(const fem2d_domain_view* view, int device, i
 /* Row-block partition of the pattern for `world` ranks: bounds[r]..bounds[r+1] are slot indices aligned to row starts
  * and balanced by nnz (bounds has world+1 entries). */
 int fem2d_plan_row_blocks(const fem2d_plan* plan, uint32_t world, uint64_t* bounds);
+
+/* Two-level partition for `world` ranks: the rows of DoFs carried by a single Elem (the reference numbers these Elem-type DoFs
+ * first, domain.rs:83-96) and the rows of shared (edge-type) DoFs are each split into `world` row-aligned, nnz-balanced blocks.
+ * Rank r assembles [bounds_single[r], bounds_single[r+1]) and [bounds_shared[r], bounds_shared[r+1]): Elem and Edge ids grow
+ * together under refinement, so a rank's edge rows mostly read the pair blocks its Elem rows already need, which balances the
+ * integrator across ranks. */
+int fem2d_plan_row_blocks_split(const fem2d_plan* plan, uint32_t world, uint64_t* bounds_single, uint64_t* bounds_shared);
 
 /* Per-phase device timings of the last numeric call in milliseconds (CUDA events on the launch stream):
  * ms[0] sampler (K1), ms[1] integrator (K2), ms[2] scatter (K3), ms[3] total; launches[0..2] kernel launch counts. */

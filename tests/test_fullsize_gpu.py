@@ -138,3 +138,30 @@ def test_row_block_slices_with_restricted_integrator():
     assert torch.equal(b.view(torch.int64), ref_b.view(torch.int64))
     assert all(0 < n < 0.6 * total_tiles for n in needed), needed       # each rank integrates a fraction of the tiles
     assert sum(needed) < 1.6 * total_tiles, needed                        # little redundancy across ranks
+
+
+def test_split_partition_balances_the_integrator():
+    """fem2d_plan_row_blocks_split: a rank's Elem-type rows and its edge-type rows in one multi-range call.  All ranks together
+    reproduce the full result bit for bit and need a balanced share of the micro-tiles (dedupe off = general case)."""
+    import torch
+    df = F.Domain.from_mesh(recipes.mesh_cfg3(recipes.api("product"), levels=4, order=6))
+    glq = (F.gauss_quadrature_points(8), F.gauss_quadrature_points(8))
+    plan = F.Plan(df.view(), device=0, dedupe=False)
+    ref_a = torch.empty(plan.nnz, dtype=torch.float64, device="cuda:0"); ref_b = torch.empty_like(ref_a)
+    plan.assemble_device(glq, ref_a.data_ptr(), ref_b.data_ptr())
+    a = torch.full_like(ref_a, float("nan")); b = torch.full_like(ref_b, float("nan"))
+    world = 4
+    b1, b2 = plan.row_blocks_split(world)
+    assert b1[0] == 0 and b1[-1] == b2[0] and b2[-1] == plan.nnz
+    rows, _ = plan.pattern()
+    assert rows[int(b2[0]) - 1] < 1024 * 60 <= rows[int(b2[0])]           # the split sits at the first edge-type DoF row
+    needed = []
+    for r in range(world):
+        plan.assemble_device_ranges(glq, a.data_ptr(), b.data_ptr(), [(int(b1[r]), int(b1[r + 1])), (int(b2[r]), int(b2[r + 1]))])
+        needed.append(plan.refresh_info()["range_tiles_needed"])
+    torch.cuda.synchronize()
+    assert torch.equal(a.view(torch.int64), ref_a.view(torch.int64))
+    assert torch.equal(b.view(torch.int64), ref_b.view(torch.int64))
+    total_tiles = 1024 * 473
+    assert max(needed) < 1.35 * min(needed), needed                      # balanced
+    assert sum(needed) < 1.35 * total_tiles, needed                      # little redundancy

@@ -50,6 +50,20 @@ def _worker(rank, world, port, recipe, out_dir):
         dist.all_gather(parts, buf)
         full = torch.cat([parts[r][: int(bounds[r + 1] - bounds[r])] for r in range(world)])
         assert np.array_equal(full.numpy().view(np.uint64), ref.a.view(np.uint64))
+        # two-level partition (Elem-type rows + edge-type rows per rank): consistent across ranks, covers every slot exactly once
+        b1, b2 = plan.row_blocks_split(world)
+        g2 = [torch.zeros(2 * (world + 1), dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(g2, torch.from_numpy(np.concatenate([b1, b2]).astype(np.int64)))
+        for g in g2:
+            assert torch.equal(g, g2[0])
+        assert b1[0] == 0 and b1[-1] == b2[0] and b2[-1] == plan.nnz
+        cover = np.zeros(plan.nnz, dtype=np.int32)
+        for r in range(world):
+            cover[int(b1[r]):int(b1[r + 1])] += 1
+            cover[int(b2[r]):int(b2[r + 1])] += 1
+        assert np.all(cover == 1)
+        if 0 < b2[0] < plan.nnz:
+            assert rows[int(b2[0])] != rows[int(b2[0]) - 1]
         # max-over-ranks timing reduction as in bench.py
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
