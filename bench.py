@@ -46,6 +46,18 @@ def _peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def _ncu_traffic(workload, dedupe, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k3_gather_kernel launch from the committed `ncu --set full` capture of this
+    workload (profiles/ncu_traffic.json, written from the .ncu-rep by scripts/ncu_summary.py); None when no capture matches."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if world != 1 or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    e = t.get(f"k3_gather_kernel/{workload}/dedupe{int(dedupe)}")
+    return None if e is None else float(e["dram_bytes_read"] + e["dram_bytes_write"])
+
+
 def build_product_domain(workload: str):
     import fem_2d_b200 as F
     import recipes
@@ -249,13 +261,17 @@ def run_ours(args):
     peaks, peak_kind = _peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     n_slots = sum(e - b for b, e in ranges)
-    # K3 algorithmic bytes: 16 B written per slot (A and B) + the 4 B source index it reads (SURVEY.md 8d budgets 4 B per pair
-    # for a push scatter; the gather form reads one index per slot)
-    alg_bytes_k3 = 16.0 * n_slots + 4.0 * n_slots
+    # K3 algorithmic bytes: 16 B written per slot (A and B) + the source map it reads.  SURVEY.md 8d budgets a 4 B index per pair; the
+    # packed map the kernel actually reads is smaller (fem2d_plan_source_map_info), and the smaller figure is the one used here.
+    smi = plan.source_map_info()
+    map_bytes = smi["map_bytes"] * (n_slots / max(nnz, 1))
+    alg_bytes_k3 = 16.0 * n_slots + map_bytes
     k3_gbs = alg_bytes_k3 / (k3_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k3_gather_kernel (DoF scatter)", "achieved": k3_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k3_gbs / hbm_peak,
-                "traffic": None, "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)" if peak_kind == "measured" else "fallback 6.65 TB/s",
-                "algorithmic_bytes_per_launch": alg_bytes_k3, "kernel_ms": float(k3_ms), "share_of_step": float(k3_ms / tot_ms)}
+                "traffic": _ncu_traffic(workload, args.dedupe, world),
+                "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)" if peak_kind == "measured" else "fallback 6.65 TB/s",
+                "algorithmic_bytes_per_launch": alg_bytes_k3, "source_map_bytes_per_launch": map_bytes, "source_map_plain_chunks": smi["plain_chunks"],
+                "survey_8d_bytes_per_launch": 20.0 * n_slots, "kernel_ms": float(k3_ms), "share_of_step": float(k3_ms / tot_ms)}
     info = plan.info
     extra = {}
     if rank == 0 and world == 1 and not args.no_extras:

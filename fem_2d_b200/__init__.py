@@ -72,7 +72,7 @@ class _View(C.Structure):
 
 # Every symbol declared in include/fem2d.h and include/fem2d_host.h (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "fem2d_symbolic", "fem2d_plan_free", "fem2d_plan_info", "fem2d_plan_pattern", "fem2d_plan_pattern_device",
+    "fem2d_symbolic", "fem2d_plan_free", "fem2d_plan_info", "fem2d_plan_source_map_info", "fem2d_plan_pattern", "fem2d_plan_pattern_device",
     "fem2d_assemble_device", "fem2d_assemble_device_ranges", "fem2d_plan_row_blocks_split", "fem2d_assemble_ranges", "fem2d_assemble", "fem2d_galerkin_sample_gep_hcurl", "fem2d_plan_row_blocks",
     "fem2d_plan_last_timing", "fem2d_plan_timing", "fem2d_assemble_range", "fem2d_host_alloc", "fem2d_host_free", "fem2d_xy_fields", "fem2d_fp64_peak",
     "fem2d_device_count", "fem2d_status_string", "fem2d_last_error", "fem2d_version",
@@ -596,6 +596,12 @@ class Plan:
         _ck(_L.fem2d_plan_info(self._h, info))
         self.info = {k: int(info[i]) for i, k in enumerate(INFO_KEYS)}
         return self.info
+
+    def source_map_info(self) -> dict:
+        """fem2d_plan_source_map_info: size of the packed source map the scatter kernel reads."""
+        info = (C.c_uint64 * 4)()
+        _ck(_L.fem2d_plan_source_map_info(self._h, info))
+        return {"plain_chunks": int(info[0]), "chunk_slots": int(info[1]), "map_bytes": int(info[2]), "plain_bytes": int(info[3])}
 
     def pattern(self):
         rows = np.zeros(self.nnz, dtype=np.uint32); cols = np.zeros(self.nnz, dtype=np.uint32)

@@ -122,6 +122,17 @@ int fem2d_plan_info(const fem2d_plan* plan, uint64_t info[16]) {
     return FEM2D_OK;
 }
 
+int fem2d_plan_source_map_info(const fem2d_plan* plan, uint64_t info[4]) {
+    if (!plan || !info) return fail(FEM2D_ERR_BAD_ARGUMENT, "null argument");
+    const fem2d::Plan& p = plan->p;
+    if (p.device < 0) return fail(FEM2D_ERR_NO_DEVICE, "host-only plan");
+    const uint64_t n_chunks = (p.nnz + fem2d::SRC_CHUNK - 1) / fem2d::SRC_CHUNK;
+    info[0] = p.n_plain_chunks; info[1] = fem2d::SRC_CHUNK;
+    info[2] = n_chunks * 4 + p.nnz * 2 + p.n_plain_chunks * fem2d::SRC_CHUNK * 4;   // bases + 16-bit offsets + the plain chunks' indices
+    info[3] = p.nnz * 4;
+    return FEM2D_OK;
+}
+
 int fem2d_plan_pattern(const fem2d_plan* plan, uint32_t* rows, uint32_t* cols) {
     if (!plan) return fail(FEM2D_ERR_BAD_ARGUMENT, "null plan");
     const fem2d::Plan& p = plan->p;

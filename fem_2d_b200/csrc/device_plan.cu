@@ -73,6 +73,29 @@ __global__ void emit_pattern_kernel(const unsigned long long* __restrict__ keys,
     }
 }
 
+// ---- packed form of the source map -----------------------------------------------------------------------------------------------
+// The scatter kernel streams 16 B of values per slot; a 4 B source index next to them is 20 % of its HBM traffic.  Consecutive
+// slots read neighbouring entries of V (a row of the pattern walks along a row or a column of one class's value tile), so per
+// chunk of SRC_CHUNK slots the sources are stored as 16-bit offsets from the chunk's smallest source: 2 B per slot + 4 B per
+// chunk, both read in one step (no dependent load in front of the gather).  A chunk whose sources span more than 2^16 entries,
+// or that holds a slot with more than one contribution (high bit of src1), keeps the plain 32-bit form (chunk_base = PLAIN).
+__global__ void __launch_bounds__(256) pack_sources_kernel(const uint32_t* __restrict__ src1, unsigned long long nnz, unsigned long long n_chunks,
+                                                          uint32_t* __restrict__ chunk_base, uint16_t* __restrict__ src16, uint32_t* __restrict__ n_plain) {
+    static_assert(SRC_CHUNK == 64, "one warp packs one chunk, two slots per lane");
+    const unsigned long long chunk = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) / 32;
+    if (chunk >= n_chunks) return;
+    const uint32_t lane = threadIdx.x % 32;
+    const unsigned long long s0 = chunk * SRC_CHUNK + lane, s1 = s0 + 32;
+    const bool in0 = s0 < nnz, in1 = s1 < nnz;
+    const uint32_t v0 = in0 ? src1[s0] : 0u, v1 = in1 ? src1[s1] : 0u;
+    uint32_t mn = min(in0 ? v0 : 0xffffffffu, in1 ? v1 : 0xffffffffu), mx = max(v0, v1);
+    for (int d = 16; d; d >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, d)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d)); }
+    const bool plain = (mx & 0x80000000u) || mx - mn > 0xffffu;
+    if (lane == 0) { chunk_base[chunk] = plain ? SRC_CHUNK_PLAIN : mn; if (plain) atomicAdd(n_plain, 1u); }
+    if (in0) src16[s0] = plain ? (uint16_t)0 : (uint16_t)(v0 - mn);
+    if (in1) src16[s1] = plain ? (uint16_t)0 : (uint16_t)(v1 - mn);
+}
+
 // longest run of equal keys and number of keys with more than one contribution
 __global__ void contrib_stats_kernel(const uint32_t* __restrict__ extra_slot, uint32_t n_extra, uint32_t* __restrict__ stats) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -236,6 +259,23 @@ int device_symbolic(Plan& P, std::string& err) {
     }
     CKC(cudaMemcpy(stats, d_stats, 8, cudaMemcpyDeviceToHost));   // synchronises the null stream: everything above is done
     P.max_contrib = stats[0]; P.n_multi = stats[1];
+
+    // ---- packed form of the source map (what the scatter kernel reads; src1 stays for the chunks that do not pack)
+    {
+        const unsigned long long n_chunks = ((unsigned long long)nnz32 + SRC_CHUNK - 1) / SRC_CHUNK;
+        Arena ra;
+        const size_t r_base = ra.reserve((n_chunks + 1) * 4), r_16 = ra.reserve(((size_t)nnz32 + 1) * 2);
+        CKC(dev_malloc(&P.d_pack_arena, ra.size));
+        P.d_chunk_base = at<uint32_t>(P.d_pack_arena, r_base); P.d_src16 = at<uint16_t>(P.d_pack_arena, r_16);
+        if (nnz32) {
+            CKC(cudaMemsetAsync(d_stats, 0, 4, nullptr));
+            pack_sources_kernel<<<(unsigned)((n_chunks * 32 + 255) / 256), 256>>>(P.d_src1, nnz32, n_chunks, P.d_chunk_base, P.d_src16, d_stats);
+            CKC(cudaGetLastError());
+            uint32_t n_plain = 0;
+            CKC(cudaMemcpy(&n_plain, d_stats, 4, cudaMemcpyDeviceToHost));
+            P.n_plain_chunks = n_plain;
+        }
+    }
     dev_free(scratch);
 #undef CKC
     for (int r = 0; r < Plan::RING; r++) for (int k = 0; k < 4; k++) CK(cudaEventCreate(&P.ev[r][k]));
@@ -388,6 +428,7 @@ void device_plan_release(Plan& P) {
     cudaSetDevice(P.device);
     cudaDeviceSynchronize();   // numeric work may still be in flight on a caller stream
     dev_free(P.d_desc_arena); dev_free(P.d_pattern_arena);   // descriptors, GLQ buffer, pattern, source map
+    dev_free(P.d_pack_arena);
     dev_free(P.d_range_items);
     dev_free(P.d_V); dev_free(P.d_tabs); dev_free(P.d_gram); dev_free(P.d_dmma_items); dev_free(P.d_out_a); dev_free(P.d_out_b);
     for (int r = 0; r < Plan::RING; r++) for (int k = 0; k < 4; k++) if (P.ev[r][k]) cudaEventDestroy(P.ev[r][k]);

@@ -33,6 +33,12 @@ struct Plan {
     uint32_t* d_extra_slot = nullptr;
     uint32_t* d_extra_src = nullptr;
     uint32_t* d_extra_first = nullptr;   // first contribution of a multi-contribution slot, stored at the head of its extras run
+    // packed form of src1 (device_plan.cu pack_sources_kernel): 16-bit offsets from a per-chunk base; chunk_base == SRC_CHUNK_PLAIN
+    // marks a chunk that keeps the 32-bit form
+    void* d_pack_arena = nullptr;
+    uint32_t* d_chunk_base = nullptr;
+    uint16_t* d_src16 = nullptr;
+    uint64_t n_plain_chunks = 0;
 
     // numeric scratch (allocated lazily, reused across calls)
     double2* d_V = nullptr;
@@ -72,6 +78,12 @@ inline void dev_free(void* p, cudaStream_t st = nullptr) { if (p) cudaFreeAsync(
 void dev_pool_init(int device);
 
 constexpr uint32_t MAX_SLOT_RANGES = 4;   // slot ranges one numeric call can cover (multi-GPU: a rank's Elem-type rows + its edge-type rows)
+constexpr uint32_t SRC_CHUNK = 64;                     // slots per chunk of the packed source map
+constexpr uint32_t SRC_CHUNK_PLAIN = 0x80000000u;      // chunk_base value of a chunk that is read through the plain 32-bit src1
+constexpr uint32_t K3_THREADS = 256;          // scatter kernel: one CTA per K3_BLOCK_SLOTS-aligned block of slots,
+constexpr uint32_t K3_ITERS = 4;              // K3_ITERS slots per thread
+constexpr uint32_t K3_BLOCK_SLOTS = K3_THREADS * K3_ITERS;
+constexpr uint32_t K3_PREFETCH_SLOTS = 1u << 20;   // distance of the L2 prefetch of the 16-bit offset stream
 constexpr uint32_t MAX_GLQ = 128;   // default_ngq(20) = 128 (basis.rs:172-177)
 
 // device_plan.cu

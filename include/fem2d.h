@@ -92,6 +92,10 @@ void fem2d_plan_free(fem2d_plan* plan);
  * 10 n_lists, 11 n_extra (2nd+ contributions), 12 / 13 wall microseconds of the host / device halves of the symbolic phase,
  * 14 micro-tile height chosen for the exact integrator (4: throughput shape, 1: latency shape for small plans) */
 int fem2d_plan_info(const fem2d_plan* plan, uint64_t info[16]);
+/* Size of the per-slot source map the scatter kernel reads.  The map is packed per chunk of slots as 16-bit offsets from the
+ * chunk's smallest source; chunks that do not fit keep plain 32-bit indices.  info[]: 0 chunks in plain form, 1 slots per chunk,
+ * 2 bytes of the map one full scatter reads, 3 bytes of an all-plain map (4 per slot).  Device plans only. */
+int fem2d_plan_source_map_info(const fem2d_plan* plan, uint64_t info[4]);
 /* Copy the pattern to host: rows[k] <= cols[k], sorted by (row, col). */
 int fem2d_plan_pattern(const fem2d_plan* plan, uint32_t* rows, uint32_t* cols);
 /* Device pointers of the pattern (uint32 rows, cols; length nnz_upper). */
