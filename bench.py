@@ -377,7 +377,7 @@ def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz):
     h_cols = torch.empty(n, dtype=torch.int32).pin_memory()
     h_a = torch.empty(n, dtype=torch.float64).pin_memory()
     h_b = torch.empty(n, dtype=torch.float64).pin_memory()
-    d2h = n * (4 + 4 + 8 + 8)
+    d2h = n * (4 + 8 + 8) + (view.n_dofs + 1) * 4    # cols, A, B + the CSR row offsets (rows are expanded from them on the host)
 
     trace = []
 
@@ -411,7 +411,7 @@ def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t.item())
     return {"value": 2.0 * nnz * steps / sec, "unit": "nnz/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * sec / steps,
-            "steps": steps, "includes": "symbolic phase (pattern + source map) + K1/K2/K3 + D2H of rows, cols, A, B into pinned host buffers",
+            "steps": steps, "includes": "symbolic phase (pattern + source map) + K1/K2/K3 + D2H of cols, A, B and the CSR row offsets into pinned host buffers + host expansion of rows[]",
             "per_step_breakdown_rank0": trace}
 
 

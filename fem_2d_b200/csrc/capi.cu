@@ -6,6 +6,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/fem2d.h"
@@ -145,6 +146,43 @@ int fem2d_plan_pattern(const fem2d_plan* plan, uint32_t* rows, uint32_t* cols) {
     if (rows) CKS(cudaMemcpy(rows, p.d_rows, p.nnz * 4, cudaMemcpyDeviceToHost));
     if (cols) CKS(cudaMemcpy(cols, p.d_cols, p.nnz * 4, cudaMemcpyDeviceToHost));
     return FEM2D_OK;
+}
+
+int fem2d_plan_row_offsets(fem2d_plan* plan, uint64_t* row_ptr) {
+    if (!plan || !row_ptr) return fail(FEM2D_ERR_BAD_ARGUMENT, "null argument");
+    fem2d::Plan& p = plan->p;
+    const uint32_t n = p.host.n_dofs;
+    if (p.device < 0) {
+        const auto& rows = p.host_pattern.rows;
+        uint64_t s = 0;
+        for (uint32_t r = 0; r <= n; r++) { while (s < rows.size() && rows[s] < r) s++; row_ptr[r] = s; }
+        return FEM2D_OK;
+    }
+    std::string err;
+    const int st = fem2d::device_row_ptr_host(p, nullptr, err);
+    if (st != FEM2D_OK) return fail(st, err);
+    for (uint32_t r = 0; r <= n; r++) row_ptr[r] = p.h_row_ptr[r];
+    return FEM2D_OK;
+}
+
+// rows[k] for the slots [b, e) written to out[0 .. e-b): expansion of the CSR row offsets on `threads` host threads
+static void expand_rows(const uint32_t* row_ptr, uint32_t n_rows, uint64_t b, uint64_t e, uint32_t* out, unsigned threads) {
+    if (e <= b) return;
+    auto work = [=](uint64_t lo, uint64_t hi) {
+        // row holding slot lo: last r with row_ptr[r] <= lo
+        uint32_t r = (uint32_t)(std::upper_bound(row_ptr, row_ptr + n_rows + 1, (uint32_t)lo) - row_ptr) - 1;
+        uint64_t s = lo;
+        while (s < hi) {
+            const uint64_t stop = std::min<uint64_t>(row_ptr[r + 1], hi);
+            std::fill(out + (s - b), out + (stop - b), r);
+            s = stop; r++;
+        }
+    };
+    threads = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(threads, (e - b) / (1u << 20)));
+    if (threads == 1) { work(b, e); return; }
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; t++) pool.emplace_back(work, b + (e - b) * t / threads, b + (e - b) * (t + 1) / threads);
+    for (auto& th : pool) th.join();
 }
 
 int fem2d_plan_pattern_device(const fem2d_plan* plan, const uint32_t** d_rows, const uint32_t** d_cols) {
@@ -295,6 +333,11 @@ int fem2d_assemble_ranges(fem2d_plan* plan, int basis_kind, int a_kind, int b_ki
     const size_t bytes = std::max<uint64_t>(p.nnz, 1) * sizeof(double);
     if (!p.d_out_a) CKS(fem2d::dev_malloc((void**)&p.d_out_a, bytes));
     if (!p.d_out_b) CKS(fem2d::dev_malloc((void**)&p.d_out_b, bytes));
+    if (rows) {   // the row indices are expanded on the host from the CSR row offsets (4 B per row instead of 4 B per slot over PCIe)
+        std::string rerr;
+        st = fem2d::device_row_ptr_host(p, nullptr, rerr);
+        if (st != FEM2D_OK) return fail(st, rerr);
+    }
     st = fem2d_assemble_device_ranges(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, n_ranges, b, e, p.d_out_a, p.d_out_b, nullptr);
     if (st != FEM2D_OK) return st;
     // D2H of the value slices (outputs hold the ranges back to back); the pattern rides along when requested
@@ -304,9 +347,13 @@ int fem2d_assemble_ranges(fem2d_plan* plan, int basis_kind, int a_kind, int b_ki
         if (n == 0) continue;
         CKS(cudaMemcpyAsync(a_vals + off, p.d_out_a + b[k], n * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
         CKS(cudaMemcpyAsync(b_vals + off, p.d_out_b + b[k], n * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
-        if (rows) CKS(cudaMemcpyAsync(rows + off, p.d_rows + b[k], n * 4, cudaMemcpyDeviceToHost, nullptr));
         if (cols) CKS(cudaMemcpyAsync(cols + off, p.d_cols + b[k], n * 4, cudaMemcpyDeviceToHost, nullptr));
         off += n;
+    }
+    if (rows) {   // while the copies above are in flight
+        const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        off = 0;
+        for (uint32_t k = 0; k < n_ranges; k++) { expand_rows(p.h_row_ptr, p.host.n_dofs, b[k], e[k], rows + off, hw); off += e[k] - b[k]; }
     }
     CKS(cudaStreamSynchronize(nullptr));
     return FEM2D_OK;

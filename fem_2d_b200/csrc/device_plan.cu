@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "device_plan.hpp"
@@ -54,13 +55,17 @@ __global__ void head_flags_kernel(const unsigned long long* __restrict__ keys, u
 __global__ void emit_pattern_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ srcs,
                                     const uint32_t* __restrict__ head, const uint32_t* __restrict__ scan, uint32_t n,
                                     uint32_t* __restrict__ rows, uint32_t* __restrict__ cols, uint32_t* __restrict__ src1,
-                                    uint32_t* __restrict__ extra_slot, uint32_t* __restrict__ extra_src, uint32_t* __restrict__ extra_first) {
+                                    uint32_t* __restrict__ extra_slot, uint32_t* __restrict__ extra_src, uint32_t* __restrict__ extra_first,
+                                    uint32_t* __restrict__ row_ptr, uint32_t n_dofs) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t slot = scan[i] - 1;
     if (head[i]) {
-        rows[slot] = (uint32_t)(keys[i] >> 32);
+        const uint32_t row = (uint32_t)(keys[i] >> 32);
+        rows[slot] = row;
         cols[slot] = (uint32_t)keys[i];
+        // CSR row offsets: this slot opens every row after the previous key's row up to its own (rows without entries stay empty)
+        for (uint32_t q = i ? (uint32_t)(keys[i - 1] >> 32) + 1 : 0u; q <= row; q++) row_ptr[q] = slot;
         if (i + 1 < n && !head[i + 1]) {   // key with more than one contribution: point at its run in the extras arrays
             const uint32_t k = i - slot;   // rank of element i+1 among the non-heads
             src1[slot] = 0x80000000u | k;
@@ -71,6 +76,7 @@ __global__ void emit_pattern_kernel(const unsigned long long* __restrict__ keys,
         extra_slot[k] = slot;
         extra_src[k] = srcs[i];
     }
+    if (i == n - 1) for (uint32_t q = (uint32_t)(keys[i] >> 32) + 1; q <= n_dofs; q++) row_ptr[q] = slot + 1;   // == nnz
 }
 
 // ---- packed form of the source map -----------------------------------------------------------------------------------------------
@@ -246,10 +252,13 @@ int device_symbolic(Plan& P, std::string& err) {
     Arena pa;
     const size_t p_rows = pa.reserve((size_t)nnz32 * 4), p_cols = pa.reserve((size_t)nnz32 * 4), p_src1 = pa.reserve((size_t)nnz32 * 4);
     const size_t p_es = pa.reserve(P.n_extra * 4), p_ex = pa.reserve(P.n_extra * 4), p_ef = pa.reserve(P.n_extra * 4);
+    const size_t p_rp = pa.reserve(((size_t)H.n_dofs + 1) * 4);
     CKC(dev_malloc(&P.d_pattern_arena, pa.size));
     P.d_rows = at<uint32_t>(P.d_pattern_arena, p_rows); P.d_cols = at<uint32_t>(P.d_pattern_arena, p_cols); P.d_src1 = at<uint32_t>(P.d_pattern_arena, p_src1);
     P.d_extra_slot = at<uint32_t>(P.d_pattern_arena, p_es); P.d_extra_src = at<uint32_t>(P.d_pattern_arena, p_ex); P.d_extra_first = at<uint32_t>(P.d_pattern_arena, p_ef);
-    emit_pattern_kernel<<<gb, 256>>>(keys_sorted, srcs_sorted, d_head, d_scan, np, P.d_rows, P.d_cols, P.d_src1, P.d_extra_slot, P.d_extra_src, P.d_extra_first);
+    P.d_row_ptr = at<uint32_t>(P.d_pattern_arena, p_rp);
+    emit_pattern_kernel<<<gb, 256>>>(keys_sorted, srcs_sorted, d_head, d_scan, np, P.d_rows, P.d_cols, P.d_src1, P.d_extra_slot, P.d_extra_src, P.d_extra_first,
+                                     P.d_row_ptr, H.n_dofs);
     CKC(cudaGetLastError());
     uint32_t stats[2] = {1, 0};
     CKC(cudaMemcpyAsync(d_stats, stats, 8, cudaMemcpyHostToDevice, nullptr));
@@ -423,12 +432,47 @@ int device_row_block_bounds_range(const Plan& P, uint64_t lo, uint64_t hi, uint3
     return FEM2D_OK;
 }
 
+namespace {
+// Small process-wide cache of pinned staging buffers: a one-shot call builds and frees a plan every time, and pinning a few MB
+// costs about as much as the copy it serves.
+std::mutex g_pin_mu;
+std::vector<std::pair<void*, size_t>> g_pin_free;
+void* pinned_acquire(size_t bytes, size_t* cap) {
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        for (size_t k = 0; k < g_pin_free.size(); k++)
+            if (g_pin_free[k].second >= bytes) { void* p = g_pin_free[k].first; *cap = g_pin_free[k].second; g_pin_free.erase(g_pin_free.begin() + k); return p; }
+    }
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *cap = bytes;
+    return p;
+}
+void pinned_release(void* p, size_t cap) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (g_pin_free.size() < 4) { g_pin_free.push_back({p, cap}); return; }
+    cudaFreeHost(p);
+}
+}  // namespace
+
+int device_row_ptr_host(Plan& P, cudaStream_t st, std::string& err) {
+    if (P.h_row_ptr) return FEM2D_OK;
+    CK(cudaSetDevice(P.device));
+    P.h_row_ptr = (uint32_t*)pinned_acquire(((size_t)P.host.n_dofs + 1) * 4, &P.h_row_ptr_cap);
+    if (!P.h_row_ptr) { err = "pinned host allocation failed"; return FEM2D_ERR_OUT_OF_MEMORY; }
+    CK(cudaMemcpyAsync(P.h_row_ptr, P.d_row_ptr, ((size_t)P.host.n_dofs + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return FEM2D_OK;
+}
+
 void device_plan_release(Plan& P) {
     if (P.device < 0) return;
     cudaSetDevice(P.device);
     cudaDeviceSynchronize();   // numeric work may still be in flight on a caller stream
     dev_free(P.d_desc_arena); dev_free(P.d_pattern_arena);   // descriptors, GLQ buffer, pattern, source map
     dev_free(P.d_pack_arena);
+    pinned_release(P.h_row_ptr, P.h_row_ptr_cap); P.h_row_ptr = nullptr;
     dev_free(P.d_range_items);
     dev_free(P.d_V); dev_free(P.d_tabs); dev_free(P.d_gram); dev_free(P.d_dmma_items); dev_free(P.d_out_a); dev_free(P.d_out_b);
     for (int r = 0; r < Plan::RING; r++) for (int k = 0; k < 4; k++) if (P.ev[r][k]) cudaEventDestroy(P.ev[r][k]);

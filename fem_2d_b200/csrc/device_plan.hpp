@@ -30,6 +30,9 @@ struct Plan {
     uint32_t* d_rows = nullptr;
     uint32_t* d_cols = nullptr;
     uint32_t* d_src1 = nullptr;
+    uint32_t* d_row_ptr = nullptr;       // [n_dofs + 1] CSR row offsets of the pattern (first slot of every row)
+    uint32_t* h_row_ptr = nullptr;       // pinned host copy, fetched on first use (host `rows` output is expanded from it)
+    size_t h_row_ptr_cap = 0;
     uint32_t* d_extra_slot = nullptr;
     uint32_t* d_extra_src = nullptr;
     uint32_t* d_extra_first = nullptr;   // first contribution of a multi-contribution slot, stored at the head of its extras run
@@ -95,6 +98,8 @@ int device_range_items(Plan& plan, uint32_t n_ranges, const uint64_t* begins, co
 // First slot whose row is >= `row` (binary search over the device pattern).
 int device_first_slot_of_row(const Plan& plan, uint32_t row, uint64_t* slot, std::string& err);
 int device_row_block_bounds_range(const Plan& plan, uint64_t lo, uint64_t hi, uint32_t world, uint64_t* bounds, std::string& err);
+// Pinned host copy of the CSR row offsets (fetched once per plan).
+int device_row_ptr_host(Plan& plan, cudaStream_t st, std::string& err);
 void device_plan_release(Plan& plan);
 
 // kernels_exact.cu  (compiled with -fmad=false)

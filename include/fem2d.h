@@ -98,6 +98,8 @@ int fem2d_plan_info(const fem2d_plan* plan, uint64_t info[16]);
 int fem2d_plan_source_map_info(const fem2d_plan* plan, uint64_t info[4]);
 /* Copy the pattern to host: rows[k] <= cols[k], sorted by (row, col). */
 int fem2d_plan_pattern(const fem2d_plan* plan, uint32_t* rows, uint32_t* cols);
+/* CSR row offsets of the pattern: row_ptr[r] = first slot of row r, row_ptr[n_dofs] = nnz_upper (n_dofs + 1 entries). */
+int fem2d_plan_row_offsets(fem2d_plan* plan, uint64_t* row_ptr);
 /* Device pointers of the pattern (uint32 rows, cols; length nnz_upper). */
 int fem2d_plan_pattern_device(const fem2d_plan* plan, const uint32_t** d_rows, const uint32_t** d_cols);
 

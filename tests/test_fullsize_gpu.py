@@ -31,6 +31,18 @@ def test_sizes_match_closed_form(full):
     assert info["max_contrib"] == 2 and info["n_extra"] == 58240656 - 57557904
 
 
+def test_source_map_packs_and_keeps_plain_chunks(full):
+    """The scatter kernel reads a packed source map: most 64-slot chunks as 16-bit offsets, the chunks holding multi-contribution slots
+    (or spanning more than 2^16 value entries) in plain 32-bit form.  Both forms must occur at this size, so the bit-identity checks
+    in this file cover both code paths of the kernel."""
+    smi = full["plan"].source_map_info()
+    n_chunks = -(-full["plan"].nnz // smi["chunk_slots"])
+    assert 0 < smi["plain_chunks"] < 0.1 * n_chunks
+    assert smi["map_bytes"] < 0.6 * smi["plain_bytes"]
+    nd = F.Plan(full["domain"].view(), device=0, dedupe=False).source_map_info()
+    assert smi["plain_chunks"] <= nd["plain_chunks"] < 0.1 * n_chunks      # dedupe off: edge rows reach across distant value tiles
+
+
 def test_pattern_is_sorted_unique_upper_triangular(full):
     rows, cols = full["plan"].pattern()
     assert np.all(rows <= cols)

@@ -79,6 +79,25 @@ def test_device_pattern_matches_host_pattern():
         assert np.array_equal(pd.row_blocks(3), ph.row_blocks(3))
 
 
+def test_device_row_offsets_and_sliced_rows():
+    """Host `rows` are expanded from the device CSR row offsets (fem2d_plan_row_offsets), also for slices that start mid-row."""
+    df = F.Domain.from_mesh(recipes.build_pair("cfg4_small")[1])
+    plan = F.Plan(df.view(), device=0)
+    rows, cols = plan.pattern()
+    rp = plan.row_offsets()
+    assert np.array_equal(np.repeat(np.arange(df.num_dofs, dtype=np.uint32), np.diff(rp).astype(np.int64)), rows)
+    glq = _glq(8, 8)
+    _, _, a_full, b_full = plan.assemble(glq)
+    n = plan.nnz
+    ranges = [(3, n // 3 + 1), (n // 2 + 5, n - 2)]
+    m = sum(e - b for b, e in ranges)
+    r2 = np.zeros(m, dtype=np.uint32); c2 = np.zeros(m, dtype=np.uint32); a2 = np.zeros(m); b2 = np.zeros(m)
+    plan.assemble_ranges_into(glq, ranges, a2.ctypes.data, b2.ctypes.data, r2.ctypes.data, c2.ctypes.data)
+    sel = np.concatenate([np.arange(b, e) for b, e in ranges])
+    assert np.array_equal(r2, rows[sel]) and np.array_equal(c2, cols[sel])
+    _assert_bit_identical(a2, a_full[sel], "A slices"); _assert_bit_identical(b2, b_full[sel], "B slices")
+
+
 def test_reference_call_and_errors():
     _, mf = recipes.build_pair("nalg")
     df = F.Domain.from_mesh(mf)

@@ -112,6 +112,15 @@ def test_row_blocks_are_row_aligned_and_balanced():
         assert np.max(np.diff(b.astype(np.int64))) < plan.nnz / world + 500
 
 
+def test_row_offsets_are_the_csr_form_of_the_pattern():
+    df = F.Domain.from_mesh(recipes.build_pair("slepc")[1])
+    plan = F.Plan(df.view(), device=-1)
+    rows, _ = plan.pattern()
+    rp = plan.row_offsets()
+    assert len(rp) == df.num_dofs + 1 and rp[0] == 0 and rp[-1] == plan.nnz
+    assert np.array_equal(np.repeat(np.arange(df.num_dofs, dtype=np.uint32), np.diff(rp).astype(np.int64)), rows)
+
+
 def test_error_behaviour_mirrors_reference():
     m = F.Mesh.unit()
     m.h_refine_elems([0], F.HRef.T)
