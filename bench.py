@@ -252,11 +252,26 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = 2.0 * nnz / (ms_step * 1e-3)
 
-    # per-phase device durations of the timed steps (events recorded by the library on the same stream)
+    # per-phase device durations: the same steps again with the library's per-phase events switched on (CUDA events on the launch
+    # stream between the kernels).  They are off in the region above because an event between two kernels keeps the second from
+    # starting under programmatic dependent launch; `ms_per_step_with_phase_events` shows what that costs.
+    plan.set_phase_timing(True)
     n_back = min(args.steps, 64)
+    for _ in range(3):
+        step()
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    for _ in range(n_back):
+        step()
+    p1.record(stream)
+    torch.cuda.synchronize()
+    ms_step_events = p0.elapsed_time(p1) / n_back
     ph = np.array([[plan.last_timing(k)[key] for key in ("sampler_ms", "integrator_ms", "scatter_ms", "total_ms")] for k in range(n_back)])
     k1_ms, k2_ms, k3_ms, tot_ms = ph.mean(axis=0)
     launches_per_step = plan.last_timing(0)["launches"]
+    plan.set_phase_timing(False)
+    barrier()
 
     peaks, peak_kind = _peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -287,6 +302,7 @@ def run_ours(args):
             plan_nd.assemble_device(glq, d_a.data_ptr(), d_b.data_ptr(), mode=mode, stream=stream.cuda_stream)
         torch.cuda.synchronize()
         reps = 5
+        plan_nd.set_phase_timing(True)
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
         for _ in range(reps):
@@ -324,7 +340,9 @@ def run_ours(args):
                        "n_classes": info["n_classes"], "nnz_counted": "2 x nnz_upper (A and B)",
                        "l2_policy": "no flush: each step streams > 0.92 GB (A/B value arrays + source map) >> 126 MB L2",
                        "parallelism": f"row blocks x{world} (Elem-type rows + edge-type rows per rank), no collective" if world > 1 else "single GPU"},
-            "phases_ms": {"sampler_k1": float(k1_ms), "integrator_k2": float(k2_ms), "scatter_k3": float(k3_ms), "sum": float(tot_ms)},
+            "phases_ms": {"sampler_k1": float(k1_ms), "integrator_k2": float(k2_ms), "scatter_k3": float(k3_ms), "sum": float(tot_ms),
+                          "ms_per_step_with_phase_events": float(ms_step_events),
+                          "note": f"{n_back} extra steps with per-phase events on, right after the timed region"},
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,

@@ -74,7 +74,7 @@ class _View(C.Structure):
 ABI_SYMBOLS = [
     "fem2d_symbolic", "fem2d_plan_free", "fem2d_plan_info", "fem2d_plan_source_map_info", "fem2d_plan_row_offsets", "fem2d_plan_pattern", "fem2d_plan_pattern_device",
     "fem2d_assemble_device", "fem2d_assemble_device_ranges", "fem2d_plan_row_blocks_split", "fem2d_assemble_ranges", "fem2d_assemble", "fem2d_galerkin_sample_gep_hcurl", "fem2d_plan_row_blocks",
-    "fem2d_plan_last_timing", "fem2d_plan_timing", "fem2d_assemble_range", "fem2d_host_alloc", "fem2d_host_free", "fem2d_xy_fields", "fem2d_fp64_peak",
+    "fem2d_plan_last_timing", "fem2d_plan_timing", "fem2d_plan_set_phase_timing", "fem2d_assemble_range", "fem2d_host_alloc", "fem2d_host_free", "fem2d_xy_fields", "fem2d_fp64_peak",
     "fem2d_device_count", "fem2d_status_string", "fem2d_last_error", "fem2d_version",
 ]
 HOST_ABI_SYMBOLS = [
@@ -683,6 +683,10 @@ class Plan:
         _ck(_L.fem2d_assemble_ranges(self._h, basis.kind, a.kind, b.kind, int(mode), _p(up, C.c_double), _p(uw, C.c_double), C.c_uint32(len(up)),
                                      _p(vp, C.c_double), _p(vw, C.c_double), C.c_uint32(len(vp)), C.c_uint32(len(ranges)), _p(bg, C.c_uint64),
                                      _p(en, C.c_uint64), C.c_void_p(rows_ptr or None), C.c_void_p(cols_ptr or None), C.c_void_p(a_ptr), C.c_void_p(b_ptr)))
+
+    def set_phase_timing(self, on: bool = True):
+        """fem2d_plan_set_phase_timing: record per-phase CUDA events in the following numeric calls (off by default)."""
+        _ck(_L.fem2d_plan_set_phase_timing(self._h, int(bool(on))))
 
     def last_timing(self, calls_back: int = 0):
         ms = (C.c_float * 4)(); ln = (C.c_uint32 * 4)()

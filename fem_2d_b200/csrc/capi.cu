@@ -277,11 +277,14 @@ int fem2d_assemble_device_ranges(fem2d_plan* plan, int basis_kind, int a_kind, i
     }
     if (!p.d_V) CKS(fem2d::dev_malloc((void**)&p.d_V, std::max<uint64_t>(p.host.n_values, 1) * sizeof(double2), s));
     for (int k = 0; k < 4; k++) p.last_launches[k] = 0;
-    cudaEvent_t* ev = p.ev[p.n_calls % fem2d::Plan::RING];
-    CKS(cudaEventRecord(ev[0], s));
+    // Per-phase events are opt-in (fem2d_plan_set_phase_timing): an event between two kernels keeps the second one from starting
+    // under programmatic dependent launch, which is how the three kernels of a call overlap their launch latencies.
+    const bool timed = p.phase_timing;
+    cudaEvent_t* ev = p.ev[p.n_timed_calls % fem2d::Plan::RING];
+    if (timed) CKS(cudaEventRecord(ev[0], s));
     CKS(fem2d::launch_k1_tables(p, basis_kind, nu, nv, NO, NPT, s));
     p.last_launches[0] = 1;
-    CKS(cudaEventRecord(ev[1], s));
+    if (timed) CKS(cudaEventRecord(ev[1], s));
     if (mode == FEM2D_MODE_EXACT) {
         const fem2d::WorkItem* items = nullptr; uint32_t n_items = 0;
         std::string ierr;
@@ -291,11 +294,17 @@ int fem2d_assemble_device_ranges(fem2d_plan* plan, int basis_kind, int a_kind, i
     }
     else if (mode == FEM2D_MODE_SUMFACT) CKS(fem2d::launch_k2_sumfact(p, nu, nv, NO, NPT, s, &p.last_launches[1]));
     else CKS(fem2d::launch_k2_dmma(p, nu, nv, NO, NPT, s, &p.last_launches[1]));
-    CKS(cudaEventRecord(ev[2], s));
+    if (timed) CKS(cudaEventRecord(ev[2], s));
     CKS(fem2d::launch_k3_scatter(p, n_ranges, slot_begins, slot_ends, d_a, d_b, a_kind == FEM2D_INTEGRAL_L2_INNER, b_kind == FEM2D_INTEGRAL_L2_INNER, s, &p.last_launches[2]));
-    CKS(cudaEventRecord(ev[3], s));
+    if (timed) { CKS(cudaEventRecord(ev[3], s)); p.n_timed_calls++; }
     p.last_launches[3] = p.last_launches[0] + p.last_launches[1] + p.last_launches[2];
     p.n_calls++;
+    return FEM2D_OK;
+}
+
+int fem2d_plan_set_phase_timing(fem2d_plan* plan, int on) {
+    if (!plan) return fail(FEM2D_ERR_BAD_ARGUMENT, "null plan");
+    plan->p.phase_timing = on != 0;
     return FEM2D_OK;
 }
 
@@ -303,8 +312,9 @@ int fem2d_plan_timing(fem2d_plan* plan, uint32_t calls_back, float ms[4], uint32
     if (!plan) return fail(FEM2D_ERR_BAD_ARGUMENT, "null plan");
     fem2d::Plan& p = plan->p;
     if (p.device < 0) return fail(FEM2D_ERR_NO_DEVICE, "host-only plan");
-    if (calls_back >= fem2d::Plan::RING || calls_back >= p.n_calls) return fail(FEM2D_ERR_BAD_ARGUMENT, "no timing recorded that far back");
-    cudaEvent_t* ev = p.ev[(p.n_calls - 1 - calls_back) % fem2d::Plan::RING];
+    if (calls_back >= fem2d::Plan::RING || calls_back >= p.n_timed_calls)
+        return fail(FEM2D_ERR_BAD_ARGUMENT, "no timing recorded that far back (fem2d_plan_set_phase_timing enables the per-phase events)");
+    cudaEvent_t* ev = p.ev[(p.n_timed_calls - 1 - calls_back) % fem2d::Plan::RING];
     CKS(cudaSetDevice(p.device));
     CKS(cudaEventSynchronize(ev[3]));
     if (ms) {

@@ -68,7 +68,8 @@ struct Plan {
 
     static constexpr int RING = 64;      // event sets of the last RING numeric calls (read back without syncing in between)
     cudaEvent_t ev[RING][4] = {};
-    uint64_t n_calls = 0;
+    uint64_t n_calls = 0, n_timed_calls = 0;
+    bool phase_timing = false;           // record the per-phase events (costs the launch overlap between the kernels)
     uint32_t last_launches[4] = {0, 0, 0, 0};
     int max_smem_optin = 0;
     int sm_count = 0;

@@ -28,6 +28,9 @@ namespace {
 // One CTA per table, one thread per point.  Output layout: out[((arr * NO) + order) * NPT + point], arr: 0 N, 1 N', 2 T, 3 T'.
 __global__ void k1_tables_kernel(const TableDesc* __restrict__ tabs, double* __restrict__ out, uint32_t NO, uint32_t NPT,
                                  const double* __restrict__ glq, uint32_t nu, uint32_t nv, uint32_t i_max, uint32_t j_max, int basis) {
+    // programmatic dependent launch: let the integrator's CTAs start their prologue (work item, class, tile decode) right away;
+    // they wait for this grid's completion (cudaGridDependencySynchronize) before they read the tables
+    cudaTriggerProgrammaticLaunchCompletion();
     const TableDesc t = tabs[blockIdx.x];
     const uint32_t np = t.axis ? nv : nu, nmax = t.axis ? j_max : i_max;
     const double* pts = glq + (t.axis ? 256 : 0);
@@ -104,6 +107,7 @@ __device__ __forceinline__ void contract_run(const double*& cp, const double*& c
 template <int TP>
 __global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g) {
     extern __shared__ __align__(16) double smem[];
+    cudaTriggerProgrammaticLaunchCompletion();   // the scatter kernel may start loading its source offsets (it waits before reading V)
     const WorkItem it = g.items[blockIdx.x];
     const ClassDesc c = g.classes[it.cls];
     const ListDesc LP = g.lists[c.listP], LQ = g.lists[c.listQ];
@@ -142,6 +146,7 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g)
     __syncthreads();
     const bool single_chunk = chunk >= npts;
     double2* out = g.V + c.v_off;
+    cudaGridDependencySynchronize();   // the sampler's tables (and, transitively, the previous call's readers of V) are complete
 
     for (uint32_t round0 = 0; round0 < it.mt_count; round0 += K2_THREADS) {
         // ---- my micro-tile of this round
@@ -302,10 +307,14 @@ cudaError_t launch_k2_exact(const Plan& P, const WorkItem* d_items, uint32_t n_i
         smem_set[P.device] = smem;
     }
     K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, chunk};
-    if (P.host.tile_p == 1) k2_exact_kernel<1><<<n_items, K2_THREADS, smem, st>>>(g);
-    else k2_exact_kernel<4><<<n_items, K2_THREADS, smem, st>>>(g);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_items); cfg.blockDim = dim3(K2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cudaError_t e = P.host.tile_p == 1 ? cudaLaunchKernelEx(&cfg, k2_exact_kernel<1>, g) : cudaLaunchKernelEx(&cfg, k2_exact_kernel<4>, g);
     if (launches) (*launches)++;
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t fp64_peak(int kind, double* gflops) {

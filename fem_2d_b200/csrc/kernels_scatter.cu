@@ -27,12 +27,21 @@ struct K3Args {
     int selA, selB;
 };
 
+// V is written by the integrator grid that, under programmatic dependent launch, can still be running when this grid starts:
+// read it with plain loads after cudaGridDependencySynchronize() (L1 is clean at grid start and no V line is touched before the
+// wait), never through the non-coherent path, whose read-only contract would not hold.
+__device__ __forceinline__ double2 ld_v(const double2* p) {
+    double2 v;
+    asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ double2 k3_value(const K3Args& g, unsigned long long slot, uint32_t s) {
-    if (!(s & 0x80000000u)) return __ldg(&g.V[s]);
+    if (!(s & 0x80000000u)) return ld_v(&g.V[s]);
     unsigned long long k = s & 0x7fffffffu;
-    double2 v = __ldg(&g.V[g.extra_first[k]]);
+    double2 v = ld_v(&g.V[g.extra_first[k]]);
     do {   // *current_value += value (sparse_matrix.rs:61,115), sequentially in the plan's fixed order
-        const double2 e = __ldg(&g.V[g.extra_src[k]]);
+        const double2 e = ld_v(&g.V[g.extra_src[k]]);
         v.x = v.x + e.x; v.y = v.y + e.y;
         k++;
     } while (k < g.n_extra && g.extra_slot[k] == slot);
@@ -79,9 +88,12 @@ __global__ void __launch_bounds__(K3_THREADS) k3_gather_kernel(const K3Args g) {
         src[it] += b;
         if (b == SRC_CHUNK_PLAIN) src[it] = ok[it] ? __ldg(&g.src1[base + it * 32]) : 0u;
     }
+    // programmatic dependent launch: everything above only reads the plan's source map and may overlap the integrator's tail;
+    // V is complete once the preceding grid is
+    cudaGridDependencySynchronize();
     double2 v[K3_ITERS];
 #pragma unroll
-    for (uint32_t it = 0; it < K3_ITERS; it++) v[it] = __ldg(&g.V[(src[it] & 0x80000000u) ? 0u : src[it]]);
+    for (uint32_t it = 0; it < K3_ITERS; it++) v[it] = ld_v(&g.V[(src[it] & 0x80000000u) ? 0u : src[it]]);
     bool any = false;
 #pragma unroll
     for (uint32_t it = 0; it < K3_ITERS; it++) {
@@ -119,9 +131,14 @@ cudaError_t launch_k3_scatter(const Plan& P, uint32_t n_ranges, const uint64_t* 
     }
     g.first_block[g.n_ranges] = (uint32_t)blocks;
     if (blocks == 0) return cudaSuccess;
-    k3_gather_kernel<<<(unsigned)blocks, K3_THREADS, 0, st>>>(g);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(K3_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k3_gather_kernel, g);
     if (launches) (*launches)++;
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace fem2d

@@ -162,7 +162,11 @@ int fem2d_plan_row_blocks(const fem2d_plan* plan, uint32_t world, uint64_t* boun
  * integrator across ranks. */
 int fem2d_plan_row_blocks_split(const fem2d_plan* plan, uint32_t world, uint64_t* bounds_single, uint64_t* bounds_shared);
 
-/* Per-phase device timings of the last numeric call in milliseconds (CUDA events on the launch stream):
+/* Per-phase timing is opt-in: with `on` != 0 every numeric call records CUDA events between its kernels (sampler, integrator, scatter).
+ * Off (the default) the three kernels are chained by programmatic dependent launch and overlap their launch latencies and prologues. */
+int fem2d_plan_set_phase_timing(fem2d_plan* plan, int on);
+
+/* Per-phase device timings of the last timed numeric call in milliseconds (CUDA events on the launch stream):
  * ms[0] sampler (K1), ms[1] integrator (K2), ms[2] scatter (K3), ms[3] total; launches[0..2] kernel launch counts. */
 int fem2d_plan_last_timing(fem2d_plan* plan, float ms[4], uint32_t launches[4]);
 /* Same for the numeric call `calls_back` calls ago (0 = last; the plan keeps the events of its last 64 calls). */

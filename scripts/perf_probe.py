@@ -15,7 +15,7 @@ for wl in which:
     g = bench.WORKLOADS[wl]["glq"]
     glq = (F.gauss_quadrature_points(g), F.gauss_quadrature_points(g))
     for dedupe in (1, 0):
-        plan = F.Plan(v, device=0, dedupe=bool(dedupe))
+        plan = F.Plan(v, device=0, dedupe=bool(dedupe)); plan.set_phase_timing(True)
         da = torch.empty(plan.nnz, dtype=torch.float64, device="cuda"); db = torch.empty_like(da)
         for mname in mlist:
             try:

@@ -11,7 +11,7 @@ modes = {"exact": F.MODE_EXACT, "sumfact": F.MODE_SUMFACT, "dmma": F.MODE_DMMA}
 d = bench.build_product_domain(wl); v = d.view()
 g = bench.WORKLOADS[wl]["glq"]
 glq = (F.gauss_quadrature_points(g), F.gauss_quadrature_points(g))
-plan = F.Plan(v, device=0, dedupe=bool(dedupe))
+plan = F.Plan(v, device=0, dedupe=bool(dedupe)); plan.set_phase_timing(True)
 a = torch.empty(plan.nnz, dtype=torch.float64, device="cuda"); b = torch.empty_like(a)
 for _ in range(steps):
     plan.assemble_device(glq, a.data_ptr(), b.data_ptr(), mode=modes[mode])
