@@ -287,10 +287,11 @@ int fem2d_assemble_device_ranges(fem2d_plan* plan, int basis_kind, int a_kind, i
     if (timed) CKS(cudaEventRecord(ev[1], s));
     if (mode == FEM2D_MODE_EXACT) {
         const fem2d::WorkItem* items = nullptr; uint32_t n_items = 0;
+        fem2d::ItemSplit split;
         std::string ierr;
-        const int ist = fem2d::device_range_items(p, n_ranges, slot_begins, slot_ends, &items, &n_items, ierr);
+        const int ist = fem2d::device_range_items(p, n_ranges, slot_begins, slot_ends, &items, &n_items, &split, ierr);
         if (ist != FEM2D_OK) return fail(ist, ierr);
-        CKS(fem2d::launch_k2_exact(p, items, n_items, nu, nv, NO, NPT, s, &p.last_launches[1]));
+        CKS(fem2d::launch_k2_exact(p, items, n_items, split.n_big, split.stride_big, split.stride_small, nu, nv, NO, NPT, s, &p.last_launches[1]));
     }
     else if (mode == FEM2D_MODE_SUMFACT) CKS(fem2d::launch_k2_sumfact(p, nu, nv, NO, NPT, s, &p.last_launches[1]));
     else CKS(fem2d::launch_k2_dmma(p, nu, nv, NO, NPT, s, &p.last_launches[1]));

@@ -162,6 +162,7 @@ int device_symbolic(Plan& P, std::string& err) {
     CK(cudaDeviceGetAttribute(&P.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, P.device));
     CK(cudaDeviceGetAttribute(&P.sm_count, cudaDevAttrMultiProcessorCount, P.device));
     const uint32_t np = (uint32_t)H.n_pairs;
+    P.split = split_items(H, H.items);
 
     // ---- descriptor blob (plan-owned part first, then the scratch-only part), laid out identically on host and device
     std::vector<DevBlock> hb(H.blocks.size());
@@ -326,14 +327,34 @@ __global__ void mark_tiles_kernel(const uint32_t* __restrict__ src1, const uint3
 }
 }  // namespace
 
-int device_range_items(Plan& P, uint32_t n_ranges, const uint64_t* begins, const uint64_t* ends, const WorkItem** d_items, uint32_t* n_items, std::string& err) {
+ItemSplit split_items(const HostPlan& H, const std::vector<WorkItem>& items) {
+    ItemSplit sp;
+    auto stride_of = [&](const WorkItem& it) {
+        const ClassDesc& c = H.classes[it.cls];
+        const ListDesc& LP = H.lists[c.listP]; const ListDesc& LQ = H.lists[c.listQ];
+        uint32_t s = slab_pad4(LP.nU) + slab_pad4(LP.n - LP.nU);
+        if (!c.local) s += slab_pad4(LQ.nU) + slab_pad4(LQ.n - LQ.nU);
+        return s;
+    };
+    // the latency shape (1 x 2 tiles, small plans) keeps one CTA size
+    const uint32_t small_tiles = H.tile_p == 1 ? 0u : (uint32_t)K2_SMALL_TILES;
+    for (const WorkItem& it : items) {
+        const bool big = it.mt_count > small_tiles || stride_of(it) > (uint32_t)K2_SMALL_STRIDE;
+        if (big) { sp.n_big++; sp.stride_big = std::max(sp.stride_big, stride_of(it)); }
+        else sp.stride_small = std::max(sp.stride_small, stride_of(it));
+    }
+    return sp;
+}
+
+int device_range_items(Plan& P, uint32_t n_ranges, const uint64_t* begins, const uint64_t* ends, const WorkItem** d_items, uint32_t* n_items, ItemSplit* split,
+                       std::string& err) {
     if (n_ranges > MAX_SLOT_RANGES) { err = "too many slot ranges"; return FEM2D_ERR_BAD_ARGUMENT; }
     const bool full = n_ranges == 1 && begins[0] == 0 && ends[0] >= P.nnz;
     // restricting is pointless when the whole integrator is a single wave of CTAs anyway
-    if (full || P.total_mt < (uint64_t)4 * 148 * K2_THREADS) { *d_items = P.d_items; *n_items = (uint32_t)P.host.items.size(); return FEM2D_OK; }
+    if (full || P.total_mt < (uint64_t)4 * 148 * K2_THREADS) { *d_items = P.d_items; *n_items = (uint32_t)P.host.items.size(); *split = P.split; return FEM2D_OK; }
     bool same = P.d_range_items && n_ranges == P.range_n;
     for (uint32_t k = 0; same && k < n_ranges; k++) same = begins[k] == P.range_begin[k] && ends[k] == P.range_end[k];
-    if (same) { *d_items = P.d_range_items; *n_items = P.n_range_items; return FEM2D_OK; }
+    if (same) { *d_items = P.d_range_items; *n_items = P.n_range_items; *split = P.range_split; return FEM2D_OK; }
     CK(cudaSetDevice(P.device));
     unsigned char* d_flags = nullptr;
     CK(dev_malloc((void**)&d_flags, P.total_mt));
@@ -400,6 +421,7 @@ int device_range_items(Plan& P, uint32_t n_ranges, const uint64_t* begins, const
     CK(dev_malloc((void**)&P.d_range_items, std::max<size_t>(items.size(), 1) * sizeof(WorkItem)));
     CK(cudaMemcpy(P.d_range_items, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
     P.n_range_items = (uint32_t)items.size(); P.range_n = n_ranges; P.range_mt_needed = needed;
+    P.range_split = split_items(P.host, items); *split = P.range_split;
     for (uint32_t k = 0; k < n_ranges; k++) { P.range_begin[k] = begins[k]; P.range_end[k] = ends[k]; }
     *d_items = P.d_range_items; *n_items = P.n_range_items;
     return FEM2D_OK;

@@ -46,7 +46,11 @@ __global__ void k1_tables_kernel(const TableDesc* __restrict__ tabs, double* __r
 struct K2Args {
     const ClassDesc* classes; const ListDesc* lists; const uint8_t* spec_i; const uint8_t* spec_j;
     const WorkItem* items; const double* tabs; const double* glq; double2* V;
-    uint32_t NO, NPT, nu, nv, chunk_pts;
+    uint32_t NO, NPT, nu, nv, slab_doubles;   // slab_doubles: shared-memory doubles available for the slabs of one CTA
+    // 1: this grid follows the sampler in the stream (it waits for it before reading the tables and only then lets its dependents
+    // launch); 0: it follows the first integrator grid, which it does not depend on -- it runs alongside it and waits for it only
+    // before exiting, so that a grid waiting on this one has transitively waited on both.
+    int follows_sampler;
 };
 
 __device__ __forceinline__ uint32_t pad4(uint32_t x) { return (x + 3u) & ~3u; }
@@ -104,17 +108,21 @@ __device__ __forceinline__ void contract_run(const double*& cp, const double*& c
     }
 }
 
-template <int TP>
-__global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g) {
+template <int TP, int NT>
+__global__ void __launch_bounds__(NT, NT == K2_THREADS ? K2_MIN_CTAS : K2_SMALL_CTAS) k2_exact_kernel(const K2Args g) {
     extern __shared__ __align__(16) double smem[];
-    cudaTriggerProgrammaticLaunchCompletion();   // the scatter kernel may start loading its source offsets (it waits before reading V)
+    // programmatic dependent launch: the next grid (second integrator grid or the scatter kernel, which starts by loading its
+    // source offsets and waits before reading V) may start once every CTA of this one has passed this point
+    if (!g.follows_sampler) cudaTriggerProgrammaticLaunchCompletion();
     const WorkItem it = g.items[blockIdx.x];
     const ClassDesc c = g.classes[it.cls];
     const ListDesc LP = g.lists[c.listP], LQ = g.lists[c.listQ];
     const uint32_t nP = LP.n, nUP = LP.nU, nQ = LQ.n, nUQ = LQ.nU;
     const uint32_t strideP = pad4(nUP) + pad4(nP - nUP);
     const uint32_t strideQ = c.local ? strideP : pad4(nUQ) + pad4(nQ - nUQ);
-    const uint32_t nu = g.nu, nv = g.nv, npts = nu * nv, chunk = g.chunk_pts;
+    const uint32_t nu = g.nu, nv = g.nv, npts = nu * nv;
+    // points per staging chunk: as many as this class's slab rows (C and F of P, and of Q unless local) fit
+    const uint32_t chunk = min(npts, g.slab_doubles / (2 * (strideP + (c.local ? 0u : strideQ))));
 
     double* s_uw = smem;                       // [128]
     double* s_vw = smem + 128;                 // [128]
@@ -146,9 +154,12 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g)
     __syncthreads();
     const bool single_chunk = chunk >= npts;
     double2* out = g.V + c.v_off;
-    cudaGridDependencySynchronize();   // the sampler's tables (and, transitively, the previous call's readers of V) are complete
+    if (g.follows_sampler) {
+        cudaGridDependencySynchronize();   // the sampler's tables (and, transitively, the previous call's readers of V) are complete
+        cudaTriggerProgrammaticLaunchCompletion();
+    }
 
-    for (uint32_t round0 = 0; round0 < it.mt_count; round0 += K2_THREADS) {
+    for (uint32_t round0 = 0; round0 < it.mt_count; round0 += NT) {
         // ---- my micro-tile of this round
         const bool active = round0 + threadIdx.x < it.mt_count;
         uint32_t sub = 0, row0 = 0, col0 = 0, row_end = 0, col_end = 0, prow = 0, pcol = 0;
@@ -261,6 +272,7 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_exact_kernel(const K2Args g)
             }
         }
     }
+    if (!g.follows_sampler) cudaGridDependencySynchronize();   // do not complete before the first integrator grid has
 }
 
 // ---------------------------------------------------------------------------------------------------------------- FP64 peak
@@ -287,34 +299,55 @@ cudaError_t launch_k1_tables(const Plan& P, int basis_kind, uint32_t nu, uint32_
     return cudaGetLastError();
 }
 
-cudaError_t launch_k2_exact(const Plan& P, const WorkItem* d_items, uint32_t n_items, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches) {
-    if (n_items == 0) return cudaSuccess;
-    // shared memory: 256 doubles of weights + chunk * (C and F slabs of both sides).  Prefer <= ~100 KB so two CTAs share an SM.
-    const uint32_t max_stride = P.host.max_slab_stride;   // widest class: pad4(U) + pad4(V) functions of P (+ of Q unless local)
+// One launch of the exact integrator over items [first, first + count) with CTAs of NT threads; max_stride = widest slab row
+// among those items' classes, soft = shared-memory budget per CTA that keeps the intended number of CTAs on an SM.
+template <int NT>
+static cudaError_t launch_k2_part(const Plan& P, const WorkItem* d_items, uint32_t count, uint32_t max_stride, size_t soft, uint32_t nu, uint32_t nv,
+                                  uint32_t NO, uint32_t NPT, int follows_sampler, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    // shared memory: 256 doubles of weights + the slabs (C and F of both sides) of as many points as fit; every CTA sizes its own
+    // chunk from its class's row width, the launch only fixes the budget: `soft` unless the widest class cannot even stage one
+    // quadrature row in it
     const size_t per_pt = (size_t)max_stride * 2 * sizeof(double);
     const size_t fixed = 256 * sizeof(double);
-    const size_t soft = 100 * 1024, hard = (size_t)P.max_smem_optin - 1024;
+    const size_t hard = (size_t)P.max_smem_optin - 1024;
     const uint32_t npts = nu * nv;
-    uint32_t chunk = (uint32_t)std::min<size_t>(npts, (soft - fixed) / per_pt);
-    if (chunk < std::min<uint32_t>(npts, nv)) chunk = (uint32_t)std::min<size_t>(npts, (hard - fixed) / per_pt);   // at least one row if possible
-    if (chunk == 0) return cudaErrorInvalidConfiguration;
-    const size_t smem = fixed + (size_t)chunk * per_pt;
-    static thread_local size_t smem_set[64] = {};   // per device: largest dynamic shared memory size already opted in
+    size_t smem = std::min(soft, fixed + (size_t)npts * per_pt);
+    if ((smem - fixed) / per_pt < std::min<uint32_t>(npts, nv)) smem = std::min(hard, fixed + (size_t)std::min<uint32_t>(npts, nv) * per_pt);
+    if ((smem - fixed) / per_pt == 0) return cudaErrorInvalidConfiguration;
+    const uint32_t slab_doubles = (uint32_t)((smem - fixed) / sizeof(double));
+    static thread_local size_t smem_set[64] = {};   // per device: largest dynamic shared memory size already opted in (per NT)
     if (P.device >= 0 && P.device < 64 && smem > smem_set[P.device]) {
-        cudaError_t e = cudaFuncSetAttribute(k2_exact_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k2_exact_kernel<4, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_exact_kernel<1, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         smem_set[P.device] = smem;
     }
-    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, chunk};
+    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, slab_doubles, follows_sampler};
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(n_items); cfg.blockDim = dim3(K2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.gridDim = dim3(count); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    const cudaError_t e = P.host.tile_p == 1 ? cudaLaunchKernelEx(&cfg, k2_exact_kernel<1>, g) : cudaLaunchKernelEx(&cfg, k2_exact_kernel<4>, g);
-    if (launches) (*launches)++;
+    const cudaError_t e = P.host.tile_p == 1 ? cudaLaunchKernelEx(&cfg, k2_exact_kernel<1, NT>, g) : cudaLaunchKernelEx(&cfg, k2_exact_kernel<4, NT>, g);
     return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+// Items are ordered by size (largest first); the first n_big of them run in K2_THREADS-wide CTAs, the rest in K2_SMALL_THREADS-wide
+// ones.  Both launches carry the programmatic-dependent-launch attribute: the small CTAs start filling SMs as soon as the last
+// big CTA has started, and wait for the big grid's completion before they exit, so that whoever waits on the second grid (the
+// scatter kernel) transitively waits on the first.
+cudaError_t launch_k2_exact(const Plan& P, const WorkItem* d_items, uint32_t n_items, uint32_t n_big, uint32_t stride_big, uint32_t stride_small,
+                            uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches) {
+    if (n_items == 0) return cudaSuccess;
+    n_big = std::min(n_big, n_items);
+    // big CTAs: prefer <= ~100 KB of shared memory so two share an SM; small CTAs: 1/8 of an SM's shared memory each
+    cudaError_t e = launch_k2_part<K2_THREADS>(P, d_items, n_big, stride_big, 100 * 1024, nu, nv, NO, NPT, 1, st);
+    if (e != cudaSuccess) return e;
+    if (launches && n_big) (*launches)++;
+    e = launch_k2_part<K2_SMALL_THREADS>(P, d_items + n_big, n_items - n_big, stride_small, 27 * 1024, nu, nv, NO, NPT, n_big == 0, st);
+    if (launches && n_items > n_big) (*launches)++;
+    return e;
 }
 
 cudaError_t fp64_peak(int kind, double* gflops) {

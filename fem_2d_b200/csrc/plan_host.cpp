@@ -369,6 +369,8 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
             if (e > b) P.items.push_back(make_item(P, c, {{b, e - b}}, nullptr));
         }
     }
+    // largest first: longest-processing-time order, and the size split of the integrator launch (device_plan.hpp split_items)
+    std::stable_sort(P.items.begin(), P.items.end(), [](const WorkItem& x, const WorkItem& y) { return x.mt_count > y.mt_count; });
     return FEM2D_OK;
 }
 

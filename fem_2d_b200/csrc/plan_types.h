@@ -21,6 +21,13 @@ constexpr int MT_Q = 2;            // micro-tile: Q functions (cols) per thread
 constexpr int K2_THREADS = 256;
 constexpr int K2_MIN_CTAS = 2;     // CTAs per SM the integrator is compiled for
 constexpr int K2_ROUNDS = 2;    // a work item covers up to K2_ROUNDS * K2_THREADS micro-tiles of one class (slabs staged once)
+// Work items with at most K2_SMALL_TILES micro-tiles (small classes: low-order Elems of an hp-mesh, remainders) run in CTAs of
+// K2_SMALL_THREADS threads, K2_SMALL_CTAS of which share an SM: a 256-thread CTA with a handful of active threads would hold half
+// an SM's registers for the whole quadrature loop.
+constexpr int K2_SMALL_THREADS = 64;
+constexpr int K2_SMALL_CTAS = 8;
+constexpr int K2_SMALL_TILES = 2 * K2_SMALL_THREADS;
+constexpr int K2_SMALL_STRIDE = 64;   // ... and a slab row of at most this many functions (1 KB per quadrature point)
 
 struct ClassDesc {
     double dxP, dyP, dxQ, dyQ;   // dx_du, dy_dv (element.rs:46-47) of P's Elem and of Q's Elem
