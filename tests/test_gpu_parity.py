@@ -79,6 +79,41 @@ def test_device_pattern_matches_host_pattern():
         assert np.array_equal(pd.row_blocks(3), ph.row_blocks(3))
 
 
+def _pair_from(build):
+    return build(recipes.api("oracle")), build(recipes.api("product"))
+
+
+def test_exact_at_the_limits():
+    """Maximum sizes of the path: MAX_POLYNOMIAL_ORDER = 20 (mesh.rs:42; 1 680 functions per Elem, multi-round work items and the widest
+    slab rows), 128 GLQ points per axis (= default_ngq(20), basis.rs:172-177; many staging chunks) and the reference's default GLQ
+    (glq_grid_dim = None)."""
+    def order20(api):
+        m = api.Mesh.from_file(recipes.MESH_C)
+        api.set_orders(m, 20, 20)
+        return m
+    mo, mf = _pair_from(order20)
+    do, df = O.Domain.from_mesh(mo), F.Domain.from_mesh(mf)
+    glq = _glq(6, 5)
+    ref = O.galerkin_sample_gep_hcurl(do, glq=glq)
+    rows, cols, a, b = F.Plan(df.view(), device=0).assemble(glq)
+    assert np.array_equal(rows, ref.rows) and np.array_equal(cols, ref.cols)
+    _assert_bit_identical(a, ref.a, "A[order 20]"); _assert_bit_identical(b, ref.b, "B[order 20]")
+
+    mo, mf = recipes.build_pair("nalg")
+    do, df = O.Domain.from_mesh(mo), F.Domain.from_mesh(mf)
+    glq = _glq(128, 128)
+    ref = O.galerkin_sample_gep_hcurl(do, glq=glq)
+    for dedupe in (True, False):
+        rows, cols, a, b = F.Plan(df.view(), device=0, dedupe=dedupe).assemble(glq)
+        _assert_bit_identical(a, ref.a, "A[128x128]"); _assert_bit_identical(b, ref.b, "B[128x128]")
+
+    # glq_grid_dim = None -> default_ngq(max order) points per axis (galerkin.rs:66-67, basis.rs:83-90): order 3 -> 16 x 16
+    assert F.default_ngq(3) == 16 and F.default_ngq(20) == 128
+    gep = F.galerkin_sample_gep_hcurl(df, None, device=0)
+    ref = O.galerkin_sample_gep_hcurl(do, glq=_glq(16, 16))
+    _assert_bit_identical(gep.a.values, ref.a, "A[default GLQ]"); _assert_bit_identical(gep.b.values, ref.b, "B[default GLQ]")
+
+
 def test_device_row_offsets_and_sliced_rows():
     """Host `rows` are expanded from the device CSR row offsets (fem2d_plan_row_offsets), also for slices that start mid-row."""
     df = F.Domain.from_mesh(recipes.build_pair("cfg4_small")[1])
