@@ -4,6 +4,9 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <new>
 #include <string>
 #include <thread>
@@ -165,18 +168,42 @@ int fem2d_plan_row_offsets(fem2d_plan* plan, uint64_t* row_ptr) {
     return FEM2D_OK;
 }
 
-// rows[k] for the slots [b, e) written to out[0 .. e-b): expansion of the CSR row offsets on `threads` host threads
+// rows[k] for the slots [b, e) written to out[0 .. e-b): expansion of the CSR row offsets on `threads` host threads.  The destination
+// is a large (pinned) buffer next to the ones the GPU's DMA engine is filling at the same time, so each worker assembles whole
+// 64-byte lines in a small cache-resident block and moves them out with non-temporal stores: no read-for-ownership traffic on the
+// memory controllers the DMA writes through.  (Streaming the short per-row runs directly would issue partial-line writes.)
 static void expand_rows(const uint32_t* row_ptr, uint32_t n_rows, uint64_t b, uint64_t e, uint32_t* out, unsigned threads) {
     if (e <= b) return;
     auto work = [=](uint64_t lo, uint64_t hi) {
         // row holding slot lo: last r with row_ptr[r] <= lo
         uint32_t r = (uint32_t)(std::upper_bound(row_ptr, row_ptr + n_rows + 1, (uint32_t)lo) - row_ptr) - 1;
+        uint64_t next = row_ptr[r + 1];
+        constexpr uint32_t BLK = 2048;                          // 8 KB staging block
+        alignas(64) uint32_t buf[BLK];
         uint64_t s = lo;
         while (s < hi) {
-            const uint64_t stop = std::min<uint64_t>(row_ptr[r + 1], hi);
-            std::fill(out + (s - b), out + (stop - b), r);
-            s = stop; r++;
+            uint32_t* dst = out + (s - b);
+            // first block: up to the next 64-byte boundary of the destination, then whole blocks
+            uint32_t n = (uint32_t)std::min<uint64_t>(BLK, hi - s);
+            const uintptr_t mis = reinterpret_cast<uintptr_t>(dst) & 63u;
+            if (mis) n = (uint32_t)std::min<uint64_t>(n, (64 - mis) / 4);
+            for (uint32_t k = 0; k < n;) {
+                while (s + k >= next) { r++; next = row_ptr[r + 1]; }
+                const uint32_t run = (uint32_t)std::min<uint64_t>(n - k, next - (s + k));
+                std::fill(buf + k, buf + k + run, r);
+                k += run;
+            }
+#if defined(__SSE2__)
+            if (!mis && n % 16 == 0) {
+                for (uint32_t k = 0; k < n; k += 4) _mm_stream_si128(reinterpret_cast<__m128i*>(dst + k), _mm_load_si128(reinterpret_cast<const __m128i*>(buf + k)));
+            } else
+#endif
+                std::memcpy(dst, buf, (size_t)n * 4);
+            s += n;
         }
+#if defined(__SSE2__)
+        _mm_sfence();   // streaming stores are weakly ordered: drain them before this worker reports completion
+#endif
     };
     threads = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(threads, (e - b) / (1u << 20)));
     if (threads == 1) { work(b, e); return; }
