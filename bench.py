@@ -33,6 +33,8 @@ WORKLOADS = {
     "cfg3": dict(mesh="a", order=6, levels=6, glq=8),        # BASELINE.json configs[2] (headline, ~1M DoFs)
     "cfg3_l5": dict(mesh="a", order=6, levels=5, glq=8),
     "cfg3_l4": dict(mesh="a", order=6, levels=4, glq=8),
+    "cfg3_l3": dict(mesh="a", order=6, levels=3, glq=8),
+    "cfg3_l2": dict(mesh="a", order=6, levels=2, glq=8),
     "cfg2": dict(mesh="b", order=8, levels=3, glq=12),       # BASELINE.json configs[1]
     "cfg4": dict(mesh="c4", glq=12),                         # BASELINE.json configs[3] (anisotropic, random p)
 }
@@ -156,16 +158,19 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    # bounded sample: the same mesh family at fewer refinement levels, sized so (steps + warmup) runs end within minutes
-    probe = cpu_port_run("cfg3_l4", threads)
+    # bounded sample: the same mesh family at fewer refinement levels (each level = 4x the work), the largest whose (steps + warmup)
+    # runs end within the budget
     budget = 150.0
     total = args.steps + args.warmup
-    sample = "cfg3_l4"
-    if probe["seconds"] * 4 * total <= budget:
-        sample = "cfg3_l5"
+    probe = cpu_port_run("cfg3_l2", threads)
+    sample, est = "cfg3_l2", probe["seconds"]
+    for nxt in ("cfg3_l3", "cfg3_l4", "cfg3_l5"):
+        if est * 4.3 * total > budget:
+            break
+        sample, est = nxt, est * 4.3
     results = []
     for k in range(total):
-        r = probe if (sample == "cfg3_l4" and k == 0) else cpu_port_run(sample, threads)
+        r = cpu_port_run(sample, threads)
         if k >= args.warmup:
             results.append(r)
     sec = sum(r["seconds"] for r in results)
