@@ -7,7 +7,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, pat = sys.argv[1], sys.argv[2]
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 30
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(out)))
+allrows = list(csv.reader(io.StringIO(out)))
+# one section per profiled launch: ["Kernel Name", name] / header / data...; take the first section whose kernel matches `pat`
+starts = [i for i, r in enumerate(allrows) if r and r[0] == "Kernel Name"] + [len(allrows)]
+import re as _re
+want = _re.sub(r"I?L[ib](\d+)E", r"\1", pat)
+sec = next((k for k in range(len(starts) - 1) if all(tok in allrows[starts[k]][1].replace("(int)", "").replace(" ", "") for tok in _re.findall(r"[A-Za-z_0-9]+", want) if not tok.isdigit() or True)), 0)
+rows = allrows[starts[sec]:starts[sec + 1]]
+print("section:", rows[0][1][:90])
 hdr = rows[1]
 iA, iS, iSamp, iInst = hdr.index("Address"), hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
