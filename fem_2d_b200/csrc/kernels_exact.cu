@@ -67,16 +67,15 @@ __device__ __forceinline__ void contract_point(const double* __restrict__ cp, co
     }
 #pragma unroll
     for (int c = 0; c < MT_Q; c += 2) { const double2 t = *reinterpret_cast<const double2*>(cq + c); qc[c] = t.x; qc[c + 1] = t.y; }
+    // The operations of one pair form a dependent chain (8-cycle FP64 latency each); they are written stage by stage over the
+    // TP x MT_Q independent pairs so that the in-order issue always has independent work (same operations, same order per value).
+    double tA[TP][MT_Q];
 #pragma unroll
     for (int r = 0; r < TP; r++)
 #pragma unroll
-        for (int c = 0; c < MT_Q; c++) {
-            double t = pc[r] * qc[c];              // p_curl * q_curl
-            if (SAME) t = t * ratio;               // * max_uv_ratios / max_vu_ratios (integrals.rs:50,86)
-            inA[r][c] = inA[r][c] + t * w;         // inner_solution += integrand * v_w (glq.rs:27)
-        }
+        for (int c = 0; c < MT_Q; c++) tA[r][c] = pc[r] * qc[c];              // p_curl * q_curl
     if (SAME) {
-        double pf[TP], qf[MT_Q];
+        double pf[TP], qf[MT_Q], tB[TP][MT_Q];
         if (TP == 1) pf[0] = fp[0];
         else {
 #pragma unroll
@@ -87,11 +86,40 @@ __device__ __forceinline__ void contract_point(const double* __restrict__ cp, co
 #pragma unroll
         for (int r = 0; r < TP; r++)
 #pragma unroll
-            for (int c = 0; c < MT_Q; c++) {
-                double t = pf[r] * qf[c];          // V2D::dot(f_p, f_q): the second product is a signed zero
-                t = t * maxdet;                    // * partial_max(det_P, det_Q) (integrals.rs:312-315)
-                inB[r][c] = inB[r][c] + t * w;
-            }
+            for (int c = 0; c < MT_Q; c++) tB[r][c] = pf[r] * qf[c];          // V2D::dot(f_p, f_q): the second product is a signed zero
+#pragma unroll
+        for (int r = 0; r < TP; r++)
+#pragma unroll
+            for (int c = 0; c < MT_Q; c++) tA[r][c] = tA[r][c] * ratio;       // * max_uv_ratios / max_vu_ratios (integrals.rs:50,86)
+#pragma unroll
+        for (int r = 0; r < TP; r++)
+#pragma unroll
+            for (int c = 0; c < MT_Q; c++) tB[r][c] = tB[r][c] * maxdet;      // * partial_max(det_P, det_Q) (integrals.rs:312-315)
+#pragma unroll
+        for (int r = 0; r < TP; r++)
+#pragma unroll
+            for (int c = 0; c < MT_Q; c++) tA[r][c] = tA[r][c] * w;
+#pragma unroll
+        for (int r = 0; r < TP; r++)
+#pragma unroll
+            for (int c = 0; c < MT_Q; c++) tB[r][c] = tB[r][c] * w;
+#pragma unroll
+        for (int r = 0; r < TP; r++)
+#pragma unroll
+            for (int c = 0; c < MT_Q; c++) inA[r][c] = inA[r][c] + tA[r][c];  // inner_solution += integrand * v_w (glq.rs:27)
+#pragma unroll
+        for (int r = 0; r < TP; r++)
+#pragma unroll
+            for (int c = 0; c < MT_Q; c++) inB[r][c] = inB[r][c] + tB[r][c];
+    } else {
+#pragma unroll
+        for (int r = 0; r < TP; r++)
+#pragma unroll
+            for (int c = 0; c < MT_Q; c++) tA[r][c] = tA[r][c] * w;
+#pragma unroll
+        for (int r = 0; r < TP; r++)
+#pragma unroll
+            for (int c = 0; c < MT_Q; c++) inA[r][c] = inA[r][c] + tA[r][c];
     }
 }
 
