@@ -114,6 +114,30 @@ def test_exact_at_the_limits():
     _assert_bit_identical(gep.a.values, ref.a, "A[default GLQ]"); _assert_bit_identical(gep.b.values, ref.b, "B[default GLQ]")
 
 
+def test_repeatable_across_calls_streams_and_launch_modes():
+    """Deterministic by construction (fixed source order per slot, no atomics): repeated calls, calls on a side stream, calls with
+    the per-phase events on (kernels not overlapped) and off (programmatic dependent launch) all give the same bits."""
+    import torch
+    df = F.Domain.from_mesh(recipes.build_pair("cfg4_small")[1])
+    glq = _glq(12, 12)
+    plan = F.Plan(df.view(), device=0)
+    outs = []
+    side = torch.cuda.Stream()
+    for k in range(6):
+        a = torch.full((plan.nnz,), float("nan"), dtype=torch.float64, device="cuda:0"); b = torch.full_like(a, float("nan"))
+        plan.set_phase_timing(k % 2 == 1)
+        stream = side if k >= 3 else torch.cuda.current_stream()
+        stream.wait_stream(torch.cuda.current_stream())
+        plan.assemble_device(glq, a.data_ptr(), b.data_ptr(), stream=stream.cuda_stream)
+        stream.synchronize()
+        outs.append((a, b))
+    for a, b in outs[1:]:
+        assert torch.equal(a.view(torch.int64), outs[0][0].view(torch.int64)) and torch.equal(b.view(torch.int64), outs[0][1].view(torch.int64))
+    assert not torch.isnan(outs[0][0]).any() and not torch.isnan(outs[0][1]).any()
+    t = plan.last_timing()
+    assert t["launches"] >= 3 and t["total_ms"] > 0
+
+
 def test_device_row_offsets_and_sliced_rows():
     """Host `rows` are expanded from the device CSR row offsets (fem2d_plan_row_offsets), also for slices that start mid-row."""
     df = F.Domain.from_mesh(recipes.build_pair("cfg4_small")[1])
