@@ -72,7 +72,7 @@ class _View(C.Structure):
 
 # Every symbol declared in include/fem2d.h and include/fem2d_host.h (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "fem2d_symbolic", "fem2d_plan_free", "fem2d_plan_info", "fem2d_plan_source_map_info", "fem2d_plan_row_offsets", "fem2d_plan_pattern", "fem2d_plan_pattern_device",
+    "fem2d_symbolic", "fem2d_plan_free", "fem2d_plan_info", "fem2d_plan_source_map_info", "fem2d_plan_row_offsets", "fem2d_plan_pattern_transfer_info", "fem2d_plan_pattern", "fem2d_plan_pattern_device",
     "fem2d_assemble_device", "fem2d_assemble_device_ranges", "fem2d_plan_row_blocks_split", "fem2d_assemble_ranges", "fem2d_assemble", "fem2d_galerkin_sample_gep_hcurl", "fem2d_plan_row_blocks",
     "fem2d_plan_last_timing", "fem2d_plan_timing", "fem2d_plan_set_phase_timing", "fem2d_assemble_range", "fem2d_host_alloc", "fem2d_host_free", "fem2d_xy_fields", "fem2d_fp64_peak",
     "fem2d_device_count", "fem2d_status_string", "fem2d_last_error", "fem2d_version",
@@ -607,6 +607,12 @@ class Plan:
         rows = np.zeros(self.nnz, dtype=np.uint32); cols = np.zeros(self.nnz, dtype=np.uint32)
         _ck(_L.fem2d_plan_pattern(self._h, _p(rows, C.c_uint32), _p(cols, C.c_uint32)))
         return rows, cols
+
+    def pattern_transfer_info(self) -> dict:
+        """fem2d_plan_pattern_transfer_info: bytes the host-output calls move for the pattern (row offsets + column runs)."""
+        info = (C.c_uint64 * 4)()
+        _ck(_L.fem2d_plan_pattern_transfer_info(self._h, info))
+        return {"row_offset_bytes": int(info[0]), "col_runs": int(info[1]), "col_run_bytes": int(info[2]), "plain_bytes": int(info[3])}
 
     def row_offsets(self) -> np.ndarray:
         """fem2d_plan_row_offsets: CSR row offsets of the upper-triangular pattern (n_dofs + 1 entries)."""

@@ -48,6 +48,55 @@ int check_numeric_args(const fem2d_plan* plan, int basis_kind, int a_kind, int b
 }
 }  // namespace
 
+// Host expansion of a run-compressed index array for the slots [b, e) into out[0 .. e-b), on `threads` host threads.
+// start[r] (n_runs + 1 entries, ascending, start[n_runs] = end) is the first slot of run r; slot s of run r gets base(r) + step * (s - start[r]).
+//   rows[]:  runs = pattern rows,            start = CSR row offsets,   value = r            (step 0)
+//   cols[]:  runs = stretches of consecutive column ids inside a row,   value = first col + offset (step 1)
+// The destination is a large (pinned) buffer next to the ones the GPU's DMA engine is filling at the same time, so each worker
+// assembles whole 64-byte lines in a small cache-resident block and moves them out with non-temporal stores: no read-for-ownership
+// traffic on the memory controllers the DMA writes through.  (Streaming the short runs directly would issue partial-line writes.)
+template <class Base>
+static void expand_runs(const uint32_t* start, uint64_t n_runs, Base base, uint32_t step, uint64_t b, uint64_t e, uint32_t* out, unsigned threads) {
+    if (e <= b) return;
+    auto work = [=](uint64_t lo, uint64_t hi) {
+        // run holding slot lo: last r with start[r] <= lo
+        uint64_t r = (uint64_t)(std::upper_bound(start, start + n_runs + 1, (uint32_t)lo) - start) - 1;
+        uint64_t next = start[r + 1];
+        constexpr uint32_t BLK = 2048;                          // 8 KB staging block
+        alignas(64) uint32_t buf[BLK];
+        uint64_t s = lo;
+        while (s < hi) {
+            uint32_t* dst = out + (s - b);
+            // first block: up to the next 64-byte boundary of the destination, then whole blocks
+            uint32_t n = (uint32_t)std::min<uint64_t>(BLK, hi - s);
+            const uintptr_t mis = reinterpret_cast<uintptr_t>(dst) & 63u;
+            if (mis) n = (uint32_t)std::min<uint64_t>(n, (64 - mis) / 4);
+            for (uint32_t k = 0; k < n;) {
+                while (s + k >= next) { r++; next = start[r + 1]; }
+                const uint32_t run = (uint32_t)std::min<uint64_t>(n - k, next - (s + k));
+                uint32_t v = base(r) + step * (uint32_t)(s + k - start[r]);
+                for (uint32_t q = 0; q < run; q++, v += step) buf[k + q] = v;
+                k += run;
+            }
+#if defined(__SSE2__)
+            if (!mis && n % 16 == 0) {
+                for (uint32_t k = 0; k < n; k += 4) _mm_stream_si128(reinterpret_cast<__m128i*>(dst + k), _mm_load_si128(reinterpret_cast<const __m128i*>(buf + k)));
+            } else
+#endif
+                std::memcpy(dst, buf, (size_t)n * 4);
+            s += n;
+        }
+#if defined(__SSE2__)
+        _mm_sfence();   // streaming stores are weakly ordered: drain them before this worker reports completion
+#endif
+    };
+    threads = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(threads, (e - b) / (1u << 20)));
+    if (threads == 1) { work(b, e); return; }
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; t++) pool.emplace_back(work, b + (e - b) * t / threads, b + (e - b) * (t + 1) / threads);
+    for (auto& th : pool) th.join();
+}
+
 extern "C" {
 
 const char* fem2d_version(void) { return "fem2d-b200 0.1.0 (sm_100a)"; }
@@ -168,48 +217,15 @@ int fem2d_plan_row_offsets(fem2d_plan* plan, uint64_t* row_ptr) {
     return FEM2D_OK;
 }
 
-// rows[k] for the slots [b, e) written to out[0 .. e-b): expansion of the CSR row offsets on `threads` host threads.  The destination
-// is a large (pinned) buffer next to the ones the GPU's DMA engine is filling at the same time, so each worker assembles whole
-// 64-byte lines in a small cache-resident block and moves them out with non-temporal stores: no read-for-ownership traffic on the
-// memory controllers the DMA writes through.  (Streaming the short per-row runs directly would issue partial-line writes.)
-static void expand_rows(const uint32_t* row_ptr, uint32_t n_rows, uint64_t b, uint64_t e, uint32_t* out, unsigned threads) {
-    if (e <= b) return;
-    auto work = [=](uint64_t lo, uint64_t hi) {
-        // row holding slot lo: last r with row_ptr[r] <= lo
-        uint32_t r = (uint32_t)(std::upper_bound(row_ptr, row_ptr + n_rows + 1, (uint32_t)lo) - row_ptr) - 1;
-        uint64_t next = row_ptr[r + 1];
-        constexpr uint32_t BLK = 2048;                          // 8 KB staging block
-        alignas(64) uint32_t buf[BLK];
-        uint64_t s = lo;
-        while (s < hi) {
-            uint32_t* dst = out + (s - b);
-            // first block: up to the next 64-byte boundary of the destination, then whole blocks
-            uint32_t n = (uint32_t)std::min<uint64_t>(BLK, hi - s);
-            const uintptr_t mis = reinterpret_cast<uintptr_t>(dst) & 63u;
-            if (mis) n = (uint32_t)std::min<uint64_t>(n, (64 - mis) / 4);
-            for (uint32_t k = 0; k < n;) {
-                while (s + k >= next) { r++; next = row_ptr[r + 1]; }
-                const uint32_t run = (uint32_t)std::min<uint64_t>(n - k, next - (s + k));
-                std::fill(buf + k, buf + k + run, r);
-                k += run;
-            }
-#if defined(__SSE2__)
-            if (!mis && n % 16 == 0) {
-                for (uint32_t k = 0; k < n; k += 4) _mm_stream_si128(reinterpret_cast<__m128i*>(dst + k), _mm_load_si128(reinterpret_cast<const __m128i*>(buf + k)));
-            } else
-#endif
-                std::memcpy(dst, buf, (size_t)n * 4);
-            s += n;
-        }
-#if defined(__SSE2__)
-        _mm_sfence();   // streaming stores are weakly ordered: drain them before this worker reports completion
-#endif
-    };
-    threads = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(threads, (e - b) / (1u << 20)));
-    if (threads == 1) { work(b, e); return; }
-    std::vector<std::thread> pool;
-    for (unsigned t = 0; t < threads; t++) pool.emplace_back(work, b + (e - b) * t / threads, b + (e - b) * (t + 1) / threads);
-    for (auto& th : pool) th.join();
+int fem2d_plan_pattern_transfer_info(fem2d_plan* plan, uint64_t info[4]) {
+    if (!plan || !info) return fail(FEM2D_ERR_BAD_ARGUMENT, "null argument");
+    fem2d::Plan& p = plan->p;
+    if (p.device < 0) return fail(FEM2D_ERR_NO_DEVICE, "host-only plan");
+    std::string err;
+    const int st = fem2d::device_col_runs_host(p, nullptr, err);
+    if (st != FEM2D_OK) return fail(st, err);
+    info[0] = ((uint64_t)p.host.n_dofs + 1) * 4; info[1] = p.n_col_runs; info[2] = (2 * p.n_col_runs + 1) * 4; info[3] = p.nnz * 8;
+    return FEM2D_OK;
 }
 
 int fem2d_plan_pattern_device(const fem2d_plan* plan, const uint32_t** d_rows, const uint32_t** d_cols) {
@@ -371,10 +387,17 @@ int fem2d_assemble_ranges(fem2d_plan* plan, int basis_kind, int a_kind, int b_ki
     const size_t bytes = std::max<uint64_t>(p.nnz, 1) * sizeof(double);
     if (!p.d_out_a) CKS(fem2d::dev_malloc((void**)&p.d_out_a, bytes));
     if (!p.d_out_b) CKS(fem2d::dev_malloc((void**)&p.d_out_b, bytes));
-    if (rows) {   // the row indices are expanded on the host from the CSR row offsets (4 B per row instead of 4 B per slot over PCIe)
+    // The pattern crosses PCIe in compressed form and is expanded on host threads while the value arrays are in flight: rows[] from
+    // the CSR row offsets (4 B per row), cols[] from the runs of consecutive column ids (8 B per run, ~5 runs per row on hp-meshes).
+    if (rows) {
         std::string rerr;
         st = fem2d::device_row_ptr_host(p, nullptr, rerr);
         if (st != FEM2D_OK) return fail(st, rerr);
+    }
+    if (cols) {
+        std::string cerr;
+        st = fem2d::device_col_runs_host(p, nullptr, cerr);
+        if (st != FEM2D_OK) return fail(st, cerr);
     }
     st = fem2d_assemble_device_ranges(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, n_ranges, b, e, p.d_out_a, p.d_out_b, nullptr);
     if (st != FEM2D_OK) return st;
@@ -385,13 +408,17 @@ int fem2d_assemble_ranges(fem2d_plan* plan, int basis_kind, int a_kind, int b_ki
         if (n == 0) continue;
         CKS(cudaMemcpyAsync(a_vals + off, p.d_out_a + b[k], n * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
         CKS(cudaMemcpyAsync(b_vals + off, p.d_out_b + b[k], n * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
-        if (cols) CKS(cudaMemcpyAsync(cols + off, p.d_cols + b[k], n * 4, cudaMemcpyDeviceToHost, nullptr));
         off += n;
     }
-    if (rows) {   // while the copies above are in flight
+    if (rows || cols) {   // while the copies above are in flight
         const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        const uint32_t* run_col = p.h_col_run_col;
         off = 0;
-        for (uint32_t k = 0; k < n_ranges; k++) { expand_rows(p.h_row_ptr, p.host.n_dofs, b[k], e[k], rows + off, hw); off += e[k] - b[k]; }
+        for (uint32_t k = 0; k < n_ranges; k++) {
+            if (rows) expand_runs(p.h_row_ptr, p.host.n_dofs, [](uint64_t r) { return (uint32_t)r; }, 0u, b[k], e[k], rows + off, hw);
+            if (cols) expand_runs(p.h_col_run_slot, p.n_col_runs, [run_col](uint64_t r) { return run_col[r]; }, 1u, b[k], e[k], cols + off, hw);
+            off += e[k] - b[k];
+        }
     }
     CKS(cudaStreamSynchronize(nullptr));
     return FEM2D_OK;

@@ -247,7 +247,7 @@ int device_symbolic(Plan& P, std::string& err) {
     CKC(cub::DeviceScan::InclusiveSum(d_temp, temp_bytes, d_head, d_scan, (int)np));
     uint32_t nnz32 = 0;
     CKC(cudaMemcpy(&nnz32, d_scan + (np - 1), 4, cudaMemcpyDeviceToHost));
-    P.nnz = nnz32; P.n_extra = (uint64_t)np - nnz32;
+    P.nnz = nnz32; P.nnz32_sentinel = nnz32; P.n_extra = (uint64_t)np - nnz32;
 
     // ---- plan-owned pattern arena
     Arena pa;
@@ -462,10 +462,13 @@ std::vector<std::pair<void*, size_t>> g_pin_free;
 void* pinned_acquire(size_t bytes, size_t* cap) {
     {
         std::lock_guard<std::mutex> lk(g_pin_mu);
+        size_t best = SIZE_MAX;   // best fit, so that the same-sized requests of successive plans land on the same buffers
         for (size_t k = 0; k < g_pin_free.size(); k++)
-            if (g_pin_free[k].second >= bytes) { void* p = g_pin_free[k].first; *cap = g_pin_free[k].second; g_pin_free.erase(g_pin_free.begin() + k); return p; }
+            if (g_pin_free[k].second >= bytes && (best == SIZE_MAX || g_pin_free[k].second < g_pin_free[best].second)) best = k;
+        if (best != SIZE_MAX) { void* p = g_pin_free[best].first; *cap = g_pin_free[best].second; g_pin_free.erase(g_pin_free.begin() + best); return p; }
     }
     void* p = nullptr;
+    bytes = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);   // MiB granularity: a slightly larger Domain re-uses the buffer
     if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     *cap = bytes;
     return p;
@@ -473,7 +476,7 @@ void* pinned_acquire(size_t bytes, size_t* cap) {
 void pinned_release(void* p, size_t cap) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(g_pin_mu);
-    if (g_pin_free.size() < 4) { g_pin_free.push_back({p, cap}); return; }
+    if (g_pin_free.size() < 8) { g_pin_free.push_back({p, cap}); return; }
     cudaFreeHost(p);
 }
 }  // namespace
@@ -488,6 +491,63 @@ int device_row_ptr_host(Plan& P, cudaStream_t st, std::string& err) {
     return FEM2D_OK;
 }
 
+namespace {
+// slot s opens a run of consecutive column ids: first slot of its row, or its column is not the previous one + 1
+struct ColRunHead {
+    const uint32_t* rows; const uint32_t* cols;
+    __device__ bool operator()(uint32_t s) const { return s == 0 || rows[s] != rows[s - 1] || cols[s] != cols[s - 1] + 1u; }
+};
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t n, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+}  // namespace
+
+int device_col_runs_host(Plan& P, cudaStream_t st, std::string& err) {
+    if (P.h_col_run_slot) return FEM2D_OK;
+    CK(cudaSetDevice(P.device));
+    const uint32_t nnz = (uint32_t)P.nnz;
+    // Scratch comes out of the plan's own value staging buffers (they are overwritten by the numeric phase that follows), not out of
+    // the memory pool: a one-shot caller builds and frees a plan per call, and an allocation pattern that changes between the
+    // symbolic phases makes the stream-ordered pool re-map its 1.5 GB scratch block (milliseconds, and erratic).
+    const size_t out_bytes = std::max<uint64_t>(P.nnz, 1) * sizeof(double);
+    if (!P.d_out_a) CK(dev_malloc((void**)&P.d_out_a, out_bytes));
+    if (!P.d_out_b) CK(dev_malloc((void**)&P.d_out_b, out_bytes));
+    uint32_t* d_slot = reinterpret_cast<uint32_t*>(P.d_out_b);            // (nnz + 1) * 4 <= nnz * 8 for nnz >= 1
+    uint32_t* d_n = reinterpret_cast<uint32_t*>(P.d_out_a);
+    uint32_t* d_col = reinterpret_cast<uint32_t*>(P.d_out_a) + 64;        // n_runs * 4 bytes
+    cub::CountingInputIterator<uint32_t> it(0);
+    ColRunHead pred{P.d_rows, P.d_cols};
+    size_t temp = 0;
+    CK(cub::DeviceSelect::If(nullptr, temp, it, d_slot, d_n, (int)nnz, pred, st));
+    const size_t col_cap = ((size_t)nnz * 4 + 256 + 255) & ~(size_t)255;  // worst case: every slot its own run
+    void* d_temp = reinterpret_cast<char*>(P.d_out_a) + col_cap;
+    void* own_temp = nullptr;
+    if (col_cap + temp > out_bytes) { CK(dev_malloc(&own_temp, temp, st)); d_temp = own_temp; }   // tiny plans only
+    cudaError_t e = cub::DeviceSelect::If(d_temp, temp, it, d_slot, d_n, (int)nnz, pred, st);
+    uint32_t n_runs = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&n_runs, d_n, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && n_runs) { gather_u32_kernel<<<(n_runs + 255) / 256, 256, 0, st>>>(P.d_cols, d_slot, n_runs, d_col); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_slot + n_runs, &P.nnz32_sentinel, 4, cudaMemcpyHostToDevice, st);   // sentinel: end of the last run
+    if (e == cudaSuccess) {
+        P.h_col_run_slot = (uint32_t*)pinned_acquire(((size_t)n_runs + 1) * 4, &P.h_col_run_cap[0]);
+        P.h_col_run_col = (uint32_t*)pinned_acquire(((size_t)n_runs + 1) * 4, &P.h_col_run_cap[1]);
+        if (!P.h_col_run_slot || !P.h_col_run_col) e = cudaErrorMemoryAllocation;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(P.h_col_run_slot, d_slot, ((size_t)n_runs + 1) * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(P.h_col_run_col, d_col, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    dev_free(own_temp, st);
+    if (e != cudaSuccess) {
+        pinned_release(P.h_col_run_slot, P.h_col_run_cap[0]); pinned_release(P.h_col_run_col, P.h_col_run_cap[1]);
+        P.h_col_run_slot = P.h_col_run_col = nullptr;
+        err = cudaGetErrorString(e); return FEM2D_ERR_CUDA;
+    }
+    P.n_col_runs = n_runs;
+    return FEM2D_OK;
+}
+
 void device_plan_release(Plan& P) {
     if (P.device < 0) return;
     cudaSetDevice(P.device);
@@ -495,6 +555,8 @@ void device_plan_release(Plan& P) {
     dev_free(P.d_desc_arena); dev_free(P.d_pattern_arena);   // descriptors, GLQ buffer, pattern, source map
     dev_free(P.d_pack_arena);
     pinned_release(P.h_row_ptr, P.h_row_ptr_cap); P.h_row_ptr = nullptr;
+    pinned_release(P.h_col_run_slot, P.h_col_run_cap[0]); pinned_release(P.h_col_run_col, P.h_col_run_cap[1]);
+    P.h_col_run_slot = P.h_col_run_col = nullptr;
     dev_free(P.d_range_items);
     dev_free(P.d_V); dev_free(P.d_tabs); dev_free(P.d_gram); dev_free(P.d_dmma_items); dev_free(P.d_out_a); dev_free(P.d_out_b);
     for (int r = 0; r < Plan::RING; r++) for (int k = 0; k < 4; k++) if (P.ev[r][k]) cudaEventDestroy(P.ev[r][k]);

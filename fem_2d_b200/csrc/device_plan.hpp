@@ -35,6 +35,12 @@ struct Plan {
     uint32_t* d_row_ptr = nullptr;       // [n_dofs + 1] CSR row offsets of the pattern (first slot of every row)
     uint32_t* h_row_ptr = nullptr;       // pinned host copy, fetched on first use (host `rows` output is expanded from it)
     size_t h_row_ptr_cap = 0;
+    // runs of consecutive column ids inside a row (built on first use by a host-output call): first slot and first column of each run,
+    // pinned host copies; h_col_run_slot has n_col_runs + 1 entries (last = nnz)
+    uint32_t* h_col_run_slot = nullptr; uint32_t* h_col_run_col = nullptr;
+    size_t h_col_run_cap[2] = {0, 0};
+    uint64_t n_col_runs = 0;
+    uint32_t nnz32_sentinel = 0;         // == nnz, kept in the plan so an async H2D of it has a stable source
     uint32_t* d_extra_slot = nullptr;
     uint32_t* d_extra_src = nullptr;
     uint32_t* d_extra_first = nullptr;   // first contribution of a multi-contribution slot, stored at the head of its extras run
@@ -105,6 +111,8 @@ int device_first_slot_of_row(const Plan& plan, uint32_t row, uint64_t* slot, std
 int device_row_block_bounds_range(const Plan& plan, uint64_t lo, uint64_t hi, uint32_t world, uint64_t* bounds, std::string& err);
 // Pinned host copy of the CSR row offsets (fetched once per plan).
 int device_row_ptr_host(Plan& plan, cudaStream_t st, std::string& err);
+// Column runs of the pattern, compacted on the device and copied to pinned host memory (once per plan).
+int device_col_runs_host(Plan& plan, cudaStream_t st, std::string& err);
 void device_plan_release(Plan& plan);
 
 // kernels_exact.cu  (compiled with -fmad=false)

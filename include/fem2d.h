@@ -100,6 +100,10 @@ int fem2d_plan_source_map_info(const fem2d_plan* plan, uint64_t info[4]);
 int fem2d_plan_pattern(const fem2d_plan* plan, uint32_t* rows, uint32_t* cols);
 /* CSR row offsets of the pattern: row_ptr[r] = first slot of row r, row_ptr[n_dofs] = nnz_upper (n_dofs + 1 entries). */
 int fem2d_plan_row_offsets(fem2d_plan* plan, uint64_t* row_ptr);
+/* What the host-output calls move over PCIe for the pattern instead of rows[] / cols[] (which they expand on host threads):
+ * info[0] bytes of the CSR row offsets, info[1] number of runs of consecutive column ids, info[2] bytes of the column runs,
+ * info[3] bytes of plain rows[] + cols[].  Builds the column runs on first use.  Device plans only. */
+int fem2d_plan_pattern_transfer_info(fem2d_plan* plan, uint64_t info[4]);
 /* Device pointers of the pattern (uint32 rows, cols; length nnz_upper). */
 int fem2d_plan_pattern_device(const fem2d_plan* plan, const uint32_t** d_rows, const uint32_t** d_cols);
 

@@ -43,6 +43,20 @@ def test_source_map_packs_and_keeps_plain_chunks(full):
     assert smi["plain_chunks"] <= nd["plain_chunks"] < 0.1 * n_chunks      # dedupe off: edge rows reach across distant value tiles
 
 
+def test_host_pattern_expansion_at_full_size(full):
+    """rows[] / cols[] of the host-output calls are expanded on host threads from the CSR row offsets and the column runs: at full
+    size (multi-threaded, streaming stores, 57.6 M slots) they must equal the device pattern."""
+    plan = full["plan"]
+    rows, cols = plan.pattern()                     # plain D2H of the device arrays
+    xfer = plan.pattern_transfer_info()
+    assert xfer["row_offset_bytes"] + xfer["col_run_bytes"] < 0.25 * xfer["plain_bytes"]
+    n = plan.nnz
+    r2 = np.zeros(n, dtype=np.uint32); c2 = np.zeros(n, dtype=np.uint32); a2 = np.zeros(n); b2 = np.zeros(n)
+    plan.assemble_ranges_into(full["glq"], [(0, n)], a2.ctypes.data, b2.ctypes.data, r2.ctypes.data, c2.ctypes.data)
+    assert np.array_equal(r2, rows) and np.array_equal(c2, cols)
+    assert np.array_equal(a2.view(np.uint64), full["a"].cpu().numpy().view(np.uint64))
+
+
 def test_pattern_is_sorted_unique_upper_triangular(full):
     rows, cols = full["plan"].pattern()
     assert np.all(rows <= cols)

@@ -145,6 +145,9 @@ def test_device_row_offsets_and_sliced_rows():
     rows, cols = plan.pattern()
     rp = plan.row_offsets()
     assert np.array_equal(np.repeat(np.arange(df.num_dofs, dtype=np.uint32), np.diff(rp).astype(np.int64)), rows)
+    xfer = plan.pattern_transfer_info()   # the host calls move row offsets + column runs instead of rows[] / cols[]
+    assert xfer["row_offset_bytes"] == 4 * (df.num_dofs + 1) and df.num_dofs <= xfer["col_runs"] <= plan.nnz
+    assert xfer["plain_bytes"] == 8 * plan.nnz
     glq = _glq(8, 8)
     _, _, a_full, b_full = plan.assemble(glq)
     n = plan.nnz
