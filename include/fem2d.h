@@ -107,7 +107,7 @@ int fem2d_plan_pattern_transfer_info(fem2d_plan* plan, uint64_t info[4]);
 /* Device pointers of the pattern (uint32 rows, cols; length nnz_upper). */
 int fem2d_plan_pattern_device(const fem2d_plan* plan, const uint32_t** d_rows, const uint32_t** d_cols);
 
-/* Numeric phase into caller-provided DEVICE buffers d_a / d_b (nnz_upper doubles each, on the plan's device),
+/* Numeric phase (same replacement as fem2d_assemble below) into caller-provided DEVICE buffers d_a / d_b (nnz_upper doubles each, on the plan's device),
  * asynchronous on `stream` (a cudaStream_t, may be NULL).  GLQ nodes / weights are HOST inputs so the caller can pass
  * the exact values of gauss_quadrature_points (glq.rs:179-222, basis.rs:83-90).
  * slot_begin/slot_end restrict the scatter to a row-block slice [slot_begin, slot_end) of the pattern (multi-GPU
@@ -127,7 +127,10 @@ int fem2d_assemble_device_ranges(fem2d_plan* plan, int basis_kind, int a_kind, i
                                  uint32_t n_ranges, const uint64_t* slot_begins, const uint64_t* slot_ends,
                                  double* d_a, double* d_b, void* stream);
 
-/* Numeric phase with HOST outputs (a_vals / b_vals: nnz_upper doubles each; rows / cols may be NULL). Synchronous. */
+/* Numeric phase with HOST outputs (a_vals / b_vals: nnz_upper doubles each; rows / cols may be NULL). Synchronous.
+ * Replaces the Rayon loop over Elems with its per-pair AI::integrate / BI::integrate calls (galerkin.rs:73-184, integrals.rs:26-92,
+ * 292-354) and the per-Elem insert_group + serial consume_matrix merge (sparse_matrix.rs:68-120, linalg.rs:59-81); the outputs are
+ * what SparseMatrix::iter_upper_tri (sparse_matrix.rs:123-127) would yield for gep.a and gep.b. */
 int fem2d_assemble(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode,
                    const double* u_pts, const double* u_w, uint32_t nu,
                    const double* v_pts, const double* v_w, uint32_t nv,
