@@ -348,7 +348,13 @@ int fem2d_assemble_device_ranges(fem2d_plan* plan, int basis_kind, int a_kind, i
 
 int fem2d_plan_set_phase_timing(fem2d_plan* plan, int on) {
     if (!plan) return fail(FEM2D_ERR_BAD_ARGUMENT, "null plan");
-    plan->p.phase_timing = on != 0;
+    fem2d::Plan& p = plan->p;
+    if (p.device < 0) return fail(FEM2D_ERR_NO_DEVICE, "host-only plan");
+    if (on && !p.ev[0][0]) {   // the event ring is created on first use
+        CKS(cudaSetDevice(p.device));
+        for (int r = 0; r < fem2d::Plan::RING; r++) for (int k = 0; k < 4; k++) CKS(cudaEventCreate(&p.ev[r][k]));
+    }
+    p.phase_timing = on != 0;
     return FEM2D_OK;
 }
 

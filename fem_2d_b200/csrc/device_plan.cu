@@ -1,6 +1,9 @@
-// Device part of the symbolic phase: pair keys -> radix sort -> unique = the fixed upper-triangular pattern
-// (BTreeMap<[u32;2]> order, sparse_matrix.rs:16,48-58) and the per-slot source map that replaces the reference's
-// per-Elem BTreeMap inserts and serial merge (sparse_matrix.rs:68-120, linalg.rs:59-81).
+// Device part of the symbolic phase: the fixed upper-triangular pattern (BTreeMap<[u32;2]> order, sparse_matrix.rs:16,48-58) and the
+// per-slot source map that replaces the reference's per-Elem BTreeMap inserts and serial merge (sparse_matrix.rs:68-120,
+// linalg.rs:59-81).  Symbolic assembly by rows: a DoF that lives in exactly one pair block (an Elem-type DoF of an Elem without
+// ancestor specs: 98 % of the slots at 1 M DoFs) gets its row written directly -- its columns are the tail of its Elem's sorted DoF
+// list -- and only the pairs whose row DoF is shared between blocks (edge-type DoFs, RBS ancestor/descendant overlaps) go through
+// keygen -> radix sort -> unique, which is also where keys with more than one contribution come from.
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -24,59 +27,151 @@ struct DevBlock {
     uint32_t local, pad;
 };
 
-// One CTA per block of pairs: key = [min(dof_p, dof_q), max] (sparse_matrix.rs:78-91), src = index of the pair's value in V.
-__global__ void keygen_kernel(const DevBlock* __restrict__ blocks, const uint32_t* __restrict__ canon_dof,
-                              unsigned long long* __restrict__ keys, uint32_t* __restrict__ srcs) {
+// Number of pair blocks every DoF takes part in (as a P function or as a Q function).  1 = the local block of its own Elem only.
+__global__ void incidence_kernel(const DevBlock* __restrict__ blocks, const uint32_t* __restrict__ canon_dof, uint32_t* __restrict__ cnt) {
+    const DevBlock b = blocks[blockIdx.x];
+    for (uint32_t t = threadIdx.x; t < b.nP; t += blockDim.x) atomicAdd(&cnt[canon_dof[b.dofP_off + t]], 1u);
+    if (!b.local) for (uint32_t t = threadIdx.x; t < b.nQ; t += blockDim.x) atomicAdd(&cnt[canon_dof[b.dofQ_off + t]], 1u);
+}
+
+constexpr uint32_t ORDER_MAX = 1024;   // >= the largest BasisSpec list (2 * 20 * 21 = 840 at MAX_POLYNOMIAL_ORDER)
+
+// One CTA per LOCAL block: sorts the Elem's DoF ids (bitonic, shared memory), stores the canonical index of the k-th smallest DoF
+// (perm) and, for every direct DoF (cnt == 1), the length of its row: the DoFs of the Elem that are >= it.
+__global__ void __launch_bounds__(256) local_order_kernel(const DevBlock* __restrict__ blocks, const uint32_t* __restrict__ canon_dof,
+                                                          const uint32_t* __restrict__ cnt, uint16_t* __restrict__ perm,
+                                                          uint32_t* __restrict__ len_all, uint32_t* __restrict__ len_dir) {
+    const DevBlock b = blocks[blockIdx.x];
+    if (!b.local) return;
+    __shared__ uint32_t s_key[ORDER_MAX];
+    __shared__ uint16_t s_idx[ORDER_MAX];
+    uint32_t n2 = 1; while (n2 < b.nP) n2 <<= 1;
+    for (uint32_t t = threadIdx.x; t < n2; t += blockDim.x) { s_key[t] = t < b.nP ? canon_dof[b.dofP_off + t] : 0xffffffffu; s_idx[t] = (uint16_t)t; }
+    __syncthreads();
+    for (uint32_t k = 2; k <= n2; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < n2; t += blockDim.x) {
+                const uint32_t x = t ^ j;
+                if (x > t) {
+                    const bool up = (t & k) == 0;
+                    const uint32_t a = s_key[t], c = s_key[x];
+                    if ((a > c) == up) { s_key[t] = c; s_key[x] = a; const uint16_t ia = s_idx[t]; s_idx[t] = s_idx[x]; s_idx[x] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    for (uint32_t k = threadIdx.x; k < b.nP; k += blockDim.x) {
+        perm[b.dofP_off + k] = s_idx[k];
+        const uint32_t dof = s_key[k];
+        if (cnt[dof] == 1u) { len_all[dof] = b.nP - k; len_dir[dof] = b.nP - k; }
+    }
+}
+
+// Pairs of a block whose row DoF (the smaller one, sparse_matrix.rs:78-91) is shared between blocks, in the block's generation order
+// (a-major, q ascending; local blocks: q >= a).  WRITE = false: count them; WRITE = true: emit key = [row << 32 | col] and the
+// pair's index in V at sub_off[block] + rank (ordered compaction, so equal keys keep the reference's generation order).
+template <bool WRITE>
+__global__ void __launch_bounds__(256) shared_pairs_kernel(const DevBlock* __restrict__ blocks, const uint32_t* __restrict__ canon_dof,
+                                                           const uint32_t* __restrict__ cnt, uint32_t* __restrict__ sub_cnt,
+                                                           const uint32_t* __restrict__ sub_off, unsigned long long* __restrict__ keys,
+                                                           uint32_t* __restrict__ srcs) {
+    typedef cub::BlockScan<uint32_t, 256> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ uint32_t s_run;
     const DevBlock b = blocks[blockIdx.x];
     const uint32_t* dp = canon_dof + b.dofP_off;
     const uint32_t* dq = canon_dof + b.dofQ_off;
     const uint32_t total = b.nP * b.nQ;
-    for (uint32_t t = threadIdx.x; t < total; t += blockDim.x) {
-        const uint32_t a = t / b.nQ, q = t - a * b.nQ;
-        unsigned long long pos;
-        if (b.local) {
-            if (q < a) continue;
-            pos = b.pair_off + (unsigned long long)a * b.nQ - (unsigned long long)a * (a - 1) / 2 - a + q;   // packed upper triangle
-        } else pos = b.pair_off + t;
-        const uint32_t x = dp[a], y = dq[q];
-        const uint32_t r = x < y ? x : y, c = x < y ? y : x;
-        keys[pos] = (unsigned long long)r << 32 | c;
-        srcs[pos] = (uint32_t)(b.v_off + t);
+    if (threadIdx.x == 0) s_run = WRITE ? sub_off[blockIdx.x] : 0u;
+    __syncthreads();
+    uint32_t mine = 0;
+    for (uint32_t t0 = 0; t0 < total; t0 += blockDim.x) {
+        const uint32_t t = t0 + threadIdx.x;
+        bool take = false; uint32_t r = 0, c = 0;
+        if (t < total) {
+            const uint32_t a = t / b.nQ, q = t - a * b.nQ;
+            if (!b.local || q >= a) {
+                const uint32_t x = dp[a], y = dq[q];
+                r = x < y ? x : y; c = x < y ? y : x;
+                take = cnt[r] != 1u;
+            }
+        }
+        if (WRITE) {
+            uint32_t rank, sum;
+            Scan(tmp).ExclusiveSum(take ? 1u : 0u, rank, sum);
+            const uint32_t base = s_run;
+            if (take) { keys[base + rank] = (unsigned long long)r << 32 | c; srcs[base + rank] = (uint32_t)(b.v_off + t); }
+            __syncthreads();
+            if (threadIdx.x == 0) s_run = base + sum;
+            __syncthreads();
+        } else mine += take ? 1u : 0u;
+    }
+    if (!WRITE) {
+        uint32_t sum;
+        Scan(tmp).ExclusiveSum(mine, mine, sum);
+        if (threadIdx.x == 0) sub_cnt[blockIdx.x] = sum;
     }
 }
 
-__global__ void head_flags_kernel(const unsigned long long* __restrict__ keys, uint32_t n, uint32_t* __restrict__ head) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
-}
-
-// slot_of[i] = (inclusive scan of head)[i] - 1.  Heads write the pattern, the others go to the extras list (kept in
-// sorted order: position i - slot_of[i] - 1 is the rank among non-heads).
-__global__ void emit_pattern_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ srcs,
-                                    const uint32_t* __restrict__ head, const uint32_t* __restrict__ scan, uint32_t n,
-                                    uint32_t* __restrict__ rows, uint32_t* __restrict__ cols, uint32_t* __restrict__ src1,
-                                    uint32_t* __restrict__ extra_slot, uint32_t* __restrict__ extra_src, uint32_t* __restrict__ extra_first,
-                                    uint32_t* __restrict__ row_ptr, uint32_t n_dofs) {
+__global__ void head_flags_kernel(const unsigned long long* __restrict__ keys, uint32_t n, uint32_t* __restrict__ head, uint32_t* __restrict__ len_all) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t slot = scan[i] - 1;
+    const bool h = i == 0 || keys[i] != keys[i - 1];
+    head[i] = h ? 1u : 0u;
+    if (h) atomicAdd(&len_all[(uint32_t)(keys[i] >> 32)], 1u);   // row length of a shared row = its unique keys
+}
+
+// Sorted shared pairs -> pattern.  rank = (inclusive scan of head)[i] - 1 is the key's rank among the shared rows' slots; its slot is
+// rank + dir_before[row] (the direct rows' slots that precede it).  Heads write the pattern, the others go to the extras list (kept in
+// sorted order: position i - rank - 1 is the rank among non-heads).
+__global__ void emit_shared_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ srcs,
+                                   const uint32_t* __restrict__ head, const uint32_t* __restrict__ scan, uint32_t n,
+                                   const uint32_t* __restrict__ dir_before,
+                                   uint32_t* __restrict__ rows, uint32_t* __restrict__ cols, uint32_t* __restrict__ src1,
+                                   uint32_t* __restrict__ extra_slot, uint32_t* __restrict__ extra_src, uint32_t* __restrict__ extra_first) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t rank = scan[i] - 1;
+    const uint32_t row = (uint32_t)(keys[i] >> 32);
+    const uint32_t slot = rank + dir_before[row];
     if (head[i]) {
-        const uint32_t row = (uint32_t)(keys[i] >> 32);
         rows[slot] = row;
         cols[slot] = (uint32_t)keys[i];
-        // CSR row offsets: this slot opens every row after the previous key's row up to its own (rows without entries stay empty)
-        for (uint32_t q = i ? (uint32_t)(keys[i - 1] >> 32) + 1 : 0u; q <= row; q++) row_ptr[q] = slot;
         if (i + 1 < n && !head[i + 1]) {   // key with more than one contribution: point at its run in the extras arrays
-            const uint32_t k = i - slot;   // rank of element i+1 among the non-heads
+            const uint32_t k = i - rank;   // rank of element i+1 among the non-heads
             src1[slot] = 0x80000000u | k;
             extra_first[k] = srcs[i];
         } else src1[slot] = srcs[i];
     } else {
-        const uint32_t k = i - slot - 1;
+        const uint32_t k = i - rank - 1;
         extra_slot[k] = slot;
         extra_src[k] = srcs[i];
     }
-    if (i == n - 1) for (uint32_t q = (uint32_t)(keys[i] >> 32) + 1; q <= n_dofs; q++) row_ptr[q] = slot + 1;   // == nnz
+}
+
+// One CTA per LOCAL block: the rows of its direct DoFs.  Row of the k-th smallest DoF: columns = the DoFs k, k+1, ... of the sorted
+// list, source = the pair's entry in the (canonically indexed, upper-triangular) value tile of the block's class.
+__global__ void __launch_bounds__(256) emit_direct_kernel(const DevBlock* __restrict__ blocks, const uint32_t* __restrict__ canon_dof,
+                                                          const uint32_t* __restrict__ cnt, const uint16_t* __restrict__ perm,
+                                                          const uint32_t* __restrict__ row_ptr,
+                                                          uint32_t* __restrict__ rows, uint32_t* __restrict__ cols, uint32_t* __restrict__ src1) {
+    const DevBlock b = blocks[blockIdx.x];
+    if (!b.local) return;
+    __shared__ uint32_t s_dof[ORDER_MAX];
+    __shared__ uint16_t s_can[ORDER_MAX];
+    for (uint32_t k = threadIdx.x; k < b.nP; k += blockDim.x) { const uint16_t a = perm[b.dofP_off + k]; s_can[k] = a; s_dof[k] = canon_dof[b.dofP_off + a]; }
+    __syncthreads();
+    for (uint32_t k = 0; k < b.nP; k++) {
+        const uint32_t r = s_dof[k];
+        if (cnt[r] != 1u) continue;            // CTA-uniform
+        const uint32_t base = row_ptr[r], a = s_can[k];
+        for (uint32_t j = k + threadIdx.x; j < b.nP; j += blockDim.x) {
+            const uint32_t q = s_can[j], lo = a < q ? a : q, hi = a < q ? q : a;
+            const uint32_t slot = base + (j - k);
+            rows[slot] = r; cols[slot] = s_dof[j];
+            src1[slot] = (uint32_t)(b.v_off + (unsigned long long)lo * b.nQ + hi);
+        }
+    }
 }
 
 // ---- packed form of the source map -----------------------------------------------------------------------------------------------
@@ -161,7 +256,6 @@ int device_symbolic(Plan& P, std::string& err) {
     dev_pool_init(P.device);
     CK(cudaDeviceGetAttribute(&P.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, P.device));
     CK(cudaDeviceGetAttribute(&P.sm_count, cudaDevAttrMultiProcessorCount, P.device));
-    const uint32_t np = (uint32_t)H.n_pairs;
     P.split = split_items(H, H.items);
 
     // ---- descriptor blob (plan-owned part first, then the scratch-only part), laid out identically on host and device
@@ -197,25 +291,25 @@ int device_symbolic(Plan& P, std::string& err) {
     put(o_voff, h_voff.data(), h_voff.size() * 4); put(o_mtoff, h_mtoff.data(), h_mtoff.size() * 4);
     put(o_blocks, hb.data(), hb.size() * sizeof(DevBlock)); put(o_canon, H.canon_dof.data(), H.canon_dof.size() * 4);
 
-    // ---- scratch arena
-    int bits = 1; while ((1ull << bits) < (unsigned long long)H.n_dofs) bits++;
-    size_t temp_bytes = 0, scan_bytes = 0;
-    {
-        cub::DoubleBuffer<unsigned long long> kq(nullptr, nullptr);
-        cub::DoubleBuffer<uint32_t> vq(nullptr, nullptr);
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, kq, vq, (int)np, 0, 32 + bits));
-        CK(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)np));
-        temp_bytes = std::max(temp_bytes, scan_bytes);
-    }
+    // ---- scratch arena 1: per-DoF and per-block bookkeeping
+    const uint32_t nd = H.n_dofs, nb = (uint32_t)hb.size();
+    if (H.max_list_n > ORDER_MAX) { err = "BasisSpec list longer than 1024 functions"; return FEM2D_ERR_UNSUPPORTED; }
+    size_t temp_small = 0, tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, temp_small, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)(nd + 1)));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)(nb + 1)));
+    temp_small = std::max(temp_small, tb);
     Arena sc;
     const size_t s_desc = sc.reserve(desc.size - desc_plan_bytes);
-    const size_t s_keys = sc.reserve((size_t)np * 8), s_keys2 = sc.reserve((size_t)np * 8);
-    const size_t s_srcs = sc.reserve((size_t)np * 4), s_srcs2 = sc.reserve((size_t)np * 4);
-    const size_t s_head = sc.reserve((size_t)np * 4), s_scan = sc.reserve((size_t)np * 4);
-    const size_t s_temp = sc.reserve(temp_bytes), s_stats = sc.reserve(8);
+    const size_t s_cnt = sc.reserve((size_t)nd * 4);                                           // blocks per DoF
+    const size_t s_len = sc.reserve(((size_t)nd + 1) * 4), s_ldir = sc.reserve(((size_t)nd + 1) * 4);   // row lengths: all rows / direct rows only
+    const size_t s_dbef = sc.reserve(((size_t)nd + 1) * 4);                                    // direct slots before each row
+    const size_t s_perm = sc.reserve(H.canon_dof.size() * 2);                                  // sorted order of every Elem's DoFs
+    const size_t s_bcnt = sc.reserve(((size_t)nb + 1) * 4), s_boff = sc.reserve(((size_t)nb + 1) * 4);
+    const size_t s_tmp1 = sc.reserve(temp_small), s_stats = sc.reserve(8);
     void* scratch = nullptr;
+    void* scratch2 = nullptr;
     CK(dev_malloc(&scratch, sc.size));
-#define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); dev_free(scratch); return FEM2D_ERR_CUDA; } } while (0)
+#define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); dev_free(scratch); dev_free(scratch2); return FEM2D_ERR_CUDA; } } while (0)
     // descriptors: the plan-owned part goes to a first small plan allocation, the rest into the scratch arena
     CKC(dev_malloc(&P.d_desc_arena, desc_plan_bytes));
     CKC(cudaMemcpyAsync(P.d_desc_arena, blob.data(), desc_plan_bytes, cudaMemcpyHostToDevice, nullptr));
@@ -227,40 +321,85 @@ int device_symbolic(Plan& P, std::string& err) {
     P.d_class_voff = at<uint32_t>(P.d_desc_arena, o_voff); P.d_class_mtoff = at<uint32_t>(P.d_desc_arena, o_mtoff);
     DevBlock* d_blocks = at<DevBlock>(scratch, s_desc + (o_blocks - desc_plan_bytes));
     uint32_t* d_canon = at<uint32_t>(scratch, s_desc + (o_canon - desc_plan_bytes));
-    unsigned long long *d_keys = at<unsigned long long>(scratch, s_keys), *d_keys2 = at<unsigned long long>(scratch, s_keys2);
-    uint32_t *d_srcs = at<uint32_t>(scratch, s_srcs), *d_srcs2 = at<uint32_t>(scratch, s_srcs2);
-    uint32_t *d_head = at<uint32_t>(scratch, s_head), *d_scan = at<uint32_t>(scratch, s_scan), *d_stats = at<uint32_t>(scratch, s_stats);
-    void* d_temp = at<char>(scratch, s_temp);
+    uint32_t *d_cnt = at<uint32_t>(scratch, s_cnt), *d_len = at<uint32_t>(scratch, s_len), *d_ldir = at<uint32_t>(scratch, s_ldir);
+    uint32_t *d_dbef = at<uint32_t>(scratch, s_dbef), *d_bcnt = at<uint32_t>(scratch, s_bcnt), *d_boff = at<uint32_t>(scratch, s_boff);
+    uint32_t* d_stats = at<uint32_t>(scratch, s_stats);
+    uint16_t* d_perm = at<uint16_t>(scratch, s_perm);
+    void* d_tmp1 = at<char>(scratch, s_tmp1);
 
-    keygen_kernel<<<(unsigned)hb.size(), 256>>>(d_blocks, d_canon, d_keys, d_srcs);
+    // ---- which rows are direct, their lengths, and how many pairs go through the sort
+    CKC(cudaMemsetAsync(at<char>(scratch, s_cnt), 0, s_dbef - s_cnt, nullptr));   // cnt, len, ldir
+    CKC(cudaMemsetAsync(d_bcnt + nb, 0, 4, nullptr));
+    incidence_kernel<<<nb, 128>>>(d_blocks, d_canon, d_cnt);
     CKC(cudaGetLastError());
-    // stable LSD radix sort on the significant key bits only ([row << 32 | col], bits(n_dofs) each): low bits of col, then of row
-    cub::DoubleBuffer<unsigned long long> kb(d_keys, d_keys2);
-    cub::DoubleBuffer<uint32_t> vb(d_srcs, d_srcs2);
-    CKC(cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, kb, vb, (int)np, 0, bits));
-    CKC(cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, kb, vb, (int)np, 32, 32 + bits));
-    const unsigned long long* keys_sorted = kb.Current();
-    const uint32_t* srcs_sorted = vb.Current();
-    const unsigned gb = (np + 255) / 256;
-    head_flags_kernel<<<gb, 256>>>(keys_sorted, np, d_head);
+    local_order_kernel<<<nb, 256>>>(d_blocks, d_canon, d_cnt, d_perm, d_len, d_ldir);
     CKC(cudaGetLastError());
-    CKC(cub::DeviceScan::InclusiveSum(d_temp, temp_bytes, d_head, d_scan, (int)np));
+    shared_pairs_kernel<false><<<nb, 256>>>(d_blocks, d_canon, d_cnt, d_bcnt, nullptr, nullptr, nullptr);
+    CKC(cudaGetLastError());
+    CKC(cub::DeviceScan::ExclusiveSum(d_tmp1, temp_small, d_bcnt, d_boff, (int)(nb + 1)));
+    uint32_t n_sub = 0;
+    CKC(cudaMemcpy(&n_sub, d_boff + nb, 4, cudaMemcpyDeviceToHost));
+
+    // ---- scratch arena 2: the shared pairs, sorted by [row, col] (stable LSD radix sort on the significant key bits only)
+    int bits = 1; while ((1ull << bits) < (unsigned long long)nd) bits++;
+    size_t temp_bytes = 0, scan_bytes = 0;
+    {
+        cub::DoubleBuffer<unsigned long long> kq(nullptr, nullptr);
+        cub::DoubleBuffer<uint32_t> vq(nullptr, nullptr);
+        CKC(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, kq, vq, (int)std::max(n_sub, 1u), 0, 32 + bits));
+        CKC(cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)std::max(n_sub, 1u)));
+        temp_bytes = std::max(temp_bytes, scan_bytes);
+    }
+    Arena s2;
+    const size_t ns = std::max(n_sub, 1u);
+    const size_t s_keys = s2.reserve(ns * 8), s_keys2 = s2.reserve(ns * 8), s_srcs = s2.reserve(ns * 4), s_srcs2 = s2.reserve(ns * 4);
+    const size_t s_head = s2.reserve(ns * 4), s_scan = s2.reserve(ns * 4), s_temp = s2.reserve(temp_bytes);
+    CKC(dev_malloc(&scratch2, s2.size));
+    unsigned long long *d_keys = at<unsigned long long>(scratch2, s_keys), *d_keys2 = at<unsigned long long>(scratch2, s_keys2);
+    uint32_t *d_srcs = at<uint32_t>(scratch2, s_srcs), *d_srcs2 = at<uint32_t>(scratch2, s_srcs2);
+    uint32_t *d_head = at<uint32_t>(scratch2, s_head), *d_scan = at<uint32_t>(scratch2, s_scan);
+    void* d_temp = at<char>(scratch2, s_temp);
+    const unsigned long long* keys_sorted = d_keys;
+    const uint32_t* srcs_sorted = d_srcs;
+    uint32_t n_heads = 0;
+    const unsigned gb = (n_sub + 255) / 256;
+    if (n_sub) {
+        shared_pairs_kernel<true><<<nb, 256>>>(d_blocks, d_canon, d_cnt, nullptr, d_boff, d_keys, d_srcs);
+        CKC(cudaGetLastError());
+        cub::DoubleBuffer<unsigned long long> kb(d_keys, d_keys2);
+        cub::DoubleBuffer<uint32_t> vb(d_srcs, d_srcs2);
+        CKC(cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, kb, vb, (int)n_sub, 0, bits));
+        CKC(cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, kb, vb, (int)n_sub, 32, 32 + bits));
+        keys_sorted = kb.Current(); srcs_sorted = vb.Current();
+        head_flags_kernel<<<gb, 256>>>(keys_sorted, n_sub, d_head, d_len);
+        CKC(cudaGetLastError());
+        CKC(cub::DeviceScan::InclusiveSum(d_temp, temp_bytes, d_head, d_scan, (int)n_sub));
+        CKC(cudaMemcpyAsync(&n_heads, d_scan + (n_sub - 1), 4, cudaMemcpyDeviceToHost, nullptr));
+    }
+
+    // ---- plan-owned pattern arena; the CSR row offsets are the scan of the row lengths
+    Arena pr;
+    const size_t p_rp = pr.reserve(((size_t)nd + 1) * 4);
+    CKC(dev_malloc(&P.d_rowptr_arena, pr.size));
+    P.d_row_ptr = at<uint32_t>(P.d_rowptr_arena, p_rp);
+    CKC(cub::DeviceScan::ExclusiveSum(d_tmp1, temp_small, d_len, P.d_row_ptr, (int)(nd + 1)));
+    CKC(cub::DeviceScan::ExclusiveSum(d_tmp1, temp_small, d_ldir, d_dbef, (int)(nd + 1)));
     uint32_t nnz32 = 0;
-    CKC(cudaMemcpy(&nnz32, d_scan + (np - 1), 4, cudaMemcpyDeviceToHost));
-    P.nnz = nnz32; P.nnz32_sentinel = nnz32; P.n_extra = (uint64_t)np - nnz32;
-
-    // ---- plan-owned pattern arena
+    CKC(cudaMemcpy(&nnz32, P.d_row_ptr + nd, 4, cudaMemcpyDeviceToHost));   // synchronises: n_heads has arrived too
+    P.nnz = nnz32; P.nnz32_sentinel = nnz32; P.n_extra = (uint64_t)n_sub - n_heads;
     Arena pa;
     const size_t p_rows = pa.reserve((size_t)nnz32 * 4), p_cols = pa.reserve((size_t)nnz32 * 4), p_src1 = pa.reserve((size_t)nnz32 * 4);
     const size_t p_es = pa.reserve(P.n_extra * 4), p_ex = pa.reserve(P.n_extra * 4), p_ef = pa.reserve(P.n_extra * 4);
-    const size_t p_rp = pa.reserve(((size_t)H.n_dofs + 1) * 4);
     CKC(dev_malloc(&P.d_pattern_arena, pa.size));
     P.d_rows = at<uint32_t>(P.d_pattern_arena, p_rows); P.d_cols = at<uint32_t>(P.d_pattern_arena, p_cols); P.d_src1 = at<uint32_t>(P.d_pattern_arena, p_src1);
     P.d_extra_slot = at<uint32_t>(P.d_pattern_arena, p_es); P.d_extra_src = at<uint32_t>(P.d_pattern_arena, p_ex); P.d_extra_first = at<uint32_t>(P.d_pattern_arena, p_ef);
-    P.d_row_ptr = at<uint32_t>(P.d_pattern_arena, p_rp);
-    emit_pattern_kernel<<<gb, 256>>>(keys_sorted, srcs_sorted, d_head, d_scan, np, P.d_rows, P.d_cols, P.d_src1, P.d_extra_slot, P.d_extra_src, P.d_extra_first,
-                                     P.d_row_ptr, H.n_dofs);
+    emit_direct_kernel<<<nb, 256>>>(d_blocks, d_canon, d_cnt, d_perm, P.d_row_ptr, P.d_rows, P.d_cols, P.d_src1);
     CKC(cudaGetLastError());
+    if (n_sub) {
+        emit_shared_kernel<<<gb, 256>>>(keys_sorted, srcs_sorted, d_head, d_scan, n_sub, d_dbef, P.d_rows, P.d_cols, P.d_src1, P.d_extra_slot, P.d_extra_src,
+                                        P.d_extra_first);
+        CKC(cudaGetLastError());
+    }
     uint32_t stats[2] = {1, 0};
     CKC(cudaMemcpyAsync(d_stats, stats, 8, cudaMemcpyHostToDevice, nullptr));
     if (P.n_extra) {
@@ -269,6 +408,7 @@ int device_symbolic(Plan& P, std::string& err) {
     }
     CKC(cudaMemcpy(stats, d_stats, 8, cudaMemcpyDeviceToHost));   // synchronises the null stream: everything above is done
     P.max_contrib = stats[0]; P.n_multi = stats[1];
+    P.n_sorted_pairs = n_sub;
 
     // ---- packed form of the source map (what the scatter kernel reads; src1 stays for the chunks that do not pack)
     {
@@ -286,9 +426,8 @@ int device_symbolic(Plan& P, std::string& err) {
             P.n_plain_chunks = n_plain;
         }
     }
-    dev_free(scratch);
+    dev_free(scratch); dev_free(scratch2);
 #undef CKC
-    for (int r = 0; r < Plan::RING; r++) for (int k = 0; k < 4; k++) CK(cudaEventCreate(&P.ev[r][k]));
     return FEM2D_OK;
 }
 
@@ -552,7 +691,7 @@ void device_plan_release(Plan& P) {
     if (P.device < 0) return;
     cudaSetDevice(P.device);
     cudaDeviceSynchronize();   // numeric work may still be in flight on a caller stream
-    dev_free(P.d_desc_arena); dev_free(P.d_pattern_arena);   // descriptors, GLQ buffer, pattern, source map
+    dev_free(P.d_desc_arena); dev_free(P.d_pattern_arena); dev_free(P.d_rowptr_arena);   // descriptors, GLQ buffer, pattern, source map
     dev_free(P.d_pack_arena);
     pinned_release(P.h_row_ptr, P.h_row_ptr_cap); P.h_row_ptr = nullptr;
     pinned_release(P.h_col_run_slot, P.h_col_run_cap[0]); pinned_release(P.h_col_run_col, P.h_col_run_cap[1]);

@@ -22,6 +22,8 @@ struct Plan {
     // device-resident plan data (sub-buffers of the two arenas below)
     void* d_desc_arena = nullptr;
     void* d_pattern_arena = nullptr;
+    void* d_rowptr_arena = nullptr;
+    uint64_t n_sorted_pairs = 0;         // pairs whose row DoF is shared between blocks (the part of the pattern that is sorted)
     ClassDesc* d_classes = nullptr;
     ListDesc* d_lists = nullptr;
     uint8_t* d_spec_i = nullptr;
