@@ -227,6 +227,55 @@ __global__ void first_slot_of_row_kernel(const uint32_t* __restrict__ rows, unsi
 
 }  // namespace
 
+namespace {
+struct DevBlk { void* p; size_t bytes; int dev; };
+std::mutex g_dev_mu;
+std::vector<DevBlk> g_dev_free;                       // cached free blocks
+std::vector<DevBlk> g_dev_live;                       // sizes of the blocks handed out (looked up at dev_free)
+size_t g_dev_cached = 0;
+constexpr size_t DEV_CACHE_BYTES = (size_t)8 << 30;   // at most this much memory parked in the cache
+constexpr size_t DEV_CACHE_BLOCKS = 96;
+}  // namespace
+
+cudaError_t dev_malloc(void** p, size_t bytes, cudaStream_t st) {
+    bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        size_t best = SIZE_MAX;   // best fit among the blocks that waste at most 1/8 (+ 1 MB)
+        for (size_t k = 0; k < g_dev_free.size(); k++) {
+            const DevBlk& b = g_dev_free[k];
+            if (b.dev == dev && b.bytes >= bytes && b.bytes <= bytes + bytes / 8 + (1u << 20) && (best == SIZE_MAX || b.bytes < g_dev_free[best].bytes)) best = k;
+        }
+        if (best != SIZE_MAX) {
+            const DevBlk b = g_dev_free[best];
+            g_dev_free.erase(g_dev_free.begin() + best);
+            g_dev_cached -= b.bytes;
+            g_dev_live.push_back(b);
+            *p = b.p;
+            return cudaSuccess;
+        }
+    }
+    const cudaError_t e = cudaMallocAsync(p, bytes, st);
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> lk(g_dev_mu); g_dev_live.push_back(DevBlk{*p, bytes, dev}); }
+    return e;
+}
+
+void dev_free(void* p, cudaStream_t st) {
+    if (!p) return;
+    DevBlk b{p, 0, 0};
+    bool cache = false;
+    {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        for (size_t k = g_dev_live.size(); k-- > 0;)
+            if (g_dev_live[k].p == p) { b = g_dev_live[k]; g_dev_live.erase(g_dev_live.begin() + k); break; }
+        cache = b.bytes && g_dev_free.size() < DEV_CACHE_BLOCKS && g_dev_cached + b.bytes <= DEV_CACHE_BYTES;
+        if (cache) { g_dev_free.push_back(b); g_dev_cached += b.bytes; }
+    }
+    if (!cache) cudaFreeAsync(p, st);
+}
+
 void dev_pool_init(int device) {
     static bool done[64] = {};
     if (device < 0 || device >= 64 || done[device]) return;

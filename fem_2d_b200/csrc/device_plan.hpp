@@ -86,10 +86,13 @@ struct Plan {
     int sm_count = 0;
 };
 
-// Device memory comes from the stream-ordered pool of the device (cudaMallocAsync) with an unlimited release threshold, so the
-// symbolic phase of a repeated one-shot call re-uses its ~1.5 GB of scratch instead of paying cudaMalloc / cudaFree every time.
-inline cudaError_t dev_malloc(void** p, size_t bytes, cudaStream_t st = nullptr) { return cudaMallocAsync(p, bytes ? bytes : 1, st); }
-inline void dev_free(void* p, cudaStream_t st = nullptr) { if (p) cudaFreeAsync(p, st); }
+// Device memory: blocks come from the stream-ordered pool of the device (cudaMallocAsync, unlimited release threshold) through a
+// small size-matched cache of freed blocks.  A one-shot caller builds and frees a plan per call; the pool alone does not hand the
+// same blocks back for the same sequence of requests (it splits large free blocks for small requests and then has to map fresh
+// memory for the large ones: milliseconds, and erratic), the cache does.  Invariant: dev_free is only called once the block's last
+// use has completed (after a synchronising call), so a cached block can be handed to any stream.
+cudaError_t dev_malloc(void** p, size_t bytes, cudaStream_t st = nullptr);
+void dev_free(void* p, cudaStream_t st = nullptr);
 void dev_pool_init(int device);
 
 constexpr uint32_t MAX_SLOT_RANGES = 4;   // slot ranges one numeric call can cover (multi-GPU: a rank's Elem-type rows + its edge-type rows)
