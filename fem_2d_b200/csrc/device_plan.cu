@@ -288,6 +288,33 @@ void dev_pool_init(int device) {
 }
 
 namespace {
+// Small process-wide cache of pinned staging buffers: a one-shot call builds and frees a plan every time, and pinning a few MB
+// costs about as much as the copy it serves.
+std::mutex g_pin_mu;
+std::vector<std::pair<void*, size_t>> g_pin_free;
+void* pinned_acquire(size_t bytes, size_t* cap) {
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        size_t best = SIZE_MAX;   // best fit, so that the same-sized requests of successive plans land on the same buffers
+        for (size_t k = 0; k < g_pin_free.size(); k++)
+            if (g_pin_free[k].second >= bytes && (best == SIZE_MAX || g_pin_free[k].second < g_pin_free[best].second)) best = k;
+        if (best != SIZE_MAX) { void* p = g_pin_free[best].first; *cap = g_pin_free[best].second; g_pin_free.erase(g_pin_free.begin() + best); return p; }
+    }
+    void* p = nullptr;
+    bytes = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);   // MiB granularity: a slightly larger Domain re-uses the buffer
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    *cap = bytes;
+    return p;
+}
+void pinned_release(void* p, size_t cap) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (g_pin_free.size() < 8) { g_pin_free.push_back({p, cap}); return; }
+    cudaFreeHost(p);
+}
+}  // namespace
+
+namespace {
 // Carves 256-byte aligned sub-buffers out of one allocation.
 struct Arena {
     size_t size = 0;
@@ -331,8 +358,12 @@ int device_symbolic(Plan& P, std::string& err) {
     const size_t o_voff = desc.reserve(h_voff.size() * 4), o_mtoff = desc.reserve(h_mtoff.size() * 4);
     const size_t desc_plan_bytes = desc.size;                     // everything above lives as long as the plan
     const size_t o_blocks = desc.reserve(hb.size() * sizeof(DevBlock)), o_canon = desc.reserve(H.canon_dof.size() * 4);
-    std::vector<unsigned char> blob(desc.size, 0);
-    auto put = [&](size_t off, const void* src, size_t n) { if (n) std::memcpy(blob.data() + off, src, n); };
+    // staged in a cached pinned buffer: one asynchronous H2D at PCIe speed instead of a pageable copy
+    size_t blob_cap = 0;
+    unsigned char* blob = (unsigned char*)pinned_acquire(desc.size, &blob_cap);
+    if (!blob) { err = "pinned host allocation failed"; return FEM2D_ERR_OUT_OF_MEMORY; }
+    struct BlobGuard { unsigned char* p; size_t cap; ~BlobGuard() { pinned_release(p, cap); } } blob_guard{blob, blob_cap};   // released after the last sync below
+    auto put = [&](size_t off, const void* src, size_t n) { if (n) std::memcpy(blob + off, src, n); };
     put(o_classes, H.classes.data(), H.classes.size() * sizeof(ClassDesc)); put(o_lists, H.lists.data(), H.lists.size() * sizeof(ListDesc));
     put(o_si, H.spec_i.data(), H.spec_i.size()); put(o_sj, H.spec_j.data(), H.spec_j.size());
     put(o_tabs, H.tables.data(), H.tables.size() * sizeof(TableDesc)); put(o_grams, H.grams.data(), H.grams.size() * sizeof(GramDesc));
@@ -361,8 +392,8 @@ int device_symbolic(Plan& P, std::string& err) {
 #define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); dev_free(scratch); dev_free(scratch2); return FEM2D_ERR_CUDA; } } while (0)
     // descriptors: the plan-owned part goes to a first small plan allocation, the rest into the scratch arena
     CKC(dev_malloc(&P.d_desc_arena, desc_plan_bytes));
-    CKC(cudaMemcpyAsync(P.d_desc_arena, blob.data(), desc_plan_bytes, cudaMemcpyHostToDevice, nullptr));
-    CKC(cudaMemcpyAsync(at<char>(scratch, s_desc), blob.data() + desc_plan_bytes, desc.size - desc_plan_bytes, cudaMemcpyHostToDevice, nullptr));
+    CKC(cudaMemcpyAsync(P.d_desc_arena, blob, desc_plan_bytes, cudaMemcpyHostToDevice, nullptr));
+    CKC(cudaMemcpyAsync(at<char>(scratch, s_desc), blob + desc_plan_bytes, desc.size - desc_plan_bytes, cudaMemcpyHostToDevice, nullptr));
     P.d_classes = at<ClassDesc>(P.d_desc_arena, o_classes); P.d_lists = at<ListDesc>(P.d_desc_arena, o_lists);
     P.d_spec_i = at<uint8_t>(P.d_desc_arena, o_si); P.d_spec_j = at<uint8_t>(P.d_desc_arena, o_sj);
     P.d_tables = at<TableDesc>(P.d_desc_arena, o_tabs); P.d_grams = at<GramDesc>(P.d_desc_arena, o_grams);
@@ -641,33 +672,6 @@ int device_row_block_bounds_range(const Plan& P, uint64_t lo, uint64_t hi, uint3
     if (e != cudaSuccess) { err = cudaGetErrorString(e); return FEM2D_ERR_CUDA; }
     return FEM2D_OK;
 }
-
-namespace {
-// Small process-wide cache of pinned staging buffers: a one-shot call builds and frees a plan every time, and pinning a few MB
-// costs about as much as the copy it serves.
-std::mutex g_pin_mu;
-std::vector<std::pair<void*, size_t>> g_pin_free;
-void* pinned_acquire(size_t bytes, size_t* cap) {
-    {
-        std::lock_guard<std::mutex> lk(g_pin_mu);
-        size_t best = SIZE_MAX;   // best fit, so that the same-sized requests of successive plans land on the same buffers
-        for (size_t k = 0; k < g_pin_free.size(); k++)
-            if (g_pin_free[k].second >= bytes && (best == SIZE_MAX || g_pin_free[k].second < g_pin_free[best].second)) best = k;
-        if (best != SIZE_MAX) { void* p = g_pin_free[best].first; *cap = g_pin_free[best].second; g_pin_free.erase(g_pin_free.begin() + best); return p; }
-    }
-    void* p = nullptr;
-    bytes = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);   // MiB granularity: a slightly larger Domain re-uses the buffer
-    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    *cap = bytes;
-    return p;
-}
-void pinned_release(void* p, size_t cap) {
-    if (!p) return;
-    std::lock_guard<std::mutex> lk(g_pin_mu);
-    if (g_pin_free.size() < 8) { g_pin_free.push_back({p, cap}); return; }
-    cudaFreeHost(p);
-}
-}  // namespace
 
 int device_row_ptr_host(Plan& P, cudaStream_t st, std::string& err) {
     if (P.h_row_ptr) return FEM2D_OK;
