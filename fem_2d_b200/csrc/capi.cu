@@ -395,15 +395,11 @@ int fem2d_assemble_ranges(fem2d_plan* plan, int basis_kind, int a_kind, int b_ki
     if (!p.d_out_b) CKS(fem2d::dev_malloc((void**)&p.d_out_b, bytes));
     // The pattern crosses PCIe in compressed form and is expanded on host threads while the value arrays are in flight: rows[] from
     // the CSR row offsets (4 B per row), cols[] from the runs of consecutive column ids (8 B per run, ~5 runs per row on hp-meshes).
-    if (rows) {
-        std::string rerr;
-        st = fem2d::device_row_ptr_host(p, nullptr, rerr);
-        if (st != FEM2D_OK) return fail(st, rerr);
-    }
-    if (cols) {
-        std::string cerr;
-        st = fem2d::device_col_runs_host(p, nullptr, cerr);
-        if (st != FEM2D_OK) return fail(st, cerr);
+    // They are fetched first: a small copy queued next to the value copies would wait behind them, and so would the expansion.
+    {
+        std::string perr;
+        if (rows) { st = fem2d::device_row_ptr_host(p, nullptr, perr); if (st != FEM2D_OK) return fail(st, perr); }
+        if (cols) { st = fem2d::device_col_runs_host(p, nullptr, perr); if (st != FEM2D_OK) return fail(st, perr); }
     }
     st = fem2d_assemble_device_ranges(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, n_ranges, b, e, p.d_out_a, p.d_out_b, nullptr);
     if (st != FEM2D_OK) return st;

@@ -699,27 +699,21 @@ int device_col_runs_host(Plan& P, cudaStream_t st, std::string& err) {
     if (P.h_col_run_slot) return FEM2D_OK;
     CK(cudaSetDevice(P.device));
     const uint32_t nnz = (uint32_t)P.nnz;
-    // Scratch comes out of the plan's own value staging buffers (they are overwritten by the numeric phase that follows), not out of
-    // the memory pool: a one-shot caller builds and frees a plan per call, and an allocation pattern that changes between the
-    // symbolic phases makes the stream-ordered pool re-map its 1.5 GB scratch block (milliseconds, and erratic).
-    const size_t out_bytes = std::max<uint64_t>(P.nnz, 1) * sizeof(double);
-    if (!P.d_out_a) CK(dev_malloc((void**)&P.d_out_a, out_bytes));
-    if (!P.d_out_b) CK(dev_malloc((void**)&P.d_out_b, out_bytes));
-    uint32_t* d_slot = reinterpret_cast<uint32_t*>(P.d_out_b);            // (nnz + 1) * 4 <= nnz * 8 for nnz >= 1
-    uint32_t* d_n = reinterpret_cast<uint32_t*>(P.d_out_a);
-    uint32_t* d_col = reinterpret_cast<uint32_t*>(P.d_out_a) + 64;        // n_runs * 4 bytes
+    // Scratch from the (size-matched, cached) device allocator.
+    uint32_t *d_slot = nullptr, *d_col = nullptr;
+    CK(dev_malloc((void**)&d_slot, ((size_t)nnz + 1) * 4 + 256, st));
+    uint32_t* d_n = d_slot + (((size_t)nnz + 1 + 63) & ~(size_t)63);   // the count lives in the slack behind the slots
     cub::CountingInputIterator<uint32_t> it(0);
     ColRunHead pred{P.d_rows, P.d_cols};
     size_t temp = 0;
     CK(cub::DeviceSelect::If(nullptr, temp, it, d_slot, d_n, (int)nnz, pred, st));
-    const size_t col_cap = ((size_t)nnz * 4 + 256 + 255) & ~(size_t)255;  // worst case: every slot its own run
-    void* d_temp = reinterpret_cast<char*>(P.d_out_a) + col_cap;
-    void* own_temp = nullptr;
-    if (col_cap + temp > out_bytes) { CK(dev_malloc(&own_temp, temp, st)); d_temp = own_temp; }   // tiny plans only
+    void* d_temp = nullptr;
+    { const cudaError_t e0 = dev_malloc(&d_temp, temp, st); if (e0 != cudaSuccess) { dev_free(d_slot, st); err = cudaGetErrorString(e0); return FEM2D_ERR_CUDA; } }
     cudaError_t e = cub::DeviceSelect::If(d_temp, temp, it, d_slot, d_n, (int)nnz, pred, st);
     uint32_t n_runs = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&n_runs, d_n, 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = dev_malloc((void**)&d_col, ((size_t)n_runs + 1) * 4, st);
     if (e == cudaSuccess && n_runs) { gather_u32_kernel<<<(n_runs + 255) / 256, 256, 0, st>>>(P.d_cols, d_slot, n_runs, d_col); e = cudaGetLastError(); }
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_slot + n_runs, &P.nnz32_sentinel, 4, cudaMemcpyHostToDevice, st);   // sentinel: end of the last run
     if (e == cudaSuccess) {
@@ -730,7 +724,7 @@ int device_col_runs_host(Plan& P, cudaStream_t st, std::string& err) {
     if (e == cudaSuccess) e = cudaMemcpyAsync(P.h_col_run_slot, d_slot, ((size_t)n_runs + 1) * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(P.h_col_run_col, d_col, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    dev_free(own_temp, st);
+    dev_free(d_slot, st); dev_free(d_col, st); dev_free(d_temp, st);
     if (e != cudaSuccess) {
         pinned_release(P.h_col_run_slot, P.h_col_run_cap[0]); pinned_release(P.h_col_run_col, P.h_col_run_cap[1]);
         P.h_col_run_slot = P.h_col_run_col = nullptr;
