@@ -98,7 +98,7 @@ void dev_pool_init(int device);
 constexpr uint32_t MAX_SLOT_RANGES = 4;   // slot ranges one numeric call can cover (multi-GPU: a rank's Elem-type rows + its edge-type rows)
 constexpr uint32_t SRC_CHUNK = 64;                     // slots per chunk of the packed source map
 constexpr uint32_t SRC_CHUNK_PLAIN = 0x80000000u;      // chunk_base value of a chunk that is read through the plain 32-bit src1
-constexpr uint32_t K3_THREADS = 256;          // scatter kernel: one CTA per K3_BLOCK_SLOTS-aligned block of slots,
+constexpr uint32_t K3_THREADS = 128;          // scatter kernel: one CTA per K3_BLOCK_SLOTS-aligned block of slots,
 constexpr uint32_t K3_ITERS = 4;              // K3_ITERS slots per thread
 constexpr uint32_t K3_BLOCK_SLOTS = K3_THREADS * K3_ITERS;
 constexpr uint32_t K3_PREFETCH_SLOTS = 1u << 20;   // distance of the L2 prefetch of the 16-bit offset stream
