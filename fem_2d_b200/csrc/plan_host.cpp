@@ -355,7 +355,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
     // Few, heavily deduplicated classes would leave most of the 148 SMs idle: shrink the item size until there are about two
     // CTAs per SM (each item re-stages its class's slabs, which is cheap next to an idle machine).
     uint32_t cap = K2_ROUNDS * K2_THREADS;
-    const uint32_t min_cap = P.tile_p == 1 ? 128u : 64u;
+    const uint32_t min_cap = P.tile_p == 1 ? 256u : 64u;   // latency shape: one full round per CTA measured best (128: +10 %, 512: +30 %)
     for (; cap > min_cap; cap /= 2) {
         uint64_t n = 0;
         for (const ClassDesc& c : P.classes) n += (c.n_mt + cap - 1) / cap;
