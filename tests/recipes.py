@@ -105,8 +105,9 @@ def mesh_cfg3(api, levels=6, order=6):   # BASELINE cfg 3: mesh_a, Orders(6,6), 
     return m
 
 
-def mesh_cfg4(api, t_levels=4, rounds=3, pmin=2, pmax=10):   # BASELINE cfg 4 (SURVEY.md 8d recipe)
-    m = api.Mesh.from_file(MESH_C)
+def mesh_cfg4(api, t_levels=4, rounds=3, pmin=2, pmax=10, seed=SEED, mesh_file=MESH_C):   # BASELINE cfg 4 (SURVEY.md 8d recipe)
+    SEED = seed
+    m = api.Mesh.from_file(mesh_file)
     for _ in range(t_levels):
         m.global_h_refinement(api.href(T))
     for r in range(rounds):

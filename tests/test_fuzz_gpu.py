@@ -1,0 +1,42 @@
+"""Randomised differential test of the whole CUDA path against the oracle: seeded anisotropic U/V refinements to n-irregularity up to 3
+with random per-Elem orders on all three reference meshes (the cfg-4 recipe family of SURVEY.md 8d with varying seeds).  Every case checks
+the device pattern (symbolic assembly by rows + sorted shared rows) and the A/B bits, with and without block dedupe."""
+import numpy as np
+import pytest
+
+import recipes
+
+pytestmark = pytest.mark.gpu
+
+import fem_2d_b200 as F  # noqa: E402
+import oracle as O  # noqa: E402
+
+CASES = [(seed, mesh, t, r, pmin, pmax)
+         for seed, (mesh, t, r, pmin, pmax) in enumerate([
+             (recipes.MESH_C, 1, 3, 1, 4), (recipes.MESH_C, 2, 2, 2, 6), (recipes.MESH_A, 0, 3, 1, 5), (recipes.MESH_A, 1, 2, 2, 4),
+             (recipes.MESH_B, 0, 3, 2, 5), (recipes.MESH_B, 1, 1, 1, 3), (recipes.MESH_C, 0, 4, 3, 7), (recipes.MESH_A, 1, 3, 1, 3),
+             (recipes.MESH_B, 1, 2, 3, 4), (recipes.MESH_C, 2, 3, 1, 2)], start=101)]
+
+
+@pytest.mark.parametrize("seed,mesh,t_levels,rounds,pmin,pmax", CASES, ids=[f"seed{c[0]}" for c in CASES])
+def test_random_hp_mesh_bit_identical(seed, mesh, t_levels, rounds, pmin, pmax):
+    def build(api):
+        return recipes.mesh_cfg4(api, t_levels=t_levels, rounds=rounds, pmin=pmin, pmax=pmax, seed=seed * 7919 + 13, mesh_file=mesh)
+    do, df = O.Domain.from_mesh(build(recipes.api("oracle"))), F.Domain.from_mesh(build(recipes.api("product")))
+    assert do.num_dofs == df.num_dofs
+    if do.num_dofs == 0:
+        pytest.skip("no DoFs on this mesh")
+    nu, nv = 4 + seed % 5, 4 + (seed // 3) % 6
+    glq = (F.gauss_quadrature_points(nu), F.gauss_quadrature_points(nv))
+    ref = O.galerkin_sample_gep_hcurl(do, glq=glq)
+    for dedupe in (True, False):
+        plan = F.Plan(df.view(), device=0, dedupe=dedupe)
+        rows, cols, a, b = plan.assemble(glq)
+        assert np.array_equal(rows, ref.rows) and np.array_equal(cols, ref.cols), f"pattern differs (dedupe={dedupe})"
+        assert np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(ref.a).view(np.uint64)), f"A differs (dedupe={dedupe})"
+        assert np.array_equal(np.ascontiguousarray(b).view(np.uint64), np.ascontiguousarray(ref.b).view(np.uint64)), f"B differs (dedupe={dedupe})"
+        assert plan.info["max_contrib"] <= 2
+        hp = F.Plan(df.view(), device=-1, dedupe=dedupe)          # independent host construction of the pattern
+        hr, hc = hp.pattern()
+        assert np.array_equal(hr, rows) and np.array_equal(hc, cols)
+        assert np.array_equal(hp.row_offsets(), plan.row_offsets())
