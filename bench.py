@@ -321,6 +321,31 @@ def run_ours(args):
         extra["other_dedupe_setting"] = {"dedupe": int(not bool(args.dedupe)), "ms_per_step": ms_nd, "value": 2.0 * nnz / (ms_nd * 1e-3), "unit": "nnz/s",
                                          "integrator_ms": t_nd["integrator_ms"], "scatter_ms": t_nd["scatter_ms"], "n_classes": plan_nd.info["n_classes"]}
         del plan_nd
+        # the other BASELINE.json configs that fit one GPU (parity-test cases, reported for context only): device-resident step time
+        others = {}
+        for wl in ("cfg2", "cfg4"):
+            try:
+                dom = build_product_domain(wl)
+                g = WORKLOADS[wl]["glq"]
+                gq = (F.gauss_quadrature_points(g), F.gauss_quadrature_points(g))
+                pl = F.Plan(dom.view(), device=local_rank, dedupe=bool(args.dedupe))
+                ta = torch.empty(pl.nnz, dtype=torch.float64, device=dev); tb = torch.empty_like(ta)
+                for _ in range(3):
+                    pl.assemble_device(gq, ta.data_ptr(), tb.data_ptr(), mode=mode, stream=stream.cuda_stream)
+                torch.cuda.synchronize()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(stream)
+                for _ in range(20):
+                    pl.assemble_device(gq, ta.data_ptr(), tb.data_ptr(), mode=mode, stream=stream.cuda_stream)
+                g1.record(stream)
+                torch.cuda.synchronize()
+                ms = g0.elapsed_time(g1) / 20
+                others[wl] = {"n_dofs": pl.n_dofs, "nnz_upper_per_matrix": pl.nnz, "n_classes": pl.info["n_classes"], "glq": [g, g], "ms_per_step": ms,
+                              "value": 2.0 * pl.nnz / (ms * 1e-3), "unit": "nnz/s"}
+                del pl, ta, tb
+            except Exception as ex:  # pragma: no cover
+                others[wl] = {"error": str(ex)}
+        extra["other_configs"] = others
 
     # ---- end to end through the reference-facing call: host Domain view -> host CSR arrays ------------------------------------
     e2e = None
