@@ -521,14 +521,7 @@ __device__ void mark_source(uint32_t v, const ClassDesc* classes, const ListDesc
     const uint32_t nP = lists[c.listP].n, nUP = lists[c.listP].nU, nQ = lists[c.listQ].n, nUQ = lists[c.listQ].nU;
     const uint32_t t = v - voff[lo], a = t / nQ, b = t - a * nQ;
     const SubBlocks sb = make_subblocks(nP, nUP, nQ, nUQ, c.local, tp);
-    const uint32_t sub = (a < nUP ? 0u : 2u) + (b < nUQ ? 0u : 1u);
-    uint32_t idx = 0;
-    for (uint32_t k = 0; k < sub; k++) idx += sb.cnt[k];
-    const uint32_t rt = (a - sb.row0[sub]) / tp, ct = (b - sb.col0[sub]) / MT_Q, nct = mt_div_up(sb.cols[sub], MT_Q);
-    if (sb.tri[sub]) {
-        for (uint32_t q = 0; q < rt; q++) { const uint32_t l0 = q * tp / MT_Q; if (nct > l0) idx += nct - l0; }
-        idx += ct - rt * tp / MT_Q;
-    } else idx += rt * nct + ct;
+    const uint32_t idx = encode_tile(sb, a, b, nUP, nUQ, tp);
     flags[mtoff[lo] + idx] = 1;
 }
 
@@ -558,7 +551,7 @@ ItemSplit split_items(const HostPlan& H, const std::vector<WorkItem>& items) {
     // the latency shape (1 x 2 tiles, small plans) keeps one CTA size
     const uint32_t small_tiles = H.tile_p == 1 ? 0u : (uint32_t)K2_SMALL_TILES;
     for (const WorkItem& it : items) {
-        const bool big = it.mt_count > small_tiles || stride_of(it) > (uint32_t)K2_SMALL_STRIDE;
+        const bool big = item_slots(it.n_same, it.mt_count) > small_tiles || stride_of(it) > (uint32_t)K2_SMALL_STRIDE;
         if (big) { sp.n_big++; sp.stride_big = std::max(sp.stride_big, stride_of(it)); }
         else sp.stride_small = std::max(sp.stride_small, stride_of(it));
     }
@@ -592,7 +585,7 @@ int device_range_items(Plan& P, uint32_t n_ranges, const uint64_t* begins, const
     // items: per class, the runs of needed tiles (gaps of up to 2 tiles are bridged) packed into CTAs of <= ITEM_MAX_RANGES runs and
     // <= 2 * K2_THREADS tiles; every item records which function columns its tiles touch so it stages only those.
     std::vector<WorkItem> items;
-    const uint32_t cap = 2 * K2_THREADS, gap = 2, tp = P.host.tile_p;
+    const uint32_t cap = 2 * K2_THREADS - 31, gap = 2, tp = P.host.tile_p;   // tiles; + up to 31 slots of warp alignment (item_slots)
     uint64_t needed = 0, off = 0;
     std::vector<std::pair<uint32_t, uint32_t>> runs, cur;
     for (uint32_t c = 0; c < P.host.classes.size(); c++) {
@@ -618,7 +611,8 @@ int device_range_items(Plan& P, uint32_t n_ranges, const uint64_t* begins, const
                 for (uint32_t t = r.first; t < r.first + r.second; t++) {
                     uint32_t sub, rt, ct;
                     decode_tile(sb, t, tp, sub, rt, ct);
-                    const uint32_t r0 = rt * tp, r1 = std::min(r0 + tp, sb.rows[sub]), c0 = ct * MT_Q, c1 = std::min<uint32_t>(c0 + MT_Q, sb.cols[sub]);
+                    const uint32_t w = mt_width(sub);
+                    const uint32_t r0 = rt * tp, r1 = std::min(r0 + tp, sb.rows[sub]), c0 = ct * w, c1 = std::min<uint32_t>(c0 + w, sb.cols[sub]);
                     uint32_t* pr = cols[0][sub >= 2]; uint32_t* qc = cols[1][sub & 1];
                     pr[0] = std::min(pr[0], r0); pr[1] = std::max(pr[1], r1);
                     qc[0] = std::min(qc[0], c0); qc[1] = std::max(qc[1], c1);

@@ -14,7 +14,8 @@
 //   A: inner += ((curl_p * curl_q) [* ratio]) * v_w[n];  sol += inner * u_w[m];  A = (1/mu) * sol      integrals.rs:36-91, glq.rs:19-32
 //   B: inner += ((val_p * val_q) * max(det_P, det_Q)) * v_w[n]; ...; B = ((eps * glq_P) * glq_Q) * sol  integrals.rs:302-353
 // curl_f and val_f depend on one function only -> they are staged per block in shared memory ("slabs"), and each thread
-// contracts a 4 x 2 register tile of pairs over the points in strict (m outer, n inner) order.
+// contracts a register tile of pairs over the points in strict (m outer, n inner) order: 4 x 2 same-direction pairs (A and B)
+// or 4 x 4 cross-direction pairs (A only; B is an exact zero) -- the same accumulator registers and about the same work.
 #include <cuda_runtime.h>
 
 #include "basis_device.cuh"
@@ -55,82 +56,92 @@ struct K2Args {
 
 __device__ __forceinline__ uint32_t pad4(uint32_t x) { return (x + 3u) & ~3u; }
 
-template <bool SAME, int TP>
-__device__ __forceinline__ void contract_point(const double* __restrict__ cp, const double* __restrict__ cq,
-                                               const double* __restrict__ fp, const double* __restrict__ fq, double ratio, double maxdet,
-                                               double w, double (&inA)[TP][MT_Q], double (&inB)[TP][MT_Q]) {
-    double pc[TP], qc[MT_Q];
-    if (TP == 1) pc[0] = cp[0];
+// Accumulators of one thread: acc[2][TP][MT_Q].  Same-direction tile (TP x MT_Q pairs): [0] = A, [1] = B.  Cross-direction tile
+// (TP x MT_QX pairs, A only): column c lives in [c >> 1][r][c & 1].
+template <int TP>
+__device__ __forceinline__ void load_rows(const double* __restrict__ p, double (&v)[TP]) {
+    if (TP == 1) v[0] = p[0];
     else {
 #pragma unroll
-        for (int r = 0; r + 1 < TP; r += 2) { const double2 t = *reinterpret_cast<const double2*>(cp + r); pc[r] = t.x; pc[r + 1] = t.y; }
+        for (int r = 0; r + 1 < TP; r += 2) { const double2 t = *reinterpret_cast<const double2*>(p + r); v[r] = t.x; v[r + 1] = t.y; }
     }
-#pragma unroll
-    for (int c = 0; c < MT_Q; c += 2) { const double2 t = *reinterpret_cast<const double2*>(cq + c); qc[c] = t.x; qc[c + 1] = t.y; }
-    // The operations of one pair form a dependent chain (8-cycle FP64 latency each); they are written stage by stage over the
-    // TP x MT_Q independent pairs so that the in-order issue always has independent work (same operations, same order per value).
-    double tA[TP][MT_Q];
+}
+
+// One point of a same-direction tile.  The operations of one pair form a dependent chain (8-cycle FP64 latency each); they are
+// written stage by stage over the independent pairs so that the in-order issue always has independent work (same operations,
+// same order per value).
+template <int TP>
+__device__ __forceinline__ void contract_point_same(const double* __restrict__ cp, const double* __restrict__ cq, const double* __restrict__ fp,
+                                                    const double* __restrict__ fq, double ratio, double maxdet, double w,
+                                                    double (&in)[2][TP][MT_Q]) {
+    double pc[TP], qc[MT_Q], pf[TP], qf[MT_Q], tA[TP][MT_Q], tB[TP][MT_Q];
+    load_rows<TP>(cp, pc); load_rows<MT_Q>(cq, qc);
 #pragma unroll
     for (int r = 0; r < TP; r++)
 #pragma unroll
         for (int c = 0; c < MT_Q; c++) tA[r][c] = pc[r] * qc[c];              // p_curl * q_curl
-    if (SAME) {
-        double pf[TP], qf[MT_Q], tB[TP][MT_Q];
-        if (TP == 1) pf[0] = fp[0];
-        else {
+    load_rows<TP>(fp, pf); load_rows<MT_Q>(fq, qf);
 #pragma unroll
-            for (int r = 0; r + 1 < TP; r += 2) { const double2 t = *reinterpret_cast<const double2*>(fp + r); pf[r] = t.x; pf[r + 1] = t.y; }
-        }
+    for (int r = 0; r < TP; r++)
 #pragma unroll
-        for (int c = 0; c < MT_Q; c += 2) { const double2 t = *reinterpret_cast<const double2*>(fq + c); qf[c] = t.x; qf[c + 1] = t.y; }
+        for (int c = 0; c < MT_Q; c++) tB[r][c] = pf[r] * qf[c];              // V2D::dot(f_p, f_q): the second product is a signed zero
 #pragma unroll
-        for (int r = 0; r < TP; r++)
+    for (int r = 0; r < TP; r++)
 #pragma unroll
-            for (int c = 0; c < MT_Q; c++) tB[r][c] = pf[r] * qf[c];          // V2D::dot(f_p, f_q): the second product is a signed zero
+        for (int c = 0; c < MT_Q; c++) tA[r][c] = tA[r][c] * ratio;           // * max_uv_ratios / max_vu_ratios (integrals.rs:50,86)
 #pragma unroll
-        for (int r = 0; r < TP; r++)
+    for (int r = 0; r < TP; r++)
 #pragma unroll
-            for (int c = 0; c < MT_Q; c++) tA[r][c] = tA[r][c] * ratio;       // * max_uv_ratios / max_vu_ratios (integrals.rs:50,86)
+        for (int c = 0; c < MT_Q; c++) tB[r][c] = tB[r][c] * maxdet;          // * partial_max(det_P, det_Q) (integrals.rs:312-315)
 #pragma unroll
-        for (int r = 0; r < TP; r++)
+    for (int r = 0; r < TP; r++)
 #pragma unroll
-            for (int c = 0; c < MT_Q; c++) tB[r][c] = tB[r][c] * maxdet;      // * partial_max(det_P, det_Q) (integrals.rs:312-315)
+        for (int c = 0; c < MT_Q; c++) tA[r][c] = tA[r][c] * w;
 #pragma unroll
-        for (int r = 0; r < TP; r++)
+    for (int r = 0; r < TP; r++)
 #pragma unroll
-            for (int c = 0; c < MT_Q; c++) tA[r][c] = tA[r][c] * w;
+        for (int c = 0; c < MT_Q; c++) tB[r][c] = tB[r][c] * w;
 #pragma unroll
-        for (int r = 0; r < TP; r++)
+    for (int r = 0; r < TP; r++)
 #pragma unroll
-            for (int c = 0; c < MT_Q; c++) tB[r][c] = tB[r][c] * w;
+        for (int c = 0; c < MT_Q; c++) in[0][r][c] = in[0][r][c] + tA[r][c];  // inner_solution += integrand * v_w (glq.rs:27)
 #pragma unroll
-        for (int r = 0; r < TP; r++)
+    for (int r = 0; r < TP; r++)
 #pragma unroll
-            for (int c = 0; c < MT_Q; c++) inA[r][c] = inA[r][c] + tA[r][c];  // inner_solution += integrand * v_w (glq.rs:27)
+        for (int c = 0; c < MT_Q; c++) in[1][r][c] = in[1][r][c] + tB[r][c];
+}
+
+// One point of a cross-direction tile: (p_curl * q_curl) * v_w only (integrals.rs:53-84: no ratio factor; the mass integrand is
+// a signed zero).
+template <int TP>
+__device__ __forceinline__ void contract_point_cross(const double* __restrict__ cp, const double* __restrict__ cq, double w,
+                                                     double (&in)[2][TP][MT_Q]) {
+    constexpr int XW = MT_QX;
+    double pc[TP], qc[XW], tA[TP][XW];
+    load_rows<TP>(cp, pc); load_rows<XW>(cq, qc);
 #pragma unroll
-        for (int r = 0; r < TP; r++)
+    for (int r = 0; r < TP; r++)
 #pragma unroll
-            for (int c = 0; c < MT_Q; c++) inB[r][c] = inB[r][c] + tB[r][c];
-    } else {
+        for (int c = 0; c < XW; c++) tA[r][c] = pc[r] * qc[c];
 #pragma unroll
-        for (int r = 0; r < TP; r++)
+    for (int r = 0; r < TP; r++)
 #pragma unroll
-            for (int c = 0; c < MT_Q; c++) tA[r][c] = tA[r][c] * w;
+        for (int c = 0; c < XW; c++) tA[r][c] = tA[r][c] * w;
 #pragma unroll
-        for (int r = 0; r < TP; r++)
+    for (int r = 0; r < TP; r++)
 #pragma unroll
-            for (int c = 0; c < MT_Q; c++) inA[r][c] = inA[r][c] + tA[r][c];
-    }
+        for (int c = 0; c < XW; c++) in[c >> 1][r][c & 1] = in[c >> 1][r][c & 1] + tA[r][c];
 }
 
 // Contract `run` consecutive points of one quadrature row (n .. n+run-1 of row m) into the inner accumulators.
 template <bool SAME, int TP>
 __device__ __forceinline__ void contract_run(const double*& cp, const double*& cq, const double*& fp, const double*& fq, uint32_t strideP,
                                              uint32_t strideQ, const double* __restrict__ vw, uint32_t run, double ratio, double maxdet,
-                                             double (&inA)[TP][MT_Q], double (&inB)[TP][MT_Q]) {
+                                             double (&in)[2][TP][MT_Q]) {
 #pragma unroll 4
     for (uint32_t k = 0; k < run; k++) {
-        contract_point<SAME, TP>(cp, cq, fp, fq, ratio, maxdet, vw[k], inA, inB);
+        if (SAME) contract_point_same<TP>(cp, cq, fp, fq, ratio, maxdet, vw[k], in);
+        else contract_point_cross<TP>(cp, cq, vw[k], in);
         cp += strideP; cq += strideQ;
         if (SAME) { fp += strideP; fq += strideQ; }
     }
@@ -144,7 +155,7 @@ __global__ void __launch_bounds__(NT, NT == K2_THREADS ? K2_MIN_CTAS : K2_SMALL_
     if (!g.follows_sampler) cudaTriggerProgrammaticLaunchCompletion();
     const WorkItem it = g.items[blockIdx.x];
     const ClassDesc c = g.classes[it.cls];
-    const ListDesc LP = g.lists[c.listP], LQ = g.lists[c.listQ];
+    const ListDesc LP = c.lp, LQ = c.lq;
     const uint32_t nP = LP.n, nUP = LP.nU, nQ = LQ.n, nUQ = LQ.nU;
     const uint32_t strideP = pad4(nUP) + pad4(nP - nUP);
     const uint32_t strideQ = c.local ? strideP : pad4(nUQ) + pad4(nQ - nUQ);
@@ -161,25 +172,34 @@ __global__ void __launch_bounds__(NT, NT == K2_THREADS ? K2_MIN_CTAS : K2_SMALL_
     for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) s_uw[k] = g.glq[128 + k];
     for (uint32_t k = threadIdx.x; k < nv; k += blockDim.x) s_vw[k] = g.glq[384 + k];
 
-    // ---- per-class constants (HierCurlBasisFn::defined_over, basis.rs:395-413; M2D::det / inverse, space.rs:138-147)
+    // ---- per-class constants (HierCurlBasisFn::defined_over, basis.rs:395-413; M2D::det / inverse, space.rs:138-147).
+    // An FP64 division is a ~25-instruction dependent chain: the nine quotients are computed once per CTA, one per lane of the
+    // second warp (the first one builds the tile enumeration meanwhile), and read back after the barrier.
     const double detP = c.dxP * c.dyP - 0.0 * 0.0, detQ = c.dxQ * c.dyQ - 0.0 * 0.0;
-    const double jiuP = c.dyP / detP, jivP = c.dxP / detP;     // jac_inv.u[0], jac_inv.v[1]
-    const double jiuQ = c.dyQ / detQ, jivQ = c.dxQ / detQ;
-    const double ge = (double)(detP >= detQ), lt = (double)(detP < detQ);
-    const double ratio_uv = ge * (c.dxP / c.dyP) + lt * (c.dxQ / c.dyQ);   // max_uv_ratios integrals.rs:250-259, basis.rs:341-343
-    const double ratio_vu = ge * (c.dyP / c.dxP) + lt * (c.dyQ / c.dxQ);   // max_vu_ratios integrals.rs:262-271, basis.rs:346-348
-    const double maxdet = detP > detQ ? detP : detQ;                        // partial_max integrals.rs:421-423
-    const double coefA = 1.0 / c.mu;                                        // integrals.rs:37
-    const double coefB = c.eps * (c.su * c.sv) * (1.0 * 1.0);               // eps * p.glq_scale() * q.glq_scale() integrals.rs:303-305
-
-    const double* tPu = g.tabs + (size_t)c.tabPu * 4 * g.NO * g.NPT;
-    const double* tPv = g.tabs + (size_t)c.tabPv * 4 * g.NO * g.NPT;
-    const double* tQu = g.tabs + (size_t)c.tabQu * 4 * g.NO * g.NPT;
-    const double* tQv = g.tabs + (size_t)c.tabQv * 4 * g.NO * g.NPT;
-    const uint32_t AS = g.NO * g.NPT;   // stride between the four arrays N, N', T, T'
+    __shared__ double s_quot[9];
     __shared__ SubBlocks sb;
     if (threadIdx.x == 0) sb = make_subblocks(nP, nUP, nQ, nUQ, c.local, TP);
+    if (threadIdx.x >= 32 && threadIdx.x < 41) {
+        const uint32_t k = threadIdx.x - 32;
+        const double num = k == 0 ? c.dyP : k == 1 ? c.dxP : k == 2 ? c.dyQ : k == 3 ? c.dxQ : k == 4 ? c.dxP : k == 5 ? c.dxQ : k == 6 ? c.dyP : k == 7 ? c.dyQ : 1.0;
+        const double den = k < 2 ? detP : k < 4 ? detQ : k == 4 ? c.dyP : k == 5 ? c.dyQ : k == 6 ? c.dxP : k == 7 ? c.dxQ : c.mu;
+        s_quot[k] = num / den;
+    }
     __syncthreads();
+    const double jiuP = s_quot[0], jivP = s_quot[1];           // jac_inv.u[0] = dy_dv / det, jac_inv.v[1] = dx_du / det
+    const double jiuQ = s_quot[2], jivQ = s_quot[3];
+    const double ge = (double)(detP >= detQ), lt = (double)(detP < detQ);
+    const double ratio_uv = ge * s_quot[4] + lt * s_quot[5];   // max_uv_ratios integrals.rs:250-259, basis.rs:341-343: ge * (dxP / dyP) + lt * (dxQ / dyQ)
+    const double ratio_vu = ge * s_quot[6] + lt * s_quot[7];   // max_vu_ratios integrals.rs:262-271, basis.rs:346-348: ge * (dyP / dxP) + lt * (dyQ / dxQ)
+    const double maxdet = detP > detQ ? detP : detQ;           // partial_max integrals.rs:421-423
+    const double coefA = s_quot[8];                            // 1.0 / mu, integrals.rs:37
+    const double coefB = c.eps * (c.su * c.sv) * (1.0 * 1.0);  // eps * p.glq_scale() * q.glq_scale() integrals.rs:303-305
+
+    const uint32_t AS = g.NO * g.NPT;   // stride between the four arrays N, N', T, T'
+    const double* tPu = g.tabs + (size_t)c.tabPu * 4 * AS;
+    const double* tPv = g.tabs + (size_t)c.tabPv * 4 * AS;
+    const double* tQu = g.tabs + (size_t)c.tabQu * 4 * AS;
+    const double* tQv = g.tabs + (size_t)c.tabQv * 4 * AS;
     const bool single_chunk = chunk >= npts;
     double2* out = g.V + c.v_off;
     if (g.follows_sampler) {
@@ -187,16 +207,19 @@ __global__ void __launch_bounds__(NT, NT == K2_THREADS ? K2_MIN_CTAS : K2_SMALL_
         cudaTriggerProgrammaticLaunchCompletion();
     }
 
-    for (uint32_t round0 = 0; round0 < it.mt_count; round0 += NT) {
+    // thread slots: same-direction tiles, padding to a warp boundary, cross-direction tiles (plan_types.h item_slots)
+    const uint32_t gap = item_gap(it.n_same, it.mt_count), n_slots = it.mt_count + gap;
+    for (uint32_t round0 = 0; round0 < n_slots; round0 += NT) {
         // ---- my micro-tile of this round
-        const bool active = round0 + threadIdx.x < it.mt_count;
+        const uint32_t slot = round0 + threadIdx.x;
+        const bool active = slot < n_slots && !(slot >= it.n_same && slot < it.n_same + gap);
         uint32_t sub = 0, row0 = 0, col0 = 0, row_end = 0, col_end = 0, prow = 0, pcol = 0;
         if (active) {
-            uint32_t li = round0 + threadIdx.x, r = 0;
+            uint32_t li = slot < it.n_same ? slot : slot - gap, r = 0;
             while (li >= it.rcount[r]) { li -= it.rcount[r]; r++; }        // which of the item's tile ranges
             uint32_t rt, ct;
             decode_tile(sb, it.rbegin[r] + li, TP, sub, rt, ct);
-            row0 = sb.row0[sub] + rt * TP; col0 = sb.col0[sub] + ct * MT_Q;
+            row0 = sb.row0[sub] + rt * TP; col0 = sb.col0[sub] + ct * mt_width(sub);
             row_end = sb.row0[sub] + sb.rows[sub]; col_end = sb.col0[sub] + sb.cols[sub];
             prow = (sub >= 2 ? pad4(nUP) - nUP : 0) + row0;            // slab column of the canonical row index
             pcol = ((sub & 1) ? pad4(nUQ) - nUQ : 0) + col0;
@@ -204,11 +227,13 @@ __global__ void __launch_bounds__(NT, NT == K2_THREADS ? K2_MIN_CTAS : K2_SMALL_
         const bool same = (sub == 0 || sub == 3);
         const double ratio = sub == 0 ? ratio_uv : ratio_vu;
 
-        double solA[TP][MT_Q], solB[TP][MT_Q], inA[TP][MT_Q], inB[TP][MT_Q];
+        double sol[2][TP][MT_Q], in[2][TP][MT_Q];
 #pragma unroll
-        for (int r = 0; r < TP; r++)
+        for (int h = 0; h < 2; h++)
 #pragma unroll
-            for (int q = 0; q < MT_Q; q++) { solA[r][q] = 0.0; solB[r][q] = 0.0; inA[r][q] = 0.0; inB[r][q] = 0.0; }
+            for (int r = 0; r < TP; r++)
+#pragma unroll
+                for (int q = 0; q < MT_Q; q++) { sol[h][r][q] = 0.0; in[h][r][q] = 0.0; }
 
         for (uint32_t pt0 = 0; pt0 < npts; pt0 += chunk) {
             const uint32_t cn = min(chunk, npts - pt0);
@@ -268,34 +293,47 @@ __global__ void __launch_bounds__(NT, NT == K2_THREADS ? K2_MIN_CTAS : K2_SMALL_
                 const double* cq = s_CQ + pcol; const double* fq = s_FQ + pcol;
                 while (pl < cn) {
                     const uint32_t run = min(cn - pl, nv - n);
-                    if (same) contract_run<true, TP>(cp, cq, fp, fq, strideP, strideQ, s_vw + n, run, ratio, maxdet, inA, inB);
-                    else contract_run<false, TP>(cp, cq, fp, fq, strideP, strideQ, s_vw + n, run, ratio, maxdet, inA, inB);
+                    if (same) contract_run<true, TP>(cp, cq, fp, fq, strideP, strideQ, s_vw + n, run, ratio, maxdet, in);
+                    else contract_run<false, TP>(cp, cq, fp, fq, strideP, strideQ, s_vw + n, run, ratio, maxdet, in);
                     pl += run; n += run;
                     if (n == nv) {   // end of the inner (v) loop: solution += inner_solution * u_w (glq.rs:29)
                         const double uw = s_uw[m];
 #pragma unroll
-                        for (int r = 0; r < TP; r++)
+                        for (int h = 0; h < 2; h++)
 #pragma unroll
-                            for (int q = 0; q < MT_Q; q++) {
-                                solA[r][q] = solA[r][q] + inA[r][q] * uw; inA[r][q] = 0.0;
-                                if (same) { solB[r][q] = solB[r][q] + inB[r][q] * uw; inB[r][q] = 0.0; }
-                            }
+                            for (int r = 0; r < TP; r++)
+#pragma unroll
+                                for (int q = 0; q < MT_Q; q++) { sol[h][r][q] = sol[h][r][q] + in[h][r][q] * uw; in[h][r][q] = 0.0; }
                         n = 0; m++;
                     }
                 }
             }
         }
         if (active) {
+            if (same) {
 #pragma unroll
-            for (int r = 0; r < TP; r++) {
-                const uint32_t a = row0 + r;
-                if (a >= row_end) continue;
+                for (int r = 0; r < TP; r++) {
+                    const uint32_t a = row0 + r;
+                    if (a >= row_end) continue;
 #pragma unroll
-                for (int q = 0; q < MT_Q; q++) {
-                    const uint32_t b = col0 + q;
-                    if (b >= col_end) continue;
-                    // cross-direction mass entries: every integrand term is a signed zero, the quadrature returns +0.0 (integrals.rs:318-339)
-                    out[(size_t)a * nQ + b] = make_double2(coefA * solA[r][q], coefB * (same ? solB[r][q] : 0.0));
+                    for (int q = 0; q < MT_Q; q++) {
+                        const uint32_t b = col0 + q;
+                        if (b >= col_end) continue;
+                        out[(size_t)a * nQ + b] = make_double2(coefA * sol[0][r][q], coefB * sol[1][r][q]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < TP; r++) {
+                    const uint32_t a = row0 + r;
+                    if (a >= row_end) continue;
+#pragma unroll
+                    for (int q = 0; q < MT_QX; q++) {
+                        const uint32_t b = col0 + q;
+                        if (b >= col_end) continue;
+                        // cross-direction mass entries: every integrand term is a signed zero, the quadrature returns +0.0 (integrals.rs:318-339)
+                        out[(size_t)a * nQ + b] = make_double2(coefA * sol[q >> 1][r][q & 1], coefB * 0.0);
+                    }
                 }
             }
         }
@@ -337,9 +375,9 @@ static cudaError_t launch_k2_part(const Plan& P, const WorkItem* d_items, uint32
     // chunk from its class's row width, the launch only fixes the budget: `soft` unless the widest class cannot even stage one
     // quadrature row in it
     const size_t per_pt = (size_t)max_stride * 2 * sizeof(double);
-    const size_t fixed = 256 * sizeof(double);
     const size_t hard = (size_t)P.max_smem_optin - 1024;
     const uint32_t npts = nu * nv;
+    const size_t fixed = 256 * sizeof(double);
     size_t smem = std::min(soft, fixed + (size_t)npts * per_pt);
     if ((smem - fixed) / per_pt < std::min<uint32_t>(npts, nv)) smem = std::min(hard, fixed + (size_t)std::min<uint32_t>(npts, nv) * per_pt);
     if ((smem - fixed) / per_pt == 0) return cudaErrorInvalidConfiguration;

@@ -87,9 +87,14 @@ int elem_geometry(const fem2d_domain_view* v, std::vector<double>& dx, std::vect
 WorkItem make_item(const HostPlan& P, uint32_t cls, const std::vector<std::pair<uint32_t, uint32_t>>& ranges, const uint32_t (*cols)[2][2]) {
     WorkItem it; std::memset(&it, 0, sizeof(it));
     it.cls = cls; it.n_ranges = (uint32_t)ranges.size();
-    for (size_t k = 0; k < ranges.size(); k++) { it.rbegin[k] = ranges[k].first; it.rcount[k] = (uint16_t)ranges[k].second; it.mt_count += ranges[k].second; }
     const ClassDesc& c = P.classes[cls];
     const ListDesc* L[2] = {&P.lists[c.listP], &P.lists[c.listQ]};
+    // ranges are ascending in the class-local numbering, which puts the same-direction tiles first
+    const uint32_t same_end = mt_same_count(make_subblocks(L[0]->n, L[0]->nU, L[1]->n, L[1]->nU, c.local, P.tile_p));
+    for (size_t k = 0; k < ranges.size(); k++) {
+        it.rbegin[k] = ranges[k].first; it.rcount[k] = (uint16_t)ranges[k].second; it.mt_count += ranges[k].second;
+        if (ranges[k].first < same_end) it.n_same += std::min(ranges[k].second, same_end - ranges[k].first);
+    }
     for (int side = 0; side < 2; side++) {
         const uint32_t nU = L[side]->nU, nV = L[side]->n - nU, padU = slab_pad4(nU);
         uint32_t ub = 0, ue = nU, vb = 0, ve = nV;                      // function ranges inside each direction group
@@ -309,6 +314,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
                 c.dxP = key.g[0]; c.dyP = key.g[1]; c.dxQ = key.g[2]; c.dyQ = key.g[3];
                 c.su = su; c.sv = sv; c.eps = key.g[8]; c.mu = key.g[9];
                 c.listP = key.listP; c.listQ = key.listQ; c.local = key.local;
+                c.lp = P.lists[c.listP]; c.lq = P.lists[c.listQ];
                 c.tabPu = local ? 0u : table_id(su, ou, 0, 0);
                 c.tabPv = local ? 1u : table_id(sv, ov, 1, 0);
                 c.tabQu = 0; c.tabQv = 1;
@@ -363,8 +369,21 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
     }
     for (uint32_t c : cls_order) {
         const uint32_t n_mt = P.classes[c].n_mt;
-        const uint32_t n_items = (n_mt + cap - 1) / cap;
-        for (uint32_t k = 0; k < n_items; k++) {   // equal shares
+        const ClassDesc& cd = P.classes[c];
+        const ListDesc& LP = P.lists[cd.listP]; const ListDesc& LQ = P.lists[cd.listQ];
+        const uint32_t same_end = mt_same_count(make_subblocks(LP.n, LP.nU, LQ.n, LQ.nU, cd.local, P.tile_p));
+        // equal shares; one more item if the warp alignment of the cross-direction tiles would push a share past the cap
+        uint32_t n_items = (n_mt + cap - 1) / cap;
+        for (;; n_items++) {
+            bool fits = true;
+            for (uint32_t k = 0; k < n_items && fits; k++) {
+                const uint32_t b = (uint32_t)((uint64_t)n_mt * k / n_items), e = (uint32_t)((uint64_t)n_mt * (k + 1) / n_items);
+                const uint32_t ns = b < same_end ? std::min(e, same_end) - b : 0u;
+                fits = item_slots(ns, e - b) <= cap;
+            }
+            if (fits || n_items >= n_mt) break;
+        }
+        for (uint32_t k = 0; k < n_items; k++) {
             const uint32_t b = (uint32_t)((uint64_t)n_mt * k / n_items), e = (uint32_t)((uint64_t)n_mt * (k + 1) / n_items);
             if (e > b) P.items.push_back(make_item(P, c, {{b, e - b}}, nullptr));
         }

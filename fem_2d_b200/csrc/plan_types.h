@@ -17,7 +17,12 @@ namespace fem2d {
 // Micro-tile of the exact integrator: TP x MT_Q pairs per thread.  TP = 4 is the throughput shape (FP64-issue bound, 16
 // independent accumulation chains per thread); TP = 1 is the latency shape used for small / heavily deduplicated plans,
 // where 4x more threads with 4x shorter instruction streams fill the machine instead.  The planner picks (HostPlan::tile_p).
-constexpr int MT_Q = 2;            // micro-tile: Q functions (cols) per thread
+// Same-direction pairs (U-U, V-V) accumulate A and B (8 FP64 operations per pair and point); cross-direction pairs (U-V, V-U)
+// accumulate A only (3 operations; their B is an exact zero), so a cross-direction tile is twice as wide: TP x MT_QX pairs use
+// the same accumulator registers (TP x 4 x {sol, inner}) and cost 48 instead of 64 operations per point at TP = 4 -- warps of
+// either kind then take about the same time between two barriers.
+constexpr int MT_Q = 2;            // same-direction micro-tile: Q functions (cols) per thread
+constexpr int MT_QX = 4;           // cross-direction micro-tile (both shapes; 1 x 2 at TP = 1 measured 16 % slower on cfg 2, equal on cfg 3)
 constexpr int K2_THREADS = 256;
 constexpr int K2_MIN_CTAS = 2;     // CTAs per SM the integrator is compiled for
 constexpr int K2_ROUNDS = 2;    // a work item covers up to K2_ROUNDS * K2_THREADS micro-tiles of one class (slabs staged once)
@@ -29,6 +34,13 @@ constexpr int K2_SMALL_CTAS = 8;
 constexpr int K2_SMALL_TILES = 2 * K2_SMALL_THREADS;
 constexpr int K2_SMALL_STRIDE = 64;   // ... and a slab row of at most this many functions (1 KB per quadrature point)
 
+struct ListDesc {
+    uint32_t off;   // into spec_i / spec_j
+    uint32_t n;     // number of functions
+    uint32_t nU;    // the first nU are U-directed, the rest V-directed
+    uint32_t pad;
+};
+
 struct ClassDesc {
     double dxP, dyP, dxQ, dyQ;   // dx_du, dy_dv (element.rs:46-47) of P's Elem and of Q's Elem
     double su, sv;               // P's para_scale (basis.rs:419); (1,1) for local blocks. Q's is always (1,1).
@@ -39,13 +51,7 @@ struct ClassDesc {
     uint32_t local;              // 1: d == e (symmetric block, only a <= b is consumed)
     uint32_t n_mt;               // micro-tiles in this class
     uint32_t gramU, gramV;       // ids of the (tabPu,tabQu) / (tabPv,tabQv) 1-D Gram sets (re-ordered modes only)
-};
-
-struct ListDesc {
-    uint32_t off;   // into spec_i / spec_j
-    uint32_t n;     // number of functions
-    uint32_t nU;    // the first nU are U-directed, the rest V-directed
-    uint32_t pad;
+    ListDesc lp, lq;             // copies of lists[listP], lists[listQ]: one dependent load less in the integrator's prologue
 };
 
 struct TableDesc {
@@ -66,7 +72,9 @@ struct WorkItem {
     uint32_t cls;
     uint32_t mt_count;                    // tiles of all ranges together, <= K2_ROUNDS * K2_THREADS
     uint32_t n_ranges;
-    uint32_t pad;
+    // The first n_same tiles (in range order) are same-direction tiles, the rest cross-direction ones (the class-local numbering
+    // puts U-U and V-V first).  Thread slots: the cross-direction tiles start on a warp boundary, so no warp runs both code paths.
+    uint32_t n_same;
     uint32_t rbegin[ITEM_MAX_RANGES];     // first micro-tile of each range (class-local numbering)
     uint16_t rcount[ITEM_MAX_RANGES];
     uint16_t stage[2][2][2];              // [side: P, Q][direction group: U, V][begin, end): slab columns to stage
@@ -80,8 +88,9 @@ struct BlockDesc {
 };
 
 // ---- micro-tile enumeration (host + device) --------------------------------------------------------------------------------
-// Sub-blocks in order: 0 = U rows x U cols, 1 = U x V, 2 = V x U (non-local only), 3 = V x V.  Local classes use the
-// upper triangle (in micro-tile granularity) of the two same-direction sub-blocks.
+// Sub-blocks: 0 = U rows x U cols, 1 = U x V, 2 = V x U (non-local only), 3 = V x V.  Class-local tile numbering: the
+// same-direction sub-blocks first (0, then 3), then the cross-direction ones (1, then 2).  Local classes use the upper
+// triangle (in micro-tile granularity) of the two same-direction sub-blocks.
 struct SubBlocks {
     uint32_t cnt[4];
     uint32_t rows[4], cols[4];     // extents
@@ -94,6 +103,8 @@ struct SubBlocks {
 #define FEM2D_HD
 #endif
 FEM2D_HD inline uint32_t mt_div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+FEM2D_HD inline uint32_t mt_sub_at(uint32_t k) { return k == 0 ? 0u : k == 1 ? 3u : k == 2 ? 1u : 2u; }   // k-th sub-block in numbering order
+FEM2D_HD inline uint32_t mt_width(uint32_t sub) { return (sub == 1 || sub == 2) ? (uint32_t)MT_QX : (uint32_t)MT_Q; }
 FEM2D_HD inline uint32_t mt_tri_count(uint32_t n, uint32_t tp) {
     const uint32_t nrt = mt_div_up(n, tp), nct = mt_div_up(n, MT_Q);
     uint32_t c = 0;
@@ -105,26 +116,44 @@ FEM2D_HD inline SubBlocks make_subblocks(uint32_t nP, uint32_t nUP, uint32_t nQ,
     const uint32_t nVP = nP - nUP, nVQ = nQ - nUQ;
     const uint32_t R[4] = {nUP, nUP, nVP, nVP}, Cc[4] = {nUQ, nVQ, nUQ, nVQ};
     const uint32_t r0[4] = {0, 0, nUP, nUP}, c0[4] = {0, nUQ, 0, nUQ};
-    for (int k = 0; k < 4; k++) {
+    for (uint32_t k = 0; k < 4; k++) {
         s.rows[k] = R[k]; s.cols[k] = Cc[k]; s.row0[k] = r0[k]; s.col0[k] = c0[k];
         s.tri[k] = (local && (k == 0 || k == 3)) ? 1u : 0u;
         if (local && k == 2) s.cnt[k] = 0;
         else if (s.tri[k]) s.cnt[k] = mt_tri_count(R[k], tp);
-        else s.cnt[k] = mt_div_up(R[k], tp) * mt_div_up(Cc[k], MT_Q);
+        else s.cnt[k] = mt_div_up(R[k], tp) * mt_div_up(Cc[k], mt_width(k));
     }
     return s;
 }
+FEM2D_HD inline uint32_t mt_same_count(const SubBlocks& sb) { return sb.cnt[0] + sb.cnt[3]; }   // tiles [0, this) are same-direction
 
 // micro-tile index (class-local) -> sub-block, row tile, column tile
 FEM2D_HD inline void decode_tile(const SubBlocks& sb, uint32_t idx, uint32_t tp, uint32_t& sub, uint32_t& rt, uint32_t& ct) {
-    sub = 0;
-    while (sub < 3 && idx >= sb.cnt[sub]) { idx -= sb.cnt[sub]; sub++; }
-    const uint32_t nct = mt_div_up(sb.cols[sub], MT_Q);
+    uint32_t k = 0;
+    sub = mt_sub_at(0);
+    while (k < 3 && idx >= sb.cnt[sub]) { idx -= sb.cnt[sub]; k++; sub = mt_sub_at(k); }
+    const uint32_t nct = mt_div_up(sb.cols[sub], mt_width(sub));
     if (sb.tri[sub]) {
         rt = 0;
         for (;;) { const uint32_t lo = rt * tp / MT_Q; const uint32_t cnt = nct > lo ? nct - lo : 0; if (idx < cnt) { ct = lo + idx; break; } idx -= cnt; rt++; }
     } else { rt = idx / nct; ct = idx - rt * nct; }
 }
+// inverse: class-local index of the tile that holds the pair (a, b) (canonical function indices)
+FEM2D_HD inline uint32_t encode_tile(const SubBlocks& sb, uint32_t a, uint32_t b, uint32_t nUP, uint32_t nUQ, uint32_t tp) {
+    const uint32_t sub = (a < nUP ? 0u : 2u) + (b < nUQ ? 0u : 1u);
+    uint32_t idx = 0;
+    for (uint32_t k = 0; k < 4 && mt_sub_at(k) != sub; k++) idx += sb.cnt[mt_sub_at(k)];
+    const uint32_t w = mt_width(sub);
+    const uint32_t rt = (a - sb.row0[sub]) / tp, ct = (b - sb.col0[sub]) / w, nct = mt_div_up(sb.cols[sub], w);
+    if (sb.tri[sub]) {
+        for (uint32_t q = 0; q < rt; q++) { const uint32_t l0 = q * tp / MT_Q; if (nct > l0) idx += nct - l0; }
+        idx += ct - rt * tp / MT_Q;
+    } else idx += rt * nct + ct;
+    return idx;
+}
+// thread slots of a work item: its same-direction tiles, padding up to a warp boundary, its cross-direction tiles
+FEM2D_HD inline uint32_t item_gap(uint32_t n_same, uint32_t mt_count) { return (n_same == 0 || n_same == mt_count) ? 0u : ((32u - (n_same & 31u)) & 31u); }
+FEM2D_HD inline uint32_t item_slots(uint32_t n_same, uint32_t mt_count) { return mt_count + item_gap(n_same, mt_count); }
 FEM2D_HD inline uint32_t slab_pad4(uint32_t x) { return (x + 3u) & ~3u; }
 
 }  // namespace fem2d
