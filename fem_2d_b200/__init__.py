@@ -72,7 +72,7 @@ class _View(C.Structure):
 
 # Every symbol declared in include/fem2d.h and include/fem2d_host.h (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "fem2d_symbolic", "fem2d_plan_free", "fem2d_plan_info", "fem2d_plan_source_map_info", "fem2d_plan_row_offsets", "fem2d_plan_pattern_transfer_info", "fem2d_plan_pattern", "fem2d_plan_pattern_device",
+    "fem2d_symbolic", "fem2d_plan_free", "fem2d_plan_info", "fem2d_plan_check_work_items", "fem2d_plan_source_map_info", "fem2d_plan_row_offsets", "fem2d_plan_pattern_transfer_info", "fem2d_plan_pattern", "fem2d_plan_pattern_device",
     "fem2d_assemble_device", "fem2d_assemble_device_ranges", "fem2d_plan_row_blocks_split", "fem2d_assemble_ranges", "fem2d_assemble", "fem2d_galerkin_sample_gep_hcurl", "fem2d_plan_row_blocks",
     "fem2d_plan_last_timing", "fem2d_plan_timing", "fem2d_plan_set_phase_timing", "fem2d_assemble_range", "fem2d_host_alloc", "fem2d_host_free", "fem2d_xy_fields", "fem2d_fp64_peak",
     "fem2d_device_count", "fem2d_status_string", "fem2d_last_error", "fem2d_version",
@@ -596,6 +596,12 @@ class Plan:
         _ck(_L.fem2d_plan_info(self._h, info))
         self.info = {k: int(info[i]) for i, k in enumerate(INFO_KEYS)}
         return self.info
+
+    def check_work_items(self) -> dict:
+        """fem2d_plan_check_work_items: self-check of the exact integrator's micro-tile / work-item decomposition."""
+        out = (C.c_uint64 * 4)()
+        _ck(_L.fem2d_plan_check_work_items(self._h, out))
+        return {"tiles": int(out[0]), "same_tiles": int(out[1]), "slots": int(out[2]), "violations": int(out[3])}
 
     def source_map_info(self) -> dict:
         """fem2d_plan_source_map_info: size of the packed source map the scatter kernel reads."""

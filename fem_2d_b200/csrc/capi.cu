@@ -175,6 +175,73 @@ int fem2d_plan_info(const fem2d_plan* plan, uint64_t info[16]) {
     return FEM2D_OK;
 }
 
+int fem2d_plan_check_work_items(const fem2d_plan* plan, uint64_t out[4]) {
+    if (!plan || !out) return fail(FEM2D_ERR_BAD_ARGUMENT, "null argument");
+    using namespace fem2d;
+    const HostPlan& H = plan->p.host;
+    const uint32_t tp = H.tile_p;
+    uint64_t n_tiles = 0, n_same = 0, n_slots = 0, bad = 0;
+    std::vector<std::vector<uint8_t>> seen(H.classes.size());
+    for (size_t ci = 0; ci < H.classes.size(); ci++) {
+        const ClassDesc& c = H.classes[ci];
+        const ListDesc& LP = H.lists[c.listP]; const ListDesc& LQ = H.lists[c.listQ];
+        if (std::memcmp(&c.lp, &LP, sizeof(ListDesc)) || std::memcmp(&c.lq, &LQ, sizeof(ListDesc))) bad++;
+        const SubBlocks sb = make_subblocks(LP.n, LP.nU, LQ.n, LQ.nU, c.local, tp);
+        const uint32_t n_mt = sb.cnt[0] + sb.cnt[1] + sb.cnt[2] + sb.cnt[3];
+        if (n_mt != c.n_mt) bad++;
+        n_tiles += n_mt; n_same += mt_same_count(sb);
+        seen[ci].assign(n_mt, 0);
+        // every consumed pair maps to a tile whose decoded extents contain it, and the kind split is where mt_same_count says
+        std::vector<uint32_t> cover(n_mt, 0);
+        for (uint32_t a = 0; a < LP.n; a++)
+            for (uint32_t b = 0; b < LQ.n; b++) {
+                const bool u_a = a < LP.nU, u_b = b < LQ.nU;
+                if (c.local && ((u_a == u_b && a > b) || (!u_a && u_b))) continue;   // lower triangle of a symmetric block: never read
+                const uint32_t idx = encode_tile(sb, a, b, LP.nU, LQ.nU, tp);
+                if (idx >= n_mt) { bad++; continue; }
+                uint32_t sub, rt, ct;
+                decode_tile(sb, idx, tp, sub, rt, ct);
+                const uint32_t r0 = sb.row0[sub] + rt * tp, c0 = sb.col0[sub] + ct * mt_width(sub);
+                if (a < r0 || a >= r0 + tp || b < c0 || b >= c0 + mt_width(sub)) bad++;
+                if ((sub == 0 || sub == 3) != (idx < mt_same_count(sb))) bad++;
+                if (sub != (u_a ? 0u : 2u) + (u_b ? 0u : 1u)) bad++;
+                cover[idx]++;
+            }
+        for (uint32_t t = 0; t < n_mt; t++) if (cover[t] == 0) bad++;   // no empty tiles in the numbering
+    }
+    for (const WorkItem& it : H.items) {
+        if (it.cls >= H.classes.size() || it.n_ranges == 0 || it.n_ranges > (uint32_t)ITEM_MAX_RANGES) { bad++; continue; }
+        const ClassDesc& c = H.classes[it.cls];
+        const ListDesc& LP = H.lists[c.listP]; const ListDesc& LQ = H.lists[c.listQ];
+        const SubBlocks sb = make_subblocks(LP.n, LP.nU, LQ.n, LQ.nU, c.local, tp);
+        const uint32_t same_end = mt_same_count(sb), padUP = slab_pad4(LP.nU), padUQ = slab_pad4(LQ.nU);
+        uint32_t cnt = 0, ns = 0, prev_end = 0;
+        for (uint32_t r = 0; r < it.n_ranges; r++) {
+            if (it.rbegin[r] < prev_end) bad++;                                    // ranges ascend, so same-direction tiles come first
+            for (uint32_t t = it.rbegin[r]; t < it.rbegin[r] + it.rcount[r]; t++) {
+                if (t >= seen[it.cls].size()) { bad++; continue; }
+                seen[it.cls][t]++;
+                ns += t < same_end;
+                uint32_t sub, rt, ct;
+                decode_tile(sb, t, tp, sub, rt, ct);
+                // slab columns the tile reads (full tile width: the padding columns must be staged too, as zeros)
+                const uint32_t side_q = c.local ? 0u : 1u;
+                const uint32_t pr0 = (sub >= 2 ? padUP : 0u) + rt * tp, pr1 = pr0 + tp;
+                const uint32_t qc0 = ((sub & 1) ? padUQ : 0u) + ct * mt_width(sub), qc1 = qc0 + mt_width(sub);
+                const uint16_t* sp = it.stage[0][sub >= 2]; const uint16_t* sq = it.stage[side_q][sub & 1];
+                if (pr0 < sp[0] || std::min(pr1, (sub >= 2 ? padUP + slab_pad4(LP.n - LP.nU) : padUP)) > sp[1]) bad++;
+                if (qc0 < sq[0] || std::min(qc1, ((sub & 1) ? padUQ + slab_pad4(LQ.n - LQ.nU) : padUQ)) > sq[1]) bad++;
+            }
+            cnt += it.rcount[r]; prev_end = it.rbegin[r] + it.rcount[r];
+        }
+        if (cnt != it.mt_count || ns != it.n_same) bad++;
+        n_slots += item_slots(it.n_same, it.mt_count);
+    }
+    for (auto& s : seen) for (uint8_t k : s) if (k != 1) bad++;
+    out[0] = n_tiles; out[1] = n_same; out[2] = n_slots; out[3] = bad;
+    return FEM2D_OK;
+}
+
 int fem2d_plan_source_map_info(const fem2d_plan* plan, uint64_t info[4]) {
     if (!plan || !info) return fail(FEM2D_ERR_BAD_ARGUMENT, "null argument");
     const fem2d::Plan& p = plan->p;

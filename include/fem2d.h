@@ -92,6 +92,12 @@ void fem2d_plan_free(fem2d_plan* plan);
  * 10 n_lists, 11 n_extra (2nd+ contributions), 12 / 13 wall microseconds of the host / device halves of the symbolic phase,
  * 14 micro-tile height chosen for the exact integrator (4: throughput shape, 1: latency shape for small plans) */
 int fem2d_plan_info(const fem2d_plan* plan, uint64_t info[16]);
+/* Self-check of the exact integrator's work decomposition (host logic, works on host-only plans): every pair the pattern reads
+ * (all (a, b) of a local-desc block, a <= b of a local-local block; galerkin.rs:91-127,138-178) lies in exactly one micro-tile of
+ * its class, the tile numbering is invertible, every tile of every class is in exactly one work item, same-direction tiles precede
+ * cross-direction ones in every item, and the staged function ranges of an item cover the functions its tiles read.
+ * out[]: 0 tiles, 1 same-direction tiles, 2 thread slots (tiles + warp-alignment gaps), 3 violations found (0 = consistent). */
+int fem2d_plan_check_work_items(const fem2d_plan* plan, uint64_t out[4]);
 /* Size of the per-slot source map the scatter kernel reads.  The map is packed per chunk of slots as 16-bit offsets from the
  * chunk's smallest source; chunks that do not fit keep plain 32-bit indices.  info[]: 0 chunks in plain form, 1 slots per chunk,
  * 2 bytes of the map one full scatter reads, 3 bytes of an all-plain map (4 per slot).  Device plans only. */

@@ -83,6 +83,32 @@ def test_host_symbolic_pattern_equals_oracle_key_set(name):
     assert plan.info["n_pairs"] == n_pairs
 
 
+@pytest.mark.parametrize("name", sorted(recipes.RECIPES))
+def test_work_items_cover_every_pair_once(name):
+    """The exact integrator's decomposition (plan_types.h): every pair the pattern reads lies in exactly one micro-tile
+    (4 x 2 / 1 x 2 same-direction, 4 x 4 / 1 x 4 cross-direction), every tile in exactly one work item, same-direction tiles
+    first, staged function ranges cover what the tiles read -- on every recipe, both dedupe settings (checked on the host)."""
+    _, mf = recipes.build_pair(name)
+    df = F.Domain.from_mesh(mf)
+    for dedupe in (True, False):
+        plan = F.Plan(df.view(), device=-1, dedupe=dedupe)
+        chk = plan.check_work_items()
+        assert chk["violations"] == 0, chk
+        assert 0 < chk["same_tiles"] < chk["tiles"] <= chk["slots"] < chk["tiles"] + 32 * plan.info["n_work_items"]
+
+
+def test_work_items_of_the_throughput_shape():
+    """A plan large enough for the 4-row tile shape (cfg 3 at 3 levels, dedupe off): closed-form tile counts of an interior leaf
+    (42 U + 42 V functions: 121 + 121 same-direction tiles of 4 x 2 in the two triangles, 11 x 11 cross-direction tiles of 4 x 4)."""
+    df = F.Domain.from_mesh(recipes.mesh_cfg3(recipes.api("product"), levels=3, order=6))
+    plan = F.Plan(df.view(), device=-1, dedupe=False)
+    assert plan.info["tile_p"] == 4
+    chk = plan.check_work_items()
+    assert chk["violations"] == 0, chk
+    n_int = 14 * 14                                            # leaves with four interior edges on the 16 x 16 leaf grid
+    assert chk["tiles"] > n_int * 363 and chk["same_tiles"] > n_int * 242
+
+
 def test_baseline_config_sizes():
     """BASELINE.md section 3 table (cfg 1, 5 fully; cfg 3 closed form at a small level)."""
     for name, (elems, dofs, pairs, nnz) in {"readme": (28, 600, 12808 + 1152, 13596), "slepc": (27, 624, 12868 + 3328, 15512)}.items():
