@@ -346,6 +346,42 @@ def run_ours(args):
             except Exception as ex:  # pragma: no cover
                 others[wl] = {"error": str(ex)}
         extra["other_configs"] = others
+        # Q-scaling: the headline mesh with the reference's default quadrature (`glq_grid_dim = None` ->
+        # default_ngq(order) points per side, basis.rs:172-177) and cfg 4 with the second basis space (HierMaxOrtho)
+        series = {}
+        try:
+            ng = int(F.default_ngq(max(domain.mesh.max_expansion_orders())))
+            gq = (F.gauss_quadrature_points(ng), F.gauss_quadrature_points(ng))
+            for _ in range(3):
+                plan.assemble_device(gq, d_a.data_ptr(), d_b.data_ptr(), mode=mode, stream=stream.cuda_stream)
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for _ in range(20):
+                plan.assemble_device(gq, d_a.data_ptr(), d_b.data_ptr(), mode=mode, stream=stream.cuda_stream)
+            g1.record(stream)
+            torch.cuda.synchronize()
+            ms = g0.elapsed_time(g1) / 20
+            series[workload + "_glq_default"] = {"glq": [ng, ng], "ms_per_step": ms, "value": 2.0 * nnz / (ms * 1e-3), "unit": "nnz/s"}
+            dom = build_product_domain("cfg4")
+            g = WORKLOADS["cfg4"]["glq"]
+            gq = (F.gauss_quadrature_points(g), F.gauss_quadrature_points(g))
+            pl = F.Plan(dom.view(), device=local_rank, dedupe=bool(args.dedupe))
+            ta = torch.empty(pl.nnz, dtype=torch.float64, device=dev); tb = torch.empty_like(ta)
+            for _ in range(3):
+                pl.assemble_device(gq, ta.data_ptr(), tb.data_ptr(), basis=F.HierMaxOrtho, mode=mode, stream=stream.cuda_stream)
+            torch.cuda.synchronize()
+            g0.record(stream)
+            for _ in range(20):
+                pl.assemble_device(gq, ta.data_ptr(), tb.data_ptr(), basis=F.HierMaxOrtho, mode=mode, stream=stream.cuda_stream)
+            g1.record(stream)
+            torch.cuda.synchronize()
+            ms = g0.elapsed_time(g1) / 20
+            series["cfg4_hier_max_ortho"] = {"glq": [g, g], "ms_per_step": ms, "value": 2.0 * pl.nnz / (ms * 1e-3), "unit": "nnz/s"}
+            del pl, ta, tb
+        except Exception as ex:  # pragma: no cover
+            series["error"] = str(ex)
+        extra["other_series"] = series
 
     # ---- end to end through the reference-facing call: host Domain view -> host CSR arrays ------------------------------------
     e2e = None

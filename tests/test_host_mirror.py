@@ -97,6 +97,19 @@ def test_work_items_cover_every_pair_once(name):
         assert 0 < chk["same_tiles"] < chk["tiles"] <= chk["slots"] < chk["tiles"] + 32 * plan.info["n_work_items"]
 
 
+def test_work_items_of_the_baseline_configs():
+    """BASELINE.json configs[1] (order 8, 144 functions per Elem) and configs[3] (anisotropic, p in [2, 10], local-desc blocks of
+    unequal lists): the decomposition is consistent in both tile shapes."""
+    import bench
+    for wl, tile_p in (("cfg2", 1), ("cfg4", 4)):
+        df = bench.build_product_domain(wl)
+        for dedupe in (True, False):
+            plan = F.Plan(df.view(), device=-1, dedupe=dedupe)
+            assert not dedupe or plan.info["tile_p"] == tile_p
+            chk = plan.check_work_items()
+            assert chk["violations"] == 0, (wl, dedupe, chk)
+
+
 def test_work_items_of_the_throughput_shape():
     """A plan large enough for the 4-row tile shape (cfg 3 at 3 levels, dedupe off): closed-form tile counts of an interior leaf
     (42 U + 42 V functions: 121 + 121 same-direction tiles of 4 x 2 in the two triangles, 11 x 11 cross-direction tiles of 4 x 4)."""
