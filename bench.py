@@ -379,6 +379,31 @@ def run_ours(args):
             ms = g0.elapsed_time(g1) / 20
             series["cfg4_hier_max_ortho"] = {"glq": [g, g], "ms_per_step": ms, "value": 2.0 * pl.nnz / (ms * 1e-3), "unit": "nnz/s"}
             del pl, ta, tb
+            # UniformFieldSpace::xy_fields (fields.rs:63-127) on the headline mesh, [16,16] points per leaf Elem,
+            # host solution vector in, host field arrays out (wall clock around the C-ABI call)
+            import ctypes as _C
+            import numpy as _np
+            dens, cap = 16, domain.mesh.num_elems
+            sol = _np.cos(_np.arange(domain.num_dofs) * 0.37) + 0.25
+            ids = _np.zeros(cap, dtype=_np.uint32)
+            fx = _np.zeros((cap, dens, dens)); fy = _np.zeros((cap, dens, dens))
+            n_out = _C.c_uint64()
+            ptr = lambda arr, t: arr.ctypes.data_as(_C.POINTER(t))
+
+            def fields_call():
+                st = F._L.fem2d_xy_fields(_C.byref(view.c), int(local_rank), F.HierPoly.kind, _C.c_uint32(dens), ptr(sol, _C.c_double), _C.c_uint64(cap),
+                                          _C.byref(n_out), ptr(ids, _C.c_uint32), ptr(fx, _C.c_double), ptr(fy, _C.c_double))
+                if st != 0:
+                    raise RuntimeError(F._L.fem2d_last_error().decode())
+
+            fields_call()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fields_call()
+            ms = (time.perf_counter() - t0) / 3 * 1e3
+            series[workload + "_xy_fields_16x16"] = {"leaf_elems": int(n_out.value), "ms_per_call_host_to_host": ms,
+                                                     "points_per_s": n_out.value * dens * dens / (ms * 1e-3),
+                                                     "note": "wall clock around fem2d_xy_fields: pageable host solution in, pageable host field arrays out"}
         except Exception as ex:  # pragma: no cover
             series["error"] = str(ex)
         extra["other_series"] = series
