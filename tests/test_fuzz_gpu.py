@@ -40,3 +40,23 @@ def test_random_hp_mesh_bit_identical(seed, mesh, t_levels, rounds, pmin, pmax):
         hr, hc = hp.pattern()
         assert np.array_equal(hr, rows) and np.array_equal(hc, cols)
         assert np.array_equal(hp.row_offsets(), plan.row_offsets())
+
+
+@pytest.mark.parametrize("basis", [0, 1])
+def test_throughput_shape_with_inter_layer_blocks_bit_identical(basis):
+    """The 4-row tile shape (4 x 2 same-direction, 4 x 4 cross-direction tiles, 256- and 64-thread CTAs) on a mesh that has
+    local-desc blocks of unequal BasisSpec lists (all four sub-blocks incl. V x U, RBS-scaled tables): the cfg-4 recipe at 3 T-levels
+    (14 611 DoFs, 886 653 pairs, 622 blocks) against the oracle, bit for bit, unequal GLQ dims so that chunks end inside quadrature rows."""
+    def build(api):
+        return recipes.mesh_cfg4(api, t_levels=3, rounds=3, pmin=2, pmax=10)
+    do, df = O.Domain.from_mesh(build(recipes.api("oracle"))), F.Domain.from_mesh(build(recipes.api("product")))
+    glq = (F.gauss_quadrature_points(6), F.gauss_quadrature_points(7))
+    ref = O.galerkin_sample_gep_hcurl(do, glq=glq, basis=basis)
+    for dedupe in (True, False):
+        plan = F.Plan(df.view(), device=0, dedupe=dedupe)
+        assert plan.info["tile_p"] == 4 and plan.info["n_pairs"] == 886653
+        assert plan.check_work_items()["violations"] == 0
+        rows, cols, a, b = plan.assemble(glq, basis=F.HierPoly if basis == 0 else F.HierMaxOrtho)
+        assert np.array_equal(rows, ref.rows) and np.array_equal(cols, ref.cols)
+        assert np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(ref.a).view(np.uint64)), f"A differs (dedupe={dedupe})"
+        assert np.array_equal(np.ascontiguousarray(b).view(np.uint64), np.ascontiguousarray(ref.b).view(np.uint64)), f"B differs (dedupe={dedupe})"
