@@ -400,19 +400,22 @@ static cudaError_t launch_k2_part(const Plan& P, const WorkItem* d_items, uint32
 }
 
 // Items are ordered by size (largest first); the first n_big of them run in K2_THREADS-wide CTAs, the rest in K2_SMALL_THREADS-wide
-// ones.  Both launches carry the programmatic-dependent-launch attribute: the small CTAs start filling SMs as soon as the last
-// big CTA has started, and wait for the big grid's completion before they exit, so that whoever waits on the second grid (the
-// scatter kernel) transitively waits on the first.
+// ones.  The small-item grid goes first: its CTAs (8 per SM) fill the whole machine for about one wave, and the big-item CTAs move
+// in as they drain (measured on cfg 4: 0.464 -> 0.452 ms against big-first, where the small grid ran in the big grid's tail at low
+// occupancy).  Both launches carry the programmatic-dependent-launch attribute: the second grid starts once every CTA of the first has
+// passed its wait for the sampler, runs alongside it and waits for its completion before exiting, so that whoever waits on the
+// second grid (the scatter kernel) transitively waits on the first.
 cudaError_t launch_k2_exact(const Plan& P, const WorkItem* d_items, uint32_t n_items, uint32_t n_big, uint32_t stride_big, uint32_t stride_small,
                             uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches) {
     if (n_items == 0) return cudaSuccess;
     n_big = std::min(n_big, n_items);
-    // big CTAs: prefer <= ~100 KB of shared memory so two share an SM; small CTAs: 1/8 of an SM's shared memory each
-    cudaError_t e = launch_k2_part<K2_THREADS>(P, d_items, n_big, stride_big, 100 * 1024, nu, nv, NO, NPT, 1, st);
+    const uint32_t n_small = n_items - n_big;
+    // small CTAs: 1/8 of an SM's shared memory each; big CTAs: prefer <= ~100 KB of shared memory so two share an SM
+    cudaError_t e = launch_k2_part<K2_SMALL_THREADS>(P, d_items + n_big, n_small, stride_small, 27 * 1024, nu, nv, NO, NPT, 1, st);
     if (e != cudaSuccess) return e;
+    if (launches && n_small) (*launches)++;
+    e = launch_k2_part<K2_THREADS>(P, d_items, n_big, stride_big, 100 * 1024, nu, nv, NO, NPT, n_small == 0, st);
     if (launches && n_big) (*launches)++;
-    e = launch_k2_part<K2_SMALL_THREADS>(P, d_items + n_big, n_items - n_big, stride_small, 27 * 1024, nu, nv, NO, NPT, n_big == 0, st);
-    if (launches && n_items > n_big) (*launches)++;
     return e;
 }
 
