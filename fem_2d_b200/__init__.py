@@ -242,9 +242,9 @@ class Mesh:
         self._h = C.c_void_p(handle)
         self._owned = owned
 
-    def __del__(self):
+    def __del__(self, _free=_L.fem2dh_mesh_free):   # bound at definition: module globals may be gone at interpreter exit
         if getattr(self, "_owned", False) and self._h:
-            _L.fem2dh_mesh_free(self._h)
+            _free(self._h)
             self._h = None
 
     @staticmethod
@@ -430,9 +430,9 @@ class Domain:
         self.mesh = Mesh(_L.fem2dh_domain_mesh(self._h), owned=False)
         self._view = None
 
-    def __del__(self):
+    def __del__(self, _free=_L.fem2dh_domain_free):
         if getattr(self, "_h", None):
-            _L.fem2dh_domain_free(self._h)
+            _free(self._h)
             self._h = None
 
     @staticmethod
@@ -586,9 +586,9 @@ class Plan:
         self.nnz = self.info["nnz_upper"]
         self.n_dofs = self.info["n_dofs"]
 
-    def __del__(self):
+    def __del__(self, _free=_L.fem2d_plan_free):
         if getattr(self, "_h", None):
-            _L.fem2d_plan_free(self._h)
+            _free(self._h)
             self._h = None
 
     def refresh_info(self) -> dict:
