@@ -209,7 +209,9 @@ int fem2d_plan_check_work_items(const fem2d_plan* plan, uint64_t out[4]) {
             }
         for (uint32_t t = 0; t < n_mt; t++) if (cover[t] == 0) bad++;   // no empty tiles in the numbering
     }
+    bool small_seen = false;   // launch order: the items that need the wide CTAs form a prefix (order_items)
     for (const WorkItem& it : H.items) {
+        if (it.cls < H.classes.size()) { const bool big = item_is_big(H, it); if (big && small_seen) bad++; small_seen |= !big; }
         if (it.cls >= H.classes.size() || it.n_ranges == 0 || it.n_ranges > (uint32_t)ITEM_MAX_RANGES) { bad++; continue; }
         const ClassDesc& c = H.classes[it.cls];
         const ListDesc& LP = H.lists[c.listP]; const ListDesc& LQ = H.lists[c.listQ];

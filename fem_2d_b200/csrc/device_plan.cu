@@ -540,20 +540,12 @@ __global__ void mark_tiles_kernel(const uint32_t* __restrict__ src1, const uint3
 }  // namespace
 
 ItemSplit split_items(const HostPlan& H, const std::vector<WorkItem>& items) {
+    // `items` is in launch order (plan_host.cpp order_items): the big items form a prefix
     ItemSplit sp;
-    auto stride_of = [&](const WorkItem& it) {
-        const ClassDesc& c = H.classes[it.cls];
-        const ListDesc& LP = H.lists[c.listP]; const ListDesc& LQ = H.lists[c.listQ];
-        uint32_t s = slab_pad4(LP.nU) + slab_pad4(LP.n - LP.nU);
-        if (!c.local) s += slab_pad4(LQ.nU) + slab_pad4(LQ.n - LQ.nU);
-        return s;
-    };
-    // the latency shape (1 x 2 tiles, small plans) keeps one CTA size
-    const uint32_t small_tiles = H.tile_p == 1 ? 0u : (uint32_t)K2_SMALL_TILES;
     for (const WorkItem& it : items) {
-        const bool big = item_slots(it.n_same, it.mt_count) > small_tiles || stride_of(it) > (uint32_t)K2_SMALL_STRIDE;
-        if (big) { sp.n_big++; sp.stride_big = std::max(sp.stride_big, stride_of(it)); }
-        else sp.stride_small = std::max(sp.stride_small, stride_of(it));
+        const uint32_t s = item_slab_stride(H, it);
+        if (item_is_big(H, it)) { sp.n_big++; sp.stride_big = std::max(sp.stride_big, s); }
+        else sp.stride_small = std::max(sp.stride_small, s);
     }
     return sp;
 }
@@ -629,7 +621,7 @@ int device_range_items(Plan& P, uint32_t n_ranges, const uint64_t* begins, const
         }
         flush();
     }
-    std::stable_sort(items.begin(), items.end(), [](const WorkItem& x, const WorkItem& y) { return x.mt_count > y.mt_count; });
+    order_items(P.host, items);
     dev_free(P.d_range_items); P.d_range_items = nullptr;
     CK(dev_malloc((void**)&P.d_range_items, std::max<size_t>(items.size(), 1) * sizeof(WorkItem)));
     CK(cudaMemcpy(P.d_range_items, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));

@@ -113,6 +113,26 @@ WorkItem make_item(const HostPlan& P, uint32_t cls, const std::vector<std::pair<
     return it;
 }
 
+uint32_t item_slab_stride(const HostPlan& H, const WorkItem& it) {
+    const ClassDesc& c = H.classes[it.cls];
+    const ListDesc& LP = H.lists[c.listP]; const ListDesc& LQ = H.lists[c.listQ];
+    uint32_t s = slab_pad4(LP.nU) + slab_pad4(LP.n - LP.nU);
+    if (!c.local) s += slab_pad4(LQ.nU) + slab_pad4(LQ.n - LQ.nU);
+    return s;
+}
+
+bool item_is_big(const HostPlan& H, const WorkItem& it) {
+    // the latency shape (1 x 2 tiles, small plans) keeps one CTA size
+    const uint32_t small_tiles = H.tile_p == 1 ? 0u : (uint32_t)K2_SMALL_TILES;
+    return item_slots(it.n_same, it.mt_count) > small_tiles || item_slab_stride(H, it) > (uint32_t)K2_SMALL_STRIDE;
+}
+
+void order_items(const HostPlan& H, std::vector<WorkItem>& items) {
+    std::stable_sort(items.begin(), items.end(), [](const WorkItem& x, const WorkItem& y) { return x.mt_count > y.mt_count; });
+    // the size predicate is not monotone in mt_count (a wide-stride item with few tiles is "big"): partition by the predicate itself
+    std::stable_partition(items.begin(), items.end(), [&](const WorkItem& it) { return item_is_big(H, it); });
+}
+
 int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::string& err) {
     if (!v) { err = "null view"; return FEM2D_ERR_BAD_ARGUMENT; }
     // Reference error order: continuity condition, then empty DoF set (galerkin.rs:42-50).
@@ -331,12 +351,12 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
             P.n_pairs += local ? (uint64_t)nd * (nd + 1) / 2 : (uint64_t)nE * nd;
         }
     }
+    if (P.blocks.empty()) { err = "the view carries DoFs but no basis specs: nothing to integrate"; return FEM2D_ERR_BAD_ARGUMENT; }
     if (P.n_values >= (1ull << 31) || P.n_pairs >= (1ull << 32)) { err = "domain too large for 32-bit source indices"; return FEM2D_ERR_UNSUPPORTED; }
 
     // ---- work items: <= K2_ROUNDS * K2_THREADS micro-tiles each (balanced split); largest classes first (longest-processing-time order)
     std::vector<uint32_t> cls_order(P.classes.size());
     std::iota(cls_order.begin(), cls_order.end(), 0u);
-    std::stable_sort(cls_order.begin(), cls_order.end(), [&](uint32_t a, uint32_t b) { return P.classes[a].n_mt > P.classes[b].n_mt; });
     for (const ClassDesc& c : P.classes) {
         const ListDesc& LP = P.lists[c.listP]; const ListDesc& LQ = P.lists[c.listQ];
         auto p4 = [](uint32_t x) { return (x + 3u) & ~3u; };
@@ -388,8 +408,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
             if (e > b) P.items.push_back(make_item(P, c, {{b, e - b}}, nullptr));
         }
     }
-    // largest first: longest-processing-time order, and the size split of the integrator launch (device_plan.hpp split_items)
-    std::stable_sort(P.items.begin(), P.items.end(), [](const WorkItem& x, const WorkItem& y) { return x.mt_count > y.mt_count; });
+    order_items(P, P.items);
     return FEM2D_OK;
 }
 

@@ -36,6 +36,12 @@ int elem_geometry(const fem2d_domain_view* view, std::vector<double>& dx, std::v
 
 WorkItem make_item(const HostPlan& plan, uint32_t cls, const std::vector<std::pair<uint32_t, uint32_t>>& ranges, const uint32_t (*cols)[2][2]);
 
+// Integrator launch order of an item list: the items that need K2_THREADS-wide CTAs first (item_is_big: more than K2_SMALL_TILES thread
+// slots or a slab row wider than K2_SMALL_STRIDE), each part largest first (longest-processing-time order).
+uint32_t item_slab_stride(const HostPlan& plan, const WorkItem& it);
+bool item_is_big(const HostPlan& plan, const WorkItem& it);
+void order_items(const HostPlan& plan, std::vector<WorkItem>& items);
+
 // Returns FEM2D_OK or a status from include/fem2d.h; err receives a detail message.
 int build_host_plan(const fem2d_domain_view* view, bool dedupe, HostPlan& plan, std::string& err);
 
