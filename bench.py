@@ -37,6 +37,8 @@ WORKLOADS = {
     "cfg3_l2": dict(mesh="a", order=6, levels=2, glq=8),
     "cfg2": dict(mesh="b", order=8, levels=3, glq=12),       # BASELINE.json configs[1]
     "cfg4": dict(mesh="c4", glq=12),                         # BASELINE.json configs[3] (anisotropic, random p)
+    # north_star target: >= 1M-DoF anisotropically hp-refined domain (cfg-4 recipe at 6 T-levels, 4 U/V rounds: 1,380,549 DoFs)
+    "hp1m": dict(mesh="hp", glq=12),
 }
 
 
@@ -69,6 +71,8 @@ def build_product_domain(workload: str):
         m = recipes.mesh_cfg3(api, levels=w["levels"], order=w["order"])
     elif w["mesh"] == "b":
         m = recipes.mesh_cfg2(api, levels=w["levels"], order=w["order"])
+    elif w["mesh"] == "hp":
+        m = recipes.mesh_hp1m(api)
     else:
         m = recipes.mesh_cfg4(api)
     return F.Domain.from_mesh(m)
@@ -83,6 +87,8 @@ def build_oracle_domain(workload: str):
         m = recipes.mesh_cfg3(api, levels=w["levels"], order=w["order"])
     elif w["mesh"] == "b":
         m = recipes.mesh_cfg2(api, levels=w["levels"], order=w["order"])
+    elif w["mesh"] == "hp":
+        m = recipes.mesh_hp1m(api)
     else:
         m = recipes.mesh_cfg4(api)
     return O.Domain.from_mesh(m)

@@ -17,7 +17,7 @@ from typing import Callable, Iterable, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfem2d_b200.so")
+LIB_PATH = os.environ.get("FEM2D_LIB") or os.path.join(_HERE, "libfem2d_b200.so")   # FEM2D_LIB: tuning builds (build.py FEM2D_VARIANT)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -11,8 +11,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT_DIR = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "libfem2d_b200.so")
+# FEM2D_VARIANT=<tag> (tuning only): a second copy of the library built with FEM2D_NVCC_FLAGS into _variants/<tag>/, loaded by
+# FEM2D_LIB=<path>; the product library is always fem_2d_b200/libfem2d_b200.so
+_VARIANT = os.environ.get("FEM2D_VARIANT", "")
+OUT_DIR = os.path.join(HERE, "_variants", _VARIANT, "_build") if _VARIANT else os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "_variants", _VARIANT, "libfem2d_b200.so") if _VARIANT else os.path.join(HERE, "libfem2d_b200.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

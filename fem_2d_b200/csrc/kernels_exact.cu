@@ -384,7 +384,7 @@ static cudaError_t launch_k2_part(const Plan& P, const WorkItem* d_items, uint32
     const uint32_t slab_doubles = (uint32_t)((smem - fixed) / sizeof(double));
     static thread_local size_t smem_set[64] = {};   // per device: largest dynamic shared memory size already opted in (per NT)
     if (P.device >= 0 && P.device < 64 && smem > smem_set[P.device]) {
-        cudaError_t e = cudaFuncSetAttribute(k2_exact_kernel<4, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k2_exact_kernel<K2_TILE_P, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_exact_kernel<1, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         smem_set[P.device] = smem;
@@ -395,7 +395,7 @@ static cudaError_t launch_k2_part(const Plan& P, const WorkItem* d_items, uint32
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    const cudaError_t e = P.host.tile_p == 1 ? cudaLaunchKernelEx(&cfg, k2_exact_kernel<1, NT>, g) : cudaLaunchKernelEx(&cfg, k2_exact_kernel<4, NT>, g);
+    const cudaError_t e = P.host.tile_p == 1 ? cudaLaunchKernelEx(&cfg, k2_exact_kernel<1, NT>, g) : cudaLaunchKernelEx(&cfg, k2_exact_kernel<K2_TILE_P, NT>, g);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
@@ -414,7 +414,7 @@ cudaError_t launch_k2_exact(const Plan& P, const WorkItem* d_items, uint32_t n_i
     cudaError_t e = launch_k2_part<K2_SMALL_THREADS>(P, d_items + n_big, n_small, stride_small, 27 * 1024, nu, nv, NO, NPT, 1, st);
     if (e != cudaSuccess) return e;
     if (launches && n_small) (*launches)++;
-    e = launch_k2_part<K2_THREADS>(P, d_items, n_big, stride_big, 100 * 1024, nu, nv, NO, NPT, n_small == 0, st);
+    e = launch_k2_part<K2_THREADS>(P, d_items, n_big, stride_big, (K2_MIN_CTAS == 2 ? 100 : 216 / K2_MIN_CTAS) * 1024, nu, nv, NO, NPT, n_small == 0, st);
     if (launches && n_big) (*launches)++;
     return e;
 }

@@ -375,8 +375,8 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
         }
         return n;
     };
-    P.tile_p = 4;
-    if (count_mt(4) < (uint64_t)148 * K2_THREADS) { P.tile_p = 1; count_mt(1); }
+    P.tile_p = K2_TILE_P;
+    if (count_mt(K2_TILE_P) < (uint64_t)148 * K2_THREADS) { P.tile_p = 1; count_mt(1); }
     std::stable_sort(cls_order.begin(), cls_order.end(), [&](uint32_t a, uint32_t b) { return P.classes[a].n_mt > P.classes[b].n_mt; });
     // Few, heavily deduplicated classes would leave most of the 148 SMs idle: shrink the item size until there are about two
     // CTAs per SM (each item re-stages its class's slabs, which is cheap next to an idle machine).

@@ -23,9 +23,22 @@ namespace fem2d {
 // either kind then take about the same time between two barriers.
 constexpr int MT_Q = 2;            // same-direction micro-tile: Q functions (cols) per thread
 constexpr int MT_QX = 4;           // cross-direction micro-tile (both shapes; 1 x 2 at TP = 1 measured 16 % slower on cfg 2, equal on cfg 3)
-constexpr int K2_THREADS = 256;
-constexpr int K2_MIN_CTAS = 2;     // CTAs per SM the integrator is compiled for
-constexpr int K2_ROUNDS = 2;    // a work item covers up to K2_ROUNDS * K2_THREADS micro-tiles of one class (slabs staged once)
+#ifndef FEM2D_TILE_P
+#define FEM2D_TILE_P 4             // throughput-shape tile height (tuning builds: -DFEM2D_TILE_P=2)
+#endif
+#ifndef FEM2D_K2_THREADS
+#define FEM2D_K2_THREADS 256
+#endif
+#ifndef FEM2D_K2_CTAS
+#define FEM2D_K2_CTAS 2
+#endif
+#ifndef FEM2D_K2_ROUNDS
+#define FEM2D_K2_ROUNDS 2
+#endif
+constexpr int K2_TILE_P = FEM2D_TILE_P;
+constexpr int K2_THREADS = FEM2D_K2_THREADS;
+constexpr int K2_MIN_CTAS = FEM2D_K2_CTAS;     // CTAs per SM the integrator is compiled for
+constexpr int K2_ROUNDS = FEM2D_K2_ROUNDS;    // a work item covers up to K2_ROUNDS * K2_THREADS micro-tiles of one class (slabs staged once)
 // Work items with at most K2_SMALL_TILES micro-tiles (small classes: low-order Elems of an hp-mesh, remainders) run in CTAs of
 // K2_SMALL_THREADS threads, K2_SMALL_CTAS of which share an SM: a 256-thread CTA with a handful of active threads would hold half
 // an SM's registers for the whole quadrature loop.

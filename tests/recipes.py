@@ -123,6 +123,13 @@ def mesh_cfg4(api, t_levels=4, rounds=3, pmin=2, pmax=10, seed=SEED, mesh_file=M
     return m
 
 
+def mesh_hp1m(api, t_levels=6, rounds=4):
+    """north_star target workload (BASELINE.json metric: ">= 1M-DoF anisotropically hp-refined H(curl) domain"): the cfg-4 recipe
+    at 6 global T-levels and 4 seeded U/V rounds, p in [2, 10] per Elem: 38 509 Elems, 1 380 549 DoFs, 84 930 129 upper-triangular
+    entries per matrix, 71 086 pair blocks (local-local and local-desc) in 63 157 classes."""
+    return mesh_cfg4(api, t_levels=t_levels, rounds=rounds)
+
+
 def mesh_edge_order(api):    # mesh.rs:1918-1937 recipe + anisotropic orders: exercises U(Some(1)) extensions and n-irregular edges
     m = api.Mesh.from_file(MESH_B)
     m.global_h_refinement(api.href(T))

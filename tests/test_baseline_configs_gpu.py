@@ -1,0 +1,174 @@
+"""Whole-matrix, bit-for-bit comparisons with the oracle on the BASELINE.json configs the oracle can assemble in seconds
+(configs[1] = cfg 2, configs[3] = cfg 4, both basis spaces), a wide oracle spot check of configs[2] (cfg 3, 1.18 M DoFs) over all
+16 classes and all four base Elements, the oracle's own Golub-Welsch GLQ nodes passed through the product ABI, and the
+north_star workload (>= 1 M-DoF anisotropic hp-mesh): a whole-matrix comparison one T-level down plus spot checks at full size.
+What must match: galerkin.rs:91-178 (pairs), integrals.rs:26-92,292-354 (values), sparse_matrix.rs:68-120 (keys, sums)."""
+import numpy as np
+import pytest
+
+import recipes
+
+pytestmark = pytest.mark.gpu
+
+import fem_2d_b200 as F  # noqa: E402
+import oracle as O  # noqa: E402
+
+
+def _bits(x):
+    return np.ascontiguousarray(x, dtype=np.float64).view(np.uint64)
+
+
+def _same_bits(got, ref, what):
+    gb, rb = _bits(got), _bits(ref)
+    if not np.array_equal(gb, rb):
+        bad = np.nonzero(gb != rb)[0]
+        raise AssertionError(f"{what}: {len(bad)}/{len(gb)} entries differ bitwise; first at {bad[0]}: got {got[bad[0]]!r} ref {ref[bad[0]]!r}")
+
+
+def _whole(mesh_fn, g, basis=0, dedupe=True, threads=16):
+    mo, mf = mesh_fn(recipes.api("oracle")), mesh_fn(recipes.api("product"))
+    do, df = O.Domain.from_mesh(mo), F.Domain.from_mesh(mf)
+    glq = (F.gauss_quadrature_points(g), F.gauss_quadrature_points(g))
+    ref = O.galerkin_sample_gep_hcurl(do, basis=basis, glq=glq, n_threads=threads)
+    plan = F.Plan(df.view(), device=0, dedupe=dedupe)
+    rows, cols, a, b = plan.assemble(glq, basis=F.HierPoly if basis == 0 else F.HierMaxOrtho)
+    return ref, plan, rows, cols, a, b
+
+
+@pytest.mark.parametrize("dedupe", [True, False])
+def test_cfg2_full_whole_matrix(dedupe):
+    """BASELINE configs[1]: test_mesh_b.json, Orders(8,8), 3x global T, GLQ 12x12 (24 320 DoFs, 1 920 192 upper entries)."""
+    ref, plan, rows, cols, a, b = _whole(recipes.mesh_cfg2, 12, dedupe=dedupe)
+    assert plan.n_dofs == 24320 and plan.nnz == 1920192 == len(ref.rows)
+    assert np.array_equal(rows, ref.rows) and np.array_equal(cols, ref.cols)
+    _same_bits(a, ref.a, "A[cfg2]"); _same_bits(b, ref.b, "B[cfg2]")
+
+
+@pytest.mark.parametrize("basis", [0, 1])
+@pytest.mark.parametrize("dedupe", [True, False])
+def test_cfg4_full_whole_matrix(basis, dedupe):
+    """BASELINE configs[3]: test_mesh_c.json, 4x T + 3 seeded U/V rounds, p in [2,10], GLQ 12x12 (57 825 DoFs, 3 505 664 upper entries),
+    HierPoly (== KOLShapeFn) and HierMaxOrtho."""
+    ref, plan, rows, cols, a, b = _whole(recipes.mesh_cfg4, 12, basis=basis, dedupe=dedupe)
+    assert plan.n_dofs == 57825 and plan.nnz == 3505664 == len(ref.rows)
+    assert np.array_equal(rows, ref.rows) and np.array_equal(cols, ref.cols)
+    _same_bits(a, ref.a, f"A[cfg4,basis{basis}]"); _same_bits(b, ref.b, f"B[cfg4,basis{basis}]")
+
+
+def test_oracle_glq_nodes_through_the_product_abi():
+    """GLQ nodes are inputs of the boundary (glq.rs:179-222 delegates to nalgebra): the ORACLE's Golub-Welsch nodes and weights, not the
+    product's Newton ones, go through the product ABI and the oracle alike; results stay bit-identical."""
+    for name, (nu, nv) in (("readme", (8, 8)), ("slepc", (9, 12)), ("cfg4_small", (12, 7))):
+        mo, mf = recipes.build_pair(name)
+        do, df = O.Domain.from_mesh(mo), F.Domain.from_mesh(mf)
+        glq = (O.gauss_quadrature_points(nu), O.gauss_quadrature_points(nv))
+        mine = (F.gauss_quadrature_points(nu), F.gauss_quadrature_points(nv))
+        assert np.allclose(glq[0][0], mine[0][0], rtol=0, atol=1e-14)
+        ref = O.galerkin_sample_gep_hcurl(do, glq=glq)
+        rows, cols, a, b = F.Plan(df.view(), device=0).assemble(glq)
+        assert np.array_equal(rows, ref.rows) and np.array_equal(cols, ref.cols)
+        _same_bits(a, ref.a, f"A[{name}, oracle nodes]"); _same_bits(b, ref.b, f"B[{name}, oracle nodes]")
+
+
+def _single_contribution_check(do, view, plan, a, b, elem_ids, glq, what, basis=0):
+    """Oracle per-Elem matrices (closure body of galerkin.rs:73-183, not merged) of `elem_ids` against the assembled GPU values at every key
+    that has an endpoint carried by exactly one Elem: such a key receives exactly one contribution (the two Elems that share an edge DoF lie
+    on opposite sides of the edge, so at most one of them is the Elem, an ancestor or a descendant of the other endpoint's only Elem), i.e.
+    the assembled value IS the oracle's per-Elem value.  Returns the number of keys compared."""
+    el, r, c, oa, ob = O.assemble_elems(do, elem_ids, glq, basis=basis)
+    cnt = np.bincount(view.bs_dof, minlength=view.n_dofs)
+    single = (cnt[r] == 1) | (cnt[c] == 1)
+    rows, cols = plan.pattern()
+    keys = rows.astype(np.int64) << 32 | cols.astype(np.int64)
+    k = r.astype(np.int64) << 32 | c.astype(np.int64)
+    slot = np.searchsorted(keys, k)
+    assert np.array_equal(keys[slot], k), f"{what}: oracle key missing from the pattern"
+    _same_bits(a[slot[single]], oa[single], f"A[{what}]"); _same_bits(b[slot[single]], ob[single], f"B[{what}]")
+    return int(single.sum()), el, slot, single
+
+
+def test_cfg3_full_wide_spot_check():
+    """configs[2] at full size: 320 leaves spread over the whole id range -- every one of the 16 dedupe classes (4 base Elements with
+    eps_r, mu_r in {1, 2} x 4 boundary situations...) and all four base Elements -- against the oracle at every single-contribution key."""
+    import torch
+    mo = recipes.mesh_cfg3(recipes.api("oracle")); mf = recipes.mesh_cfg3(recipes.api("product"))
+    do, df = O.Domain.from_mesh(mo), F.Domain.from_mesh(mf)
+    glq = (F.gauss_quadrature_points(8), F.gauss_quadrature_points(8))
+    plan = F.Plan(df.view(), device=0, dedupe=True)
+    assert plan.info["n_classes"] == 16
+    da = torch.empty(plan.nnz, dtype=torch.float64, device="cuda:0"); db = torch.empty_like(da)
+    plan.assemble_device(glq, da.data_ptr(), db.data_ptr())
+    a, b = da.cpu().numpy(), db.cpu().numpy()
+    n_leaf0 = 21844 - 16384
+    rng = np.random.default_rng(20261017)
+    ids = np.unique(np.concatenate([n_leaf0 + rng.choice(16384, 300, replace=False), [n_leaf0, 21843]]))
+    # all four base Elements (materials differ) must be present among the sampled leaves
+    def base_of(e):
+        while mo.elem(e).parent >= 0:
+            e = mo.elem(e).parent
+        return e
+    assert {base_of(int(e)) for e in ids} == {0, 1, 2, 3}
+    n, *_ = _single_contribution_check(do, df.view(), plan, a, b, ids, glq, "cfg3 full")
+    assert n >= len(ids) * (60 * 61 // 2 + 60 * 24)     # Elem-type x Elem-type and Elem-type x edge-type keys of every sampled leaf
+
+
+def test_hp_mesh_whole_matrix_one_level_down():
+    """The north_star mesh family (cfg-4 recipe, 4 U/V rounds, p in [2,10], GLQ 12x12) at 5 global T-levels: 345 k DoFs, whole matrices
+    against the oracle, bit for bit (local-local and local-desc blocks, n-irregular edges, 2-contribution keys)."""
+    fn = lambda api: recipes.mesh_hp1m(api, t_levels=5)
+    ref, plan, rows, cols, a, b = _whole(fn, 12, dedupe=True)
+    assert plan.n_dofs > 300000 and plan.info["max_contrib"] == 2
+    assert np.array_equal(rows, ref.rows) and np.array_equal(cols, ref.cols)
+    _same_bits(a, ref.a, "A[hp, 5 T-levels]"); _same_bits(b, ref.b, "B[hp, 5 T-levels]")
+
+
+def test_hp1m_full_size_properties_and_spot_checks():
+    """north_star workload at full size (1 380 549 DoFs, 84.9 M upper entries per matrix): closed sizes, sorted unique upper-triangular
+    pattern, <= 2 contributions, dedupe on == dedupe off bitwise, 4 row-block shards == full range bitwise, and oracle spot checks of
+    400 Elems (leaves AND ancestors that carry edge functions, i.e. local-desc blocks) at every single-contribution key."""
+    import torch
+    mo = recipes.mesh_hp1m(recipes.api("oracle")); mf = recipes.mesh_hp1m(recipes.api("product"))
+    do, df = O.Domain.from_mesh(mo), F.Domain.from_mesh(mf)
+    view = df.view()
+    glq = (F.gauss_quadrature_points(12), F.gauss_quadrature_points(12))
+    plan = F.Plan(view, device=0, dedupe=True)
+    info = plan.info
+    assert plan.n_dofs == 1380549 == do.num_dofs and plan.nnz == 84930129 and info["n_pairs"] == 85999438
+    assert info["n_blocks"] == 71086 and info["max_contrib"] == 2 and info["n_extra"] == 85999438 - 84930129
+    da = torch.empty(plan.nnz, dtype=torch.float64, device="cuda:0"); db = torch.empty_like(da)
+    plan.assemble_device(glq, da.data_ptr(), db.data_ptr())
+    torch.cuda.synchronize()
+    rows, cols = plan.pattern()
+    assert np.all(rows <= cols)
+    keys = rows.astype(np.int64) << 32 | cols.astype(np.int64)
+    assert np.all(np.diff(keys) > 0) and np.count_nonzero(rows == cols) == plan.n_dofs
+    del keys
+    # dedupe off: every block integrated on its own
+    pn = F.Plan(view, device=0, dedupe=False)
+    assert pn.info["n_classes"] == pn.info["n_blocks"] == 71086
+    ea = torch.empty_like(da); eb = torch.empty_like(db)
+    pn.assemble_device(glq, ea.data_ptr(), eb.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(ea.view(torch.int64), da.view(torch.int64)) and torch.equal(eb.view(torch.int64), db.view(torch.int64))
+    del pn
+    # 4 shards (Elem-type rows + edge-type rows per rank) with the restricted integrator
+    ea.fill_(float("nan")); eb.fill_(float("nan"))
+    b1, b2 = plan.row_blocks_split(4)
+    for r in range(4):
+        plan.assemble_device_ranges(glq, ea.data_ptr(), eb.data_ptr(), [(int(b1[r]), int(b1[r + 1])), (int(b2[r]), int(b2[r + 1]))])
+    torch.cuda.synchronize()
+    assert torch.equal(ea.view(torch.int64), da.view(torch.int64)) and torch.equal(eb.view(torch.int64), db.view(torch.int64))
+    del ea, eb
+    a, b = da.cpu().numpy(), db.cpu().numpy()
+    # oracle spot checks: 250 random Elems with functions + the 150 non-leaf Elems with the most functions (local-desc blocks)
+    nspec = np.diff(view.bs_off)
+    with_specs = np.nonzero(nspec > 0)[0]
+    is_leaf = np.ones(view.n_elems, dtype=bool); is_leaf[view.elem_parent[view.elem_parent >= 0]] = False
+    anc = with_specs[~is_leaf[with_specs]]
+    assert len(anc) > 1000
+    rng = np.random.default_rng(7)
+    ids = np.unique(np.concatenate([rng.choice(with_specs, 250, replace=False), anc[np.argsort(nspec[anc])[-150:]]]))
+    n, el, slot, single = _single_contribution_check(do, view, plan, a, b, ids, glq, "hp1m full")
+    assert n > 500000
+    # the sample must contain local-desc pairs: keys produced by a non-leaf Elem
+    assert np.count_nonzero(single & ~is_leaf[el]) > 10000
