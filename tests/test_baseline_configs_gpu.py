@@ -109,7 +109,8 @@ def test_cfg3_full_wide_spot_check():
         return e
     assert {base_of(int(e)) for e in ids} == {0, 1, 2, 3}
     n, *_ = _single_contribution_check(do, df.view(), plan, a, b, ids, glq, "cfg3 full")
-    assert n >= len(ids) * (60 * 61 // 2 + 60 * 24)     # Elem-type x Elem-type and Elem-type x edge-type keys of every sampled leaf
+    # Elem-type x Elem-type and Elem-type x edge-type keys of every sampled leaf (24 edge functions, fewer on the domain boundary)
+    assert len(ids) * (60 * 61 // 2 + 60 * 12) <= n <= len(ids) * (60 * 61 // 2 + 60 * 24)
 
 
 def test_hp_mesh_whole_matrix_one_level_down():
