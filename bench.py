@@ -42,6 +42,15 @@ WORKLOADS = {
 }
 
 
+WORKLOAD_TEXT = {
+    "cfg3": "cfg3: test_mesh_a.json, Orders(6,6), 6x global T (BASELINE.json configs[2]), HierPoly/CurlCurl/L2Inner, GLQ [8,8]",
+    "cfg2": "cfg2: test_mesh_b.json, Orders(8,8), 3x global T (BASELINE.json configs[1]), GLQ [12,12]",
+    "cfg4": "cfg4: test_mesh_c.json, 4x T + 3 seeded U/V rounds, p in [2,10] (BASELINE.json configs[3]), GLQ [12,12]",
+    "hp1m": "hp1m: test_mesh_c.json, 6x global T + 4 seeded anisotropic U/V rounds, random p in [2,10] per Elem (north_star target: >= 1M-DoF "
+            "anisotropically hp-refined H(curl) domain; 1,380,549 DoFs), HierPoly/CurlCurl/L2Inner, GLQ [12,12]",
+}
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -160,37 +169,39 @@ def cpu_port_run(workload: str, threads: int):
 
 
 def run_reference(args):
+    """CPU arm on the SAME config as the GPU arm: the full headline workload (BASELINE configs[2]) assembled by the C++ restatement of the
+    Rayon path on all host threads.  One assembly takes about half a minute (the serial ordered-map merge of linalg.rs:74-79 dominates), so
+    the number of repetitions is bounded by a wall-clock budget; `steps_timed` says how many were run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    # bounded sample: the same mesh family at fewer refinement levels (each level = 4x the work), the largest whose (steps + warmup)
-    # runs end within the budget
-    budget = 150.0
-    total = args.steps + args.warmup
-    probe = cpu_port_run("cfg3_l2", threads)
-    sample, est = "cfg3_l2", probe["seconds"]
-    for nxt in ("cfg3_l3", "cfg3_l4", "cfg3_l5"):
-        if est * 4.3 * total > budget:
-            break
-        sample, est = nxt, est * 4.3
+    workload = args.workload
+    budget = float(os.environ.get("FEM2D_REF_BUDGET_S", "600"))
+    t_begin = time.perf_counter()
     results = []
-    for k in range(total):
-        r = cpu_port_run(sample, threads)
-        if k >= args.warmup:
-            results.append(r)
+    warm = None
+    if args.warmup > 0:
+        warm = cpu_port_run(workload, threads)          # also tells how many timed steps fit
+    est = warm["seconds"] if warm else None
+    for k in range(args.steps):
+        if results and (time.perf_counter() - t_begin) + (est or results[-1]["seconds"]) > budget:
+            break
+        results.append(cpu_port_run(workload, threads))
+        est = results[-1]["seconds"]
     sec = sum(r["seconds"] for r in results)
     nnz2 = sum(2 * r["nnz"] for r in results)
     value = nnz2 / sec
-    w = WORKLOADS[sample]
     line = {
         "impl": "reference", "metric": "assembly_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * sec / len(results), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg3: test_mesh_a.json, Orders(6,6), 6x global T, HierPoly/CurlCurl/L2Inner, GLQ [8,8]",
-                   "sample": f"{sample}: same recipe at {w['levels']} T-levels ({results[0]['dofs']} DoFs, {results[0]['nnz']} upper entries per matrix)"},
+        "warmup": args.warmup, "steps_timed": len(results), "warmup_run": 1 if warm else 0, "ms_per_step": 1e3 * sec / len(results),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT.get(workload, workload), "mode": "exact", "n_dofs": results[0]["dofs"],
+                   "nnz_upper_per_matrix": results[0]["nnz"], "nnz_counted": "2 x nnz_upper (A and B)",
+                   "same_config_as_gpu_arm": workload == "cfg3",
+                   "repetitions": f"{len(results)} timed full assemblies within a {budget:.0f} s budget (requested {args.steps})"},
         "cpu_baseline": {"value": value, "unit": "nnz/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} ({results[0]['nnz']} upper entries/matrix), C++ restatement of the Rayon path; integrate {results[0]['integrate_s']:.2f}s + serial merge {results[0]['merge_s']:.2f}s per step"},
+                         "sample": f"full workload ({results[0]['nnz']} upper entries/matrix), C++ restatement of the Rayon path; integrate {results[0]['integrate_s']:.2f}s ({threads} threads) + serial merge {results[0]['merge_s']:.2f}s per step"},
         "e2e": {"value": value, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "Rust reference cannot be built in this image (no rustc/cargo): CPU arm = C++ restatement (oracle), all host threads",
@@ -222,9 +233,99 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    stream = torch.cuda.current_stream()
+    mode = {"exact": F.MODE_EXACT, "sumfact": F.MODE_SUMFACT, "dmma": F.MODE_DMMA}[args.mode]
+    peaks, peak_kind = _peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    fp64 = {}
+    try:   # FP64 pipe denominators, measured on this GPU in this run (the EXACT integrator issues only non-fusable DMUL / DADD)
+        fp64 = {"dfma_gflops": F.fp64_peak(local_rank, 0), "dmul_dadd_gflops": F.fp64_peak(local_rank, 1)}
+    except Exception as ex:  # pragma: no cover
+        fp64 = {"error": str(ex)}
+    fp64_peak_gops = float(fp64.get("dmul_dadd_gflops", 18300.0))
+
+    def timed(step, steps, warmup, sampler=None):
+        """`steps` steps between two CUDA events on the launch stream, barrier + synchronize on both sides, max over ranks -> ms per step."""
+        for _ in range(warmup):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.start()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        while not e1.query():
+            time.sleep(0.0005)
+        torch.cuda.synchronize()
+        if sampler is not None:
+            sampler.stop()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        barrier()
+        return ms / steps
+
+    def phases(plan, step, n):
+        """Per-phase device durations: `n` more steps with the library's per-phase events on (CUDA events on the launch stream between
+        the kernels).  They are off in the timed regions because an event between two kernels keeps the second from starting under
+        programmatic dependent launch."""
+        plan.set_phase_timing(True)
+        for _ in range(3):
+            step()
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for _ in range(n):
+            step()
+        p1.record(stream)
+        torch.cuda.synchronize()
+        ms_events = p0.elapsed_time(p1) / n
+        ph = np.array([[plan.last_timing(k)[key] for key in ("sampler_ms", "integrator_ms", "scatter_ms", "total_ms")] for k in range(n)])
+        launches = plan.last_timing(0)["launches"]
+        plan.set_phase_timing(False)
+        barrier()
+        k1, k2, k3, tot = ph.mean(axis=0)
+        return {"sampler_k1": float(k1), "integrator_k2": float(k2), "scatter_k3": float(k3), "sum": float(tot),
+                "ms_per_step_with_phase_events": float(ms_events)}, launches
+
+    def hbm_roofline(plan, ranges, k3_ms, tot_ms, wl, dedupe):
+        n_slots = sum(e - b for b, e in ranges)
+        # K3 algorithmic bytes: 16 B written per slot (A and B) + the source map it reads.  SURVEY.md 8d budgets a 4 B index per pair; the
+        # packed map the kernel actually reads is smaller (fem2d_plan_source_map_info), and the smaller figure is the one used here.
+        smi = plan.source_map_info()
+        map_bytes = smi["map_bytes"] * (n_slots / max(plan.nnz, 1))
+        alg = 16.0 * n_slots + map_bytes
+        gbs = alg / (k3_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "k3_gather_kernel (DoF scatter)", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                "traffic": _ncu_traffic(wl, dedupe, world),
+                "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)" if peak_kind == "measured" else "fallback 6.65 TB/s",
+                "algorithmic_bytes_per_launch": alg, "source_map_bytes_per_launch": map_bytes, "source_map_plain_chunks": smi["plain_chunks"],
+                "survey_8d_bytes_per_launch": 20.0 * n_slots, "kernel_ms": float(k3_ms), "share_of_step": float(k3_ms / tot_ms)}
+
+    def fp64_roofline(plan, g, k2_ms, tot_ms):
+        """Integrator roofline: algorithmic FP64 lane-operations of the reference's per-pair quadrature (fem2d_plan_work_info: 8 per same-
+        direction pair and point + 4 per row, 3 + 2 for cross-direction pairs; nothing fusable, tile padding and slab staging not counted)
+        over the integrator's device time, against the DMUL+DADD issue rate measured in this run.  At N > 1 every rank is charged 1/N of the
+        operations, so recomputed halo tiles and imbalance lower the fraction."""
+        ops = plan.fp64_lane_ops(g, g) / world
+        rate = ops / (k2_ms * 1e-3) / 1e9
+        w = plan.work_info()
+        return {"bound": "fp64_issue", "kernel": "k2_ws_kernel<4> + k2_exact_kernel<4,64> (exact per-pair integrator)", "achieved": rate, "peak": fp64_peak_gops,
+                "unit": "G lane-ops/s", "frac": rate / fp64_peak_gops, "traffic": None,
+                "peak_source": "non-fused DMUL+DADD chain measured in this run (fem2d_fp64_peak kind 1); DFMA peak is 2x and unusable: every operation of the reference order is separately rounded",
+                "algorithmic_lane_ops_per_launch": ops, "same_pairs": w["same_pairs"], "cross_pairs": w["cross_pairs"],
+                "kernel_ms": float(k2_ms), "share_of_step": float(k2_ms / tot_ms)}
+
+    # ---------------------------------------------------------------------------------------------- headline: BASELINE configs[2]
     workload = args.workload
     w = WORKLOADS[workload]
-    mode = {"exact": F.MODE_EXACT, "sumfact": F.MODE_SUMFACT, "dmma": F.MODE_DMMA}[args.mode]
     domain = build_product_domain(workload)
     view = domain.view()
     glq = (F.gauss_quadrature_points(w["glq"]), F.gauss_quadrature_points(w["glq"]))
@@ -233,186 +334,70 @@ def run_ours(args):
     ranges = rank_ranges(plan, world, rank)
     if args.emulate_world > 1:   # tuning aid: time one rank's share of an N-rank run on a single GPU
         ranges = rank_ranges(plan, args.emulate_world, args.emulate_rank)
-    stream = torch.cuda.current_stream()
     d_a = torch.empty(nnz, dtype=torch.float64, device=dev)
     d_b = torch.empty(nnz, dtype=torch.float64, device=dev)
 
     def step():
         plan.assemble_device_ranges(glq, d_a.data_ptr(), d_b.data_ptr(), ranges, mode=mode, stream=stream.cuda_stream)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.start()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    while not e1.query():
-        time.sleep(0.0005)
-    torch.cuda.synchronize()
-    sampler.stop()
-    ms_total = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    barrier()
-    ms_step = ms_total / args.steps
+    ms_step = timed(step, args.steps, max(args.warmup, 3), sampler)
     value = 2.0 * nnz / (ms_step * 1e-3)
-
-    # per-phase device durations: the same steps again with the library's per-phase events switched on (CUDA events on the launch
-    # stream between the kernels).  They are off in the region above because an event between two kernels keeps the second from
-    # starting under programmatic dependent launch; `ms_per_step_with_phase_events` shows what that costs.
-    plan.set_phase_timing(True)
-    n_back = min(args.steps, 64)
-    for _ in range(3):
-        step()
-    barrier()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record(stream)
-    for _ in range(n_back):
-        step()
-    p1.record(stream)
-    torch.cuda.synchronize()
-    ms_step_events = p0.elapsed_time(p1) / n_back
-    ph = np.array([[plan.last_timing(k)[key] for key in ("sampler_ms", "integrator_ms", "scatter_ms", "total_ms")] for k in range(n_back)])
-    k1_ms, k2_ms, k3_ms, tot_ms = ph.mean(axis=0)
-    launches_per_step = plan.last_timing(0)["launches"]
-    plan.set_phase_timing(False)
-    barrier()
-
-    peaks, peak_kind = _peaks()
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    n_slots = sum(e - b for b, e in ranges)
-    # K3 algorithmic bytes: 16 B written per slot (A and B) + the source map it reads.  SURVEY.md 8d budgets a 4 B index per pair; the
-    # packed map the kernel actually reads is smaller (fem2d_plan_source_map_info), and the smaller figure is the one used here.
-    smi = plan.source_map_info()
-    map_bytes = smi["map_bytes"] * (n_slots / max(nnz, 1))
-    alg_bytes_k3 = 16.0 * n_slots + map_bytes
-    k3_gbs = alg_bytes_k3 / (k3_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k3_gather_kernel (DoF scatter)", "achieved": k3_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k3_gbs / hbm_peak,
-                "traffic": _ncu_traffic(workload, args.dedupe, world),
-                "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs, burst copy)" if peak_kind == "measured" else "fallback 6.65 TB/s",
-                "algorithmic_bytes_per_launch": alg_bytes_k3, "source_map_bytes_per_launch": map_bytes, "source_map_plain_chunks": smi["plain_chunks"],
-                "survey_8d_bytes_per_launch": 20.0 * n_slots, "kernel_ms": float(k3_ms), "share_of_step": float(k3_ms / tot_ms)}
+    ph, launches_per_step = phases(plan, step, min(args.steps, 64))
+    roofline = hbm_roofline(plan, ranges, ph["scatter_k3"], ph["sum"], workload, args.dedupe)
     info = plan.info
+
+    # ------------------------------------------------------------- first-class second results: where the integrator is the step
+    workloads = {}
+    if not args.no_second:
+        # (1) the north_star target: >= 1M-DoF anisotropically hp-refined domain, sharded like the headline at N > 1
+        try:
+            hp_dom = build_product_domain("hp1m")
+            g = WORKLOADS["hp1m"]["glq"]
+            gq = (F.gauss_quadrature_points(g), F.gauss_quadrature_points(g))
+            hp = F.Plan(hp_dom.view(), device=local_rank, dedupe=True)
+            hr = rank_ranges(hp, world, rank)
+            ha = torch.empty(hp.nnz, dtype=torch.float64, device=dev); hb = torch.empty_like(ha)
+
+            def hp_step():
+                hp.assemble_device_ranges(gq, ha.data_ptr(), hb.data_ptr(), hr, mode=mode, stream=stream.cuda_stream)
+
+            n_hp = max(3, min(args.steps, 20))
+            ms_hp = timed(hp_step, n_hp, 3)
+            hph, _ = phases(hp, hp_step, min(n_hp, 10))
+            k2_max, tot_max = max_over_ranks(hph["integrator_k2"]), max_over_ranks(hph["sum"])
+            workloads["hp1m"] = {
+                "workload": WORKLOAD_TEXT["hp1m"], "n_dofs": hp.n_dofs, "nnz_upper_per_matrix": hp.nnz, "n_pairs": hp.info["n_pairs"],
+                "n_blocks": hp.info["n_blocks"], "n_classes": hp.info["n_classes"], "dedupe": 1, "glq": [g, g], "steps": n_hp, "n_gpus": world,
+                "ms_per_step": ms_hp, "value": 2.0 * hp.nnz / (ms_hp * 1e-3), "unit": "nnz/s", "phases_ms_rank0": hph,
+                "roofline": fp64_roofline(hp, g, k2_max, tot_max),
+                "roofline_hbm": hbm_roofline(hp, hr, hph["scatter_k3"], hph["sum"], "hp1m", 1),
+            }
+            del hp, ha, hb, hp_dom
+        except Exception as ex:  # pragma: no cover
+            workloads["hp1m"] = {"error": repr(ex)}
+        # (2) the headline mesh without block dedupe: every one of the 16 384 leaf blocks integrated on its own (single GPU only)
+        if world == 1:
+            try:
+                pn = F.Plan(view, device=local_rank, dedupe=not bool(args.dedupe))
+
+                def nd_step():
+                    pn.assemble_device(glq, d_a.data_ptr(), d_b.data_ptr(), mode=mode, stream=stream.cuda_stream)
+
+                ms_nd = timed(nd_step, 10, 3)
+                nph, _ = phases(pn, nd_step, 5)
+                key = f"{workload}_dedupe{int(not bool(args.dedupe))}"
+                workloads[key] = {"workload": WORKLOAD_TEXT.get(workload, workload), "dedupe": int(not bool(args.dedupe)), "n_classes": pn.info["n_classes"],
+                                  "ms_per_step": ms_nd, "value": 2.0 * nnz / (ms_nd * 1e-3), "unit": "nnz/s", "phases_ms": nph,
+                                  "roofline": fp64_roofline(pn, w["glq"], nph["integrator_k2"], nph["sum"]),
+                                  "roofline_hbm": hbm_roofline(pn, [(0, nnz)], nph["scatter_k3"], nph["sum"], workload, int(not bool(args.dedupe)))}
+                del pn
+            except Exception as ex:  # pragma: no cover
+                workloads["dedupe_off"] = {"error": repr(ex)}
+
     extra = {}
     if rank == 0 and world == 1 and not args.no_extras:
-        # FP64 pipe denominators and the integrator's own roofline (the EXACT integrator is FP64-issue bound, not HBM bound)
-        try:
-            dfma, dmuladd = F.fp64_peak(local_rank, 0), F.fp64_peak(local_rank, 1)
-            extra["fp64_peak_gflops"] = {"dfma": dfma, "dmul_dadd": dmuladd}
-        except Exception as ex:  # pragma: no cover
-            extra["fp64_peak_error"] = str(ex)
-        # general-case series: every block integrated on its own (no bit-identical-block dedupe)
-        plan_nd = F.Plan(view, device=local_rank, dedupe=not bool(args.dedupe))
-        for _ in range(3):
-            plan_nd.assemble_device(glq, d_a.data_ptr(), d_b.data_ptr(), mode=mode, stream=stream.cuda_stream)
-        torch.cuda.synchronize()
-        reps = 5
-        plan_nd.set_phase_timing(True)
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        for _ in range(reps):
-            plan_nd.assemble_device(glq, d_a.data_ptr(), d_b.data_ptr(), mode=mode, stream=stream.cuda_stream)
-        f1.record(stream)
-        torch.cuda.synchronize()
-        ms_nd = f0.elapsed_time(f1) / reps
-        t_nd = plan_nd.last_timing(0)
-        # algorithmic FP64 issue slots of the EXACT contraction: per quadrature point 8 per same-direction pair (A: 3 mul + add,
-        # B: 3 mul + add), 3 per cross-direction pair (A only: 2 mul + add)
-        extra["other_dedupe_setting"] = {"dedupe": int(not bool(args.dedupe)), "ms_per_step": ms_nd, "value": 2.0 * nnz / (ms_nd * 1e-3), "unit": "nnz/s",
-                                         "integrator_ms": t_nd["integrator_ms"], "scatter_ms": t_nd["scatter_ms"], "n_classes": plan_nd.info["n_classes"]}
-        del plan_nd
-        # the other BASELINE.json configs that fit one GPU (parity-test cases, reported for context only): device-resident step time
-        others = {}
-        for wl in ("cfg2", "cfg4"):
-            try:
-                dom = build_product_domain(wl)
-                g = WORKLOADS[wl]["glq"]
-                gq = (F.gauss_quadrature_points(g), F.gauss_quadrature_points(g))
-                pl = F.Plan(dom.view(), device=local_rank, dedupe=bool(args.dedupe))
-                ta = torch.empty(pl.nnz, dtype=torch.float64, device=dev); tb = torch.empty_like(ta)
-                for _ in range(3):
-                    pl.assemble_device(gq, ta.data_ptr(), tb.data_ptr(), mode=mode, stream=stream.cuda_stream)
-                torch.cuda.synchronize()
-                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                g0.record(stream)
-                for _ in range(20):
-                    pl.assemble_device(gq, ta.data_ptr(), tb.data_ptr(), mode=mode, stream=stream.cuda_stream)
-                g1.record(stream)
-                torch.cuda.synchronize()
-                ms = g0.elapsed_time(g1) / 20
-                others[wl] = {"n_dofs": pl.n_dofs, "nnz_upper_per_matrix": pl.nnz, "n_classes": pl.info["n_classes"], "glq": [g, g], "ms_per_step": ms,
-                              "value": 2.0 * pl.nnz / (ms * 1e-3), "unit": "nnz/s"}
-                del pl, ta, tb
-            except Exception as ex:  # pragma: no cover
-                others[wl] = {"error": str(ex)}
-        extra["other_configs"] = others
-        # Q-scaling: the headline mesh with the reference's default quadrature (`glq_grid_dim = None` ->
-        # default_ngq(order) points per side, basis.rs:172-177) and cfg 4 with the second basis space (HierMaxOrtho)
-        series = {}
-        try:
-            ng = int(F.default_ngq(max(domain.mesh.max_expansion_orders())))
-            gq = (F.gauss_quadrature_points(ng), F.gauss_quadrature_points(ng))
-            for _ in range(3):
-                plan.assemble_device(gq, d_a.data_ptr(), d_b.data_ptr(), mode=mode, stream=stream.cuda_stream)
-            torch.cuda.synchronize()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record(stream)
-            for _ in range(20):
-                plan.assemble_device(gq, d_a.data_ptr(), d_b.data_ptr(), mode=mode, stream=stream.cuda_stream)
-            g1.record(stream)
-            torch.cuda.synchronize()
-            ms = g0.elapsed_time(g1) / 20
-            series[workload + "_glq_default"] = {"glq": [ng, ng], "ms_per_step": ms, "value": 2.0 * nnz / (ms * 1e-3), "unit": "nnz/s"}
-            dom = build_product_domain("cfg4")
-            g = WORKLOADS["cfg4"]["glq"]
-            gq = (F.gauss_quadrature_points(g), F.gauss_quadrature_points(g))
-            pl = F.Plan(dom.view(), device=local_rank, dedupe=bool(args.dedupe))
-            ta = torch.empty(pl.nnz, dtype=torch.float64, device=dev); tb = torch.empty_like(ta)
-            for _ in range(3):
-                pl.assemble_device(gq, ta.data_ptr(), tb.data_ptr(), basis=F.HierMaxOrtho, mode=mode, stream=stream.cuda_stream)
-            torch.cuda.synchronize()
-            g0.record(stream)
-            for _ in range(20):
-                pl.assemble_device(gq, ta.data_ptr(), tb.data_ptr(), basis=F.HierMaxOrtho, mode=mode, stream=stream.cuda_stream)
-            g1.record(stream)
-            torch.cuda.synchronize()
-            ms = g0.elapsed_time(g1) / 20
-            series["cfg4_hier_max_ortho"] = {"glq": [g, g], "ms_per_step": ms, "value": 2.0 * pl.nnz / (ms * 1e-3), "unit": "nnz/s"}
-            del pl, ta, tb
-            # UniformFieldSpace::xy_fields (fields.rs:63-127) on the headline mesh, [16,16] points per leaf Elem,
-            # host solution vector in, host field arrays out (wall clock around the C-ABI call)
-            import ctypes as _C
-            import numpy as _np
-            dens, cap = 16, domain.mesh.num_elems
-            sol = _np.cos(_np.arange(domain.num_dofs) * 0.37) + 0.25
-            ids = _np.zeros(cap, dtype=_np.uint32)
-            fx = _np.zeros((cap, dens, dens)); fy = _np.zeros((cap, dens, dens))
-            n_out = _C.c_uint64()
-            ptr = lambda arr, t: arr.ctypes.data_as(_C.POINTER(t))
-
-            def fields_call():
-                st = F._L.fem2d_xy_fields(_C.byref(view.c), int(local_rank), F.HierPoly.kind, _C.c_uint32(dens), ptr(sol, _C.c_double), _C.c_uint64(cap),
-                                          _C.byref(n_out), ptr(ids, _C.c_uint32), ptr(fx, _C.c_double), ptr(fy, _C.c_double))
-                if st != 0:
-                    raise RuntimeError(F._L.fem2d_last_error().decode())
-
-            fields_call()
-            t0 = time.perf_counter()
-            for _ in range(3):
-                fields_call()
-            ms = (time.perf_counter() - t0) / 3 * 1e3
-            series[workload + "_xy_fields_16x16"] = {"leaf_elems": int(n_out.value), "ms_per_call_host_to_host": ms,
-                                                     "points_per_s": n_out.value * dens * dens / (ms * 1e-3),
-                                                     "note": "wall clock around fem2d_xy_fields: pageable host solution in, pageable host field arrays out"}
-        except Exception as ex:  # pragma: no cover
-            series["error"] = str(ex)
-        extra["other_series"] = series
+        extra = run_extras(F, torch, args, domain, view, plan, glq, d_a, d_b, mode, stream, dev, local_rank, workload, nnz, hbm_peak)
 
     # ---- end to end through the reference-facing call: host Domain view -> host CSR arrays ------------------------------------
     e2e = None
@@ -421,26 +406,27 @@ def run_ours(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        # the SAME workload, whole: ~30 s on 16 host cores (the serial ordered-map merge dominates, as in the reference's design)
         threads = os.cpu_count() or 1
-        r = cpu_port_run("cfg3_l4", threads)
+        r = cpu_port_run(workload, threads)
         cpu_baseline = {"value": 2.0 * r["nnz"] / r["seconds"], "unit": "nnz/s", "cores": threads, "kind": "port",
-                        "sample": f"cfg3 recipe at 4 T-levels ({r['dofs']} DoFs, {r['nnz']} upper entries/matrix): C++ restatement of the Rayon path, "
+                        "sample": f"the full workload, once ({r['dofs']} DoFs, {r['nnz']} upper entries/matrix): C++ restatement of the Rayon path, "
                                   f"{r['seconds']:.2f}s = integrate {r['integrate_s']:.2f}s ({threads} threads) + serial merge {r['merge_s']:.2f}s"}
 
     if rank == 0:
         line = {
             "metric": "assembly_nnz_per_s", "value": value, "unit": "nnz/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{workload}: test_mesh_a.json, Orders(6,6), 6x global T (BASELINE.json configs[2]), HierPoly/CurlCurl/L2Inner, GLQ [8,8]"
-                       if workload == "cfg3" else workload,
+            "config": {"workload": WORKLOAD_TEXT.get(workload, workload),
                        "mode": args.mode, "dedupe": int(args.dedupe), "n_dofs": info["n_dofs"], "nnz_upper_per_matrix": nnz, "n_pairs": info["n_pairs"],
                        "n_classes": info["n_classes"], "nnz_counted": "2 x nnz_upper (A and B)",
                        "l2_policy": "no flush: each step streams > 0.92 GB (A/B value arrays + source map) >> 126 MB L2",
                        "parallelism": f"row blocks x{world} (Elem-type rows + edge-type rows per rank), no collective" if world > 1 else "single GPU"},
-            "phases_ms": {"sampler_k1": float(k1_ms), "integrator_k2": float(k2_ms), "scatter_k3": float(k3_ms), "sum": float(tot_ms),
-                          "ms_per_step_with_phase_events": float(ms_step_events),
-                          "note": f"{n_back} extra steps with per-phase events on, right after the timed region"},
+            "phases_ms": dict(ph, note="extra steps with per-phase events on, right after the timed region"),
             "roofline": roofline,
+            "roofline_fp64": workloads.get("hp1m", {}).get("roofline"),
+            "workloads": workloads,
+            "fp64_peak": fp64,
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "gpu_launches": int(launches_per_step * args.steps),
@@ -451,6 +437,116 @@ def run_ours(args):
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def run_extras(F, torch, args, domain, view, plan, glq, d_a, d_b, mode, stream, dev, local_rank, workload, nnz, hbm_peak):
+    """Context series (N = 1 only): the other BASELINE configs that fit one GPU, Q-scaling, the second basis space, xy_fields, and the
+    re-ordered integrator modes with their own HBM roofline and both tolerance verdicts."""
+    import numpy as np
+    extra = {}
+
+    def time_plan(pl, gq, a, b, reps=20, **kw):
+        for _ in range(3):
+            pl.assemble_device(gq, a.data_ptr(), b.data_ptr(), stream=stream.cuda_stream, **kw)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(reps):
+            pl.assemble_device(gq, a.data_ptr(), b.data_ptr(), stream=stream.cuda_stream, **kw)
+        g1.record(stream)
+        torch.cuda.synchronize()
+        return g0.elapsed_time(g1) / reps
+
+    others = {}
+    for wl in ("cfg2", "cfg4"):
+        try:
+            dom = build_product_domain(wl)
+            g = WORKLOADS[wl]["glq"]
+            gq = (F.gauss_quadrature_points(g), F.gauss_quadrature_points(g))
+            pl = F.Plan(dom.view(), device=local_rank, dedupe=bool(args.dedupe))
+            ta = torch.empty(pl.nnz, dtype=torch.float64, device=dev); tb = torch.empty_like(ta)
+            ms = time_plan(pl, gq, ta, tb, mode=mode)
+            others[wl] = {"n_dofs": pl.n_dofs, "nnz_upper_per_matrix": pl.nnz, "n_classes": pl.info["n_classes"], "glq": [g, g], "ms_per_step": ms,
+                          "value": 2.0 * pl.nnz / (ms * 1e-3), "unit": "nnz/s"}
+            if wl == "cfg4":
+                ms2 = time_plan(pl, gq, ta, tb, mode=mode, basis=F.HierMaxOrtho)
+                others["cfg4_hier_max_ortho"] = {"glq": [g, g], "ms_per_step": ms2, "value": 2.0 * pl.nnz / (ms2 * 1e-3), "unit": "nnz/s"}
+            del pl, ta, tb
+        except Exception as ex:  # pragma: no cover
+            others[wl] = {"error": str(ex)}
+    extra["other_configs"] = others
+    series = {}
+    try:
+        # Q-scaling (SURVEY 8d): the headline mesh with the reference's default quadrature (`glq_grid_dim = None` -> default_ngq(order)
+        # points per side, basis.rs:172-177)
+        ng = int(F.default_ngq(max(domain.mesh.max_expansion_orders())))
+        gq = (F.gauss_quadrature_points(ng), F.gauss_quadrature_points(ng))
+        ms = time_plan(plan, gq, d_a, d_b, mode=mode)
+        series[workload + "_glq_default"] = {"glq": [ng, ng], "ms_per_step": ms, "value": 2.0 * nnz / (ms * 1e-3), "unit": "nnz/s"}
+        # SURVEY 8f row 1: UniformFieldSpace::xy_fields (fields.rs:63-127) on the headline mesh, [16,16] points per leaf Elem,
+        # host solution vector in, host field arrays out (wall clock around the C-ABI call)
+        import ctypes as _C
+        dens, cap = 16, domain.mesh.num_elems
+        sol = np.cos(np.arange(domain.num_dofs) * 0.37) + 0.25
+        ids = np.zeros(cap, dtype=np.uint32)
+        fx = np.zeros((cap, dens, dens)); fy = np.zeros((cap, dens, dens))
+        n_out = _C.c_uint64()
+        ptr = lambda arr, t: arr.ctypes.data_as(_C.POINTER(t))
+
+        def fields_call():
+            st = F._L.fem2d_xy_fields(_C.byref(view.c), int(local_rank), F.HierPoly.kind, _C.c_uint32(dens), ptr(sol, _C.c_double), _C.c_uint64(cap),
+                                      _C.byref(n_out), ptr(ids, _C.c_uint32), ptr(fx, _C.c_double), ptr(fy, _C.c_double))
+            if st != 0:
+                raise RuntimeError(F._L.fem2d_last_error().decode())
+
+        fields_call()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fields_call()
+        ms = (time.perf_counter() - t0) / 3 * 1e3
+        series[workload + "_xy_fields_16x16"] = {"leaf_elems": int(n_out.value), "ms_per_call_host_to_host": ms,
+                                                 "points_per_s": n_out.value * dens * dens / (ms * 1e-3),
+                                                 "note": "wall clock around fem2d_xy_fields: pageable host solution in, pageable host field arrays out"}
+    except Exception as ex:  # pragma: no cover
+        series["error"] = str(ex)
+    extra["other_series"] = series
+    # re-ordered integrator modes (opt-in, never the default): time, HBM roofline of the whole step, and both tolerance verdicts against
+    # the EXACT (reference-order) values of the same plan
+    fast = {}
+    try:
+        pn = F.Plan(view, device=local_rank, dedupe=False)
+        ref_a = torch.empty(nnz, dtype=torch.float64, device=dev); ref_b = torch.empty_like(ref_a)
+        pn.assemble_device(glq, ref_a.data_ptr(), ref_b.data_ptr(), mode=F.MODE_EXACT, stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        for name, md in (("sumfact", F.MODE_SUMFACT), ("dmma", F.MODE_DMMA)):
+            ms = time_plan(pn, glq, d_a, d_b, reps=10, mode=md)
+            pn.set_phase_timing(True)
+            pn.assemble_device(glq, d_a.data_ptr(), d_b.data_ptr(), mode=md, stream=stream.cuda_stream)
+            torch.cuda.synchronize()
+            t = pn.last_timing(0)
+            pn.set_phase_timing(False)
+            verdict = {}
+            for nm, got, ref in (("A", d_a, ref_a), ("B", d_b, ref_b)):
+                err = (got - ref).abs()
+                scale = float(ref.abs().max())
+                lit = int((err > torch.clamp(1e-12 * ref.abs(), min=1e-14)).sum())
+                sca = int((err > torch.clamp(1e-12 * ref.abs(), min=1e-14 * scale)).sum())
+                verdict[nm] = {"violations_literal_1e-12_rel_1e-14_abs": lit, "violations_scale_aware_floor_1e-14_x_max": sca, "max_abs": scale,
+                               "max_abs_err": float(err.max())}
+            # bytes the step must move: V written by the integrator and read by the scatter (16 B per pair, dedupe off) + A, B out + source map
+            v_bytes = 16.0 * pn.info["n_values"]
+            step_bytes = 2 * v_bytes + 16.0 * nnz + pn.source_map_info()["map_bytes"]
+            fast[name] = {"dedupe": 0, "ms_per_step": ms, "value": 2.0 * nnz / (ms * 1e-3), "unit": "nnz/s", "integrator_ms": t["integrator_ms"],
+                          "scatter_ms": t["scatter_ms"],
+                          "roofline": {"bound": "hbm", "kernel": f"{name} integrator + scatter (whole step)", "achieved": step_bytes / (ms * 1e-3) / 1e9,
+                                       "peak": hbm_peak, "unit": "GB/s", "frac": step_bytes / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                                       "algorithmic_bytes_per_step": step_bytes},
+                          "tolerance_vs_exact_mode": verdict}
+        del pn, ref_a, ref_b
+    except Exception as ex:  # pragma: no cover
+        fast["error"] = repr(ex)
+    extra["reordered_modes"] = fast
+    return extra
 
 
 def rank_ranges(plan, world, rank):
@@ -546,6 +642,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-second", action="store_true", help="skip the hp1m / dedupe-off first-class second results")
     ap.add_argument("--emulate-world", type=int, default=1)
     ap.add_argument("--emulate-rank", type=int, default=0)
     args = ap.parse_args()

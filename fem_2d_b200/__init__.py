@@ -72,10 +72,10 @@ class _View(C.Structure):
 
 # Every symbol declared in include/fem2d.h and include/fem2d_host.h (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "fem2d_symbolic", "fem2d_plan_free", "fem2d_plan_info", "fem2d_plan_check_work_items", "fem2d_plan_source_map_info", "fem2d_plan_row_offsets", "fem2d_plan_pattern_transfer_info", "fem2d_plan_pattern", "fem2d_plan_pattern_device",
+    "fem2d_symbolic", "fem2d_plan_free", "fem2d_plan_info", "fem2d_plan_check_work_items", "fem2d_plan_work_info", "fem2d_plan_source_map_info", "fem2d_plan_row_offsets", "fem2d_plan_pattern_transfer_info", "fem2d_plan_pattern", "fem2d_plan_pattern_device",
     "fem2d_assemble_device", "fem2d_assemble_device_ranges", "fem2d_plan_row_blocks_split", "fem2d_assemble_ranges", "fem2d_assemble", "fem2d_galerkin_sample_gep_hcurl", "fem2d_plan_row_blocks",
     "fem2d_plan_last_timing", "fem2d_plan_timing", "fem2d_plan_set_phase_timing", "fem2d_assemble_range", "fem2d_host_alloc", "fem2d_host_free", "fem2d_xy_fields", "fem2d_fp64_peak",
-    "fem2d_device_count", "fem2d_status_string", "fem2d_last_error", "fem2d_version",
+    "fem2d_petsc_aij_size", "fem2d_petsc_aij_image", "fem2d_write_petsc_aij", "fem2d_device_count", "fem2d_status_string", "fem2d_last_error", "fem2d_version",
 ]
 HOST_ABI_SYMBOLS = [
     "fem2dh_last_error", "fem2dh_mesh_from_file", "fem2dh_mesh_from_arrays", "fem2dh_mesh_unit", "fem2dh_mesh_clone",
@@ -603,6 +603,20 @@ class Plan:
         _ck(_L.fem2d_plan_check_work_items(self._h, out))
         return {"tiles": int(out[0]), "same_tiles": int(out[1]), "slots": int(out[2]), "violations": int(out[3])}
 
+    def work_info(self) -> dict:
+        """fem2d_plan_work_info: pairs / micro-tiles one numeric call integrates (every class once)."""
+        out = (C.c_uint64 * 8)()
+        _ck(_L.fem2d_plan_work_info(self._h, out))
+        keys = ["same_pairs", "cross_pairs", "same_tiles", "cross_tiles", "pairs_per_same_tile", "pairs_per_cross_tile", "staged_columns", "work_items"]
+        return {k: int(out[i]) for i, k in enumerate(keys)}
+
+    def fp64_lane_ops(self, nu: int, nv: int) -> int:
+        """FP64 operations (lane-ops, none of them fusable) of the reference's per-pair quadrature for one numeric call: per same-direction pair
+        8 per point (A: 3 products + 1 sum, B: the same) + 4 per quadrature row (solution += inner * u_w, twice); per cross-direction pair 3 per
+        point + 2 per row.  Tile padding, slab staging and the final coefficient products are NOT counted."""
+        w = self.work_info()
+        return w["same_pairs"] * (8 * nu * nv + 4 * nu) + w["cross_pairs"] * (3 * nu * nv + 2 * nu)
+
     def source_map_info(self) -> dict:
         """fem2d_plan_source_map_info: size of the packed source map the scatter kernel reads."""
         info = (C.c_uint64 * 4)()
@@ -695,6 +709,19 @@ class Plan:
         _ck(_L.fem2d_assemble_ranges(self._h, basis.kind, a.kind, b.kind, int(mode), _p(up, C.c_double), _p(uw, C.c_double), C.c_uint32(len(up)),
                                      _p(vp, C.c_double), _p(vw, C.c_double), C.c_uint32(len(vp)), C.c_uint32(len(ranges)), _p(bg, C.c_uint64),
                                      _p(en, C.c_uint64), C.c_void_p(rows_ptr or None), C.c_void_p(cols_ptr or None), C.c_void_p(a_ptr), C.c_void_p(b_ptr)))
+
+    def petsc_aij_image(self, d_vals: int) -> np.ndarray:
+        """fem2d_petsc_aij_image: the PETSc AIJ binary image (sparse_matrix.rs:184-264) of the matrix whose nnz_upper values sit at the DEVICE
+        pointer `d_vals`, built on the GPU; returns the bytes."""
+        nbytes = C.c_uint64(); nf = C.c_uint64()
+        _ck(_L.fem2d_petsc_aij_size(self._h, C.byref(nbytes), C.byref(nf)))
+        img = np.empty(nbytes.value, dtype=np.uint8)
+        _ck(_L.fem2d_petsc_aij_image(self._h, C.c_void_p(d_vals), img.ctypes.data_as(C.c_void_p), C.c_uint64(nbytes.value)))
+        return img
+
+    def write_petsc_aij(self, d_vals: int, path: str) -> None:
+        """fem2d_write_petsc_aij: the same image straight into a file."""
+        _ck(_L.fem2d_write_petsc_aij(self._h, C.c_void_p(d_vals), os.fsencode(path)))
 
     def set_phase_timing(self, on: bool = True):
         """fem2d_plan_set_phase_timing: record per-phase CUDA events in the following numeric calls (off by default)."""

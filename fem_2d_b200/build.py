@@ -29,6 +29,7 @@ UNITS = [
     ("kernels_scatter.cu", ["-fmad=false"]),
     ("kernels_fast.cu", []),
     ("fields.cu", ["-fmad=false"]),
+    ("petsc.cu", []),
     ("plan_host.cpp", []),
     ("host/host_capi.cpp", []),
 ]

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
 #include <cstring>
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -241,6 +242,24 @@ int fem2d_plan_check_work_items(const fem2d_plan* plan, uint64_t out[4]) {
     }
     for (auto& s : seen) for (uint8_t k : s) if (k != 1) bad++;
     out[0] = n_tiles; out[1] = n_same; out[2] = n_slots; out[3] = bad;
+    return FEM2D_OK;
+}
+
+int fem2d_plan_work_info(const fem2d_plan* plan, uint64_t out[8]) {
+    if (!plan || !out) return fail(FEM2D_ERR_BAD_ARGUMENT, "null argument");
+    using namespace fem2d;
+    const HostPlan& H = plan->p.host;
+    std::memset(out, 0, 8 * sizeof(uint64_t));
+    for (const ClassDesc& c : H.classes) {
+        const ListDesc& LP = H.lists[c.listP]; const ListDesc& LQ = H.lists[c.listQ];
+        const uint64_t uP = LP.nU, vP = LP.n - LP.nU, uQ = LQ.nU, vQ = LQ.n - LQ.nU;
+        if (c.local) { out[0] += uP * (uP + 1) / 2 + vP * (vP + 1) / 2; out[1] += uP * vQ; }   // a <= b of a symmetric block (galerkin.rs:91-127)
+        else { out[0] += uP * uQ + vP * vQ; out[1] += uP * vQ + vP * uQ; }                      // galerkin.rs:138-178
+        const SubBlocks sb = make_subblocks(LP.n, LP.nU, LQ.n, LQ.nU, c.local, H.tile_p);
+        out[2] += sb.cnt[0] + sb.cnt[3]; out[3] += sb.cnt[1] + sb.cnt[2];
+        out[6] += (uint64_t)LP.n + (c.local ? 0u : LQ.n);
+    }
+    out[4] = (uint64_t)H.tile_p * MT_Q; out[5] = (uint64_t)H.tile_p * MT_QX; out[7] = H.items.size();
     return FEM2D_OK;
 }
 
@@ -524,6 +543,51 @@ int fem2d_galerkin_sample_gep_hcurl(const fem2d_domain_view* view, int device, i
     return st;
 }
 
+int fem2d_petsc_aij_size(fem2d_plan* plan, uint64_t* bytes, uint64_t* nnz_full) {
+    if (!plan) return fail(FEM2D_ERR_BAD_ARGUMENT, "null plan");
+    if (plan->p.device < 0) return fail(FEM2D_ERR_NO_DEVICE, "host-only plan");
+    std::string err;
+    const int st = fem2d::device_petsc_prepare(plan->p, err);
+    if (st != FEM2D_OK) return fail(st, err);
+    if (bytes) *bytes = 16 + 4ull * plan->p.host.n_dofs + 12ull * plan->p.aij_nnz_full;
+    if (nnz_full) *nnz_full = plan->p.aij_nnz_full;
+    return FEM2D_OK;
+}
+
+int fem2d_petsc_aij_image(fem2d_plan* plan, const double* d_vals, void* host_image, uint64_t capacity) {
+    if (!plan || !d_vals || !host_image) return fail(FEM2D_ERR_BAD_ARGUMENT, "null argument");
+    if (plan->p.device < 0) return fail(FEM2D_ERR_NO_DEVICE, "host-only plan");
+    std::string err;
+    void* img = nullptr; uint64_t bytes = 0;
+    const int st = fem2d::device_petsc_image(plan->p, d_vals, &img, &bytes, err);
+    if (st != FEM2D_OK) return fail(st, err);
+    if (bytes > capacity) { fem2d::dev_free(img); return fail(FEM2D_ERR_BAD_ARGUMENT, "image capacity too small (see fem2d_petsc_aij_size)"); }
+    const cudaError_t e = cudaMemcpy(host_image, img, bytes, cudaMemcpyDeviceToHost);
+    fem2d::dev_free(img);
+    if (e != cudaSuccess) return fail(FEM2D_ERR_CUDA, cudaGetErrorString(e));
+    return FEM2D_OK;
+}
+
+int fem2d_write_petsc_aij(fem2d_plan* plan, const double* d_vals, const char* path) {
+    if (!path) return fail(FEM2D_ERR_BAD_ARGUMENT, "null path");
+    uint64_t bytes = 0;
+    int st = fem2d_petsc_aij_size(plan, &bytes, nullptr);
+    if (st != FEM2D_OK) return st;
+    void* host = nullptr;
+    if (cudaMallocHost(&host, bytes) != cudaSuccess) { cudaGetLastError(); return fail(FEM2D_ERR_OUT_OF_MEMORY, "pinned host allocation failed"); }
+    st = fem2d_petsc_aij_image(plan, d_vals, host, bytes);
+    if (st == FEM2D_OK) {
+        FILE* f = std::fopen(path, "wb");
+        if (!f) st = fail(FEM2D_ERR_BAD_ARGUMENT, std::string("cannot open ") + path);
+        else {
+            if (std::fwrite(host, 1, bytes, f) != bytes) st = fail(FEM2D_ERR_INTERNAL, "short write");
+            std::fclose(f);
+        }
+    }
+    cudaFreeHost(host);
+    return st;
+}
+
 void* fem2d_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -537,6 +601,14 @@ int fem2d_fp64_peak(int device, int kind, double* gflops) {
     if (st != FEM2D_OK) return st;
     CKS(cudaSetDevice(device));
     CKS(fem2d::fp64_peak(kind, gflops));
+    return FEM2D_OK;
+}
+
+/* tuning builds only (-DFEM2D_WS_PROFILE; zeros otherwise): cycle counters of the warp-specialised integrator; not part of include/fem2d.h */
+int fem2d_debug_ws_profile(uint64_t out[8], int reset) {
+    unsigned long long t[8];
+    CKS(fem2d::ws_profile(t, reset));
+    for (int k = 0; k < 8; k++) out[k] = t[k];
     return FEM2D_OK;
 }
 

@@ -347,6 +347,7 @@ int device_symbolic(Plan& P, std::string& err) {
     const size_t o_tabs = desc.reserve(H.tables.size() * sizeof(TableDesc)), o_grams = desc.reserve(H.grams.size() * sizeof(GramDesc));
     const size_t o_items = desc.reserve(H.items.size() * sizeof(WorkItem));
     const size_t o_glq = desc.reserve(4 * 128 * sizeof(double));
+    const size_t o_ctr = desc.reserve(256);
     std::vector<uint32_t> h_voff(H.classes.size() + 1), h_mtoff(H.classes.size() + 1);
     {
         uint64_t mt = 0;
@@ -398,6 +399,7 @@ int device_symbolic(Plan& P, std::string& err) {
     P.d_spec_i = at<uint8_t>(P.d_desc_arena, o_si); P.d_spec_j = at<uint8_t>(P.d_desc_arena, o_sj);
     P.d_tables = at<TableDesc>(P.d_desc_arena, o_tabs); P.d_grams = at<GramDesc>(P.d_desc_arena, o_grams);
     P.d_items = at<WorkItem>(P.d_desc_arena, o_items); P.d_glq = at<double>(P.d_desc_arena, o_glq);
+    P.d_work_counter = at<uint32_t>(P.d_desc_arena, o_ctr);
     P.d_class_voff = at<uint32_t>(P.d_desc_arena, o_voff); P.d_class_mtoff = at<uint32_t>(P.d_desc_arena, o_mtoff);
     DevBlock* d_blocks = at<DevBlock>(scratch, s_desc + (o_blocks - desc_plan_bytes));
     uint32_t* d_canon = at<uint32_t>(scratch, s_desc + (o_canon - desc_plan_bytes));
@@ -577,7 +579,7 @@ int device_range_items(Plan& P, uint32_t n_ranges, const uint64_t* begins, const
     // items: per class, the runs of needed tiles (gaps of up to 2 tiles are bridged) packed into CTAs of <= ITEM_MAX_RANGES runs and
     // <= 2 * K2_THREADS tiles; every item records which function columns its tiles touch so it stages only those.
     std::vector<WorkItem> items;
-    const uint32_t cap = K2_ROUNDS * K2_THREADS - 31, gap = 2, tp = P.host.tile_p;   // tiles; + up to 31 slots of warp alignment (item_slots)
+    const uint32_t cap = K2_ROUNDS * (P.host.use_ws && P.host.tile_p == (uint32_t)K2_TILE_P ? K2_WS_CONS_WARPS * 32 : K2_THREADS) - 31, gap = 2, tp = P.host.tile_p;   // tiles; + up to 31 slots of warp alignment (item_slots)
     uint64_t needed = 0, off = 0;
     std::vector<std::pair<uint32_t, uint32_t>> runs, cur;
     for (uint32_t c = 0; c < P.host.classes.size(); c++) {
@@ -729,7 +731,7 @@ void device_plan_release(Plan& P) {
     pinned_release(P.h_row_ptr, P.h_row_ptr_cap); P.h_row_ptr = nullptr;
     pinned_release(P.h_col_run_slot, P.h_col_run_cap[0]); pinned_release(P.h_col_run_col, P.h_col_run_cap[1]);
     P.h_col_run_slot = P.h_col_run_col = nullptr;
-    dev_free(P.d_range_items);
+    dev_free(P.d_range_items); dev_free(P.d_aij_arena);
     dev_free(P.d_V); dev_free(P.d_tabs); dev_free(P.d_gram); dev_free(P.d_dmma_items); dev_free(P.d_out_a); dev_free(P.d_out_b);
     for (int r = 0; r < Plan::RING; r++) for (int k = 0; k < 4; k++) if (P.ev[r][k]) cudaEventDestroy(P.ev[r][k]);
 }

@@ -61,6 +61,7 @@ struct Plan {
     double h_glq[512] = {};     // host copy of what d_glq holds (skips the upload when the caller passes the same nodes again)
     bool glq_valid = false;
     double* d_gram = nullptr;   // fast modes scratch
+    uint32_t* d_work_counter = nullptr;  // work-item counter of the persistent integrator (desc arena; reset by the sampler kernel)
     uint32_t* d_class_voff = nullptr;    // [n_classes + 1] first V entry of each class (desc arena)
     uint32_t* d_class_mtoff = nullptr;   // [n_classes + 1] first micro-tile of each class in the plan-wide tile numbering
     uint64_t total_mt = 0;
@@ -74,6 +75,11 @@ struct Plan {
     void* d_dmma_items = nullptr;   // tile work items of the DMMA integrator (built on first use)
     uint32_t n_dmma_items = 0;
     size_t gram_capacity = 0;
+    // PETSc AIJ emission (petsc.cu): transpose of the strictly upper pattern and full-row offsets, built on first use
+    void* d_aij_arena = nullptr;
+    uint32_t *d_aij_lower_cnt = nullptr, *d_aij_lower_start = nullptr, *d_aij_counts = nullptr, *d_aij_full_start = nullptr, *d_aij_lower_slot = nullptr;
+    uint32_t aij_n_lower = 0;
+    uint64_t aij_nnz_full = 0;
     double* d_out_a = nullptr;  // staging for host-output calls
     double* d_out_b = nullptr;
 
@@ -128,10 +134,15 @@ cudaError_t launch_k2_exact(const Plan& plan, const WorkItem* d_items, uint32_t 
 // slab row (pad4(U) + pad4(V) functions of P, + of Q unless local) among the classes of each part.
 ItemSplit split_items(const HostPlan& host, const std::vector<WorkItem>& items);
 cudaError_t fp64_peak(int kind, double* gflops);
+cudaError_t ws_profile(unsigned long long out[8], int reset);   // tuning builds (-DFEM2D_WS_PROFILE): cycle counters of k2_ws_kernel
 
 // kernels_fast.cu
 cudaError_t launch_k2_sumfact(Plan& plan, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches);
 cudaError_t launch_k2_dmma(Plan& plan, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches);
+
+// petsc.cu
+int device_petsc_prepare(Plan& plan, std::string& err);
+int device_petsc_image(Plan& plan, const double* d_vals, void** d_image, uint64_t* bytes, std::string& err);
 
 // kernels_scatter.cu
 cudaError_t launch_k3_scatter(const Plan& plan, uint32_t n_ranges, const uint64_t* begins, const uint64_t* ends, double* d_a, double* d_b, int selA, int selB,

@@ -28,7 +28,10 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------------- K1
 // One CTA per table, one thread per point.  Output layout: out[((arr * NO) + order) * NPT + point], arr: 0 N, 1 N', 2 T, 3 T'.
 __global__ void k1_tables_kernel(const TableDesc* __restrict__ tabs, double* __restrict__ out, uint32_t NO, uint32_t NPT,
-                                 const double* __restrict__ glq, uint32_t nu, uint32_t nv, uint32_t i_max, uint32_t j_max, int basis) {
+                                 const double* __restrict__ glq, uint32_t nu, uint32_t nv, uint32_t i_max, uint32_t j_max, int basis,
+                                 uint32_t* __restrict__ work_counter) {
+    // the persistent integrator (k2_ws_kernel) hands out its work items through this counter; every numeric call starts at 0
+    if (blockIdx.x == 0 && threadIdx.x == 0) *work_counter = 0u;
     // programmatic dependent launch: let the integrator's CTAs start their prologue (work item, class, tile decode) right away;
     // they wait for this grid's completion (cudaGridDependencySynchronize) before they read the tables
     cudaTriggerProgrammaticLaunchCompletion();
@@ -52,6 +55,7 @@ struct K2Args {
     // launch); 0: it follows the first integrator grid, which it does not depend on -- it runs alongside it and waits for it only
     // before exiting, so that a grid waiting on this one has transitively waited on both.
     int follows_sampler;
+    uint32_t list_cap;   // warp-specialised integrator: bytes reserved per cached BasisSpec order list (>= the longest list, multiple of 16)
 };
 
 __device__ __forceinline__ uint32_t pad4(uint32_t x) { return (x + 3u) & ~3u; }
@@ -341,6 +345,445 @@ __global__ void __launch_bounds__(NT, NT == K2_THREADS ? K2_MIN_CTAS : K2_SMALL_
     if (!g.follows_sampler) cudaGridDependencySynchronize();   // do not complete before the first integrator grid has
 }
 
+
+// ---------------------------------------------------------------------------------------------------- K2, warp-specialised
+// Persistent form of the integrator for the throughput shape (4-row tiles): K2_WS_CONS_WARPS contraction warps and one staging warp
+// per CTA, two CTAs per SM.  The staging warp takes work items from a global counter, computes the item's class constants, and fills
+// a ring of K2_WS_NBUF slab buffers chunk by chunk; the contraction warps consume the chunks in the same order.  Hand-over is by
+// mbarriers (full[b]: one arrival by the staging warp; empty[b]: one arrival per contraction warp), so the contraction warps never
+// stage and never meet a CTA-wide barrier: while they contract chunk k the staging warp prepares chunk k+1 -- of the same round, of
+// the next round, or of the next work item (its descriptor loads, FP64 quotients and first slab included).  Same tiles, same
+// per-pair operation order as k2_exact_kernel: results are bit-identical.
+struct alignas(16) WsCtx {
+    WorkItem it;
+    SubBlocks sb;
+    double ratio_uv, ratio_vu, maxdet, coefA, coefB;
+    unsigned long long v_off;
+    uint32_t nP, nUP, nQ, nUQ, strideP, strideQ, local, chunk_rows, n_slots, gap, end, pad;
+};
+constexpr int K2_WS_NCTX = K2_WS_NBUF + 2;   // item contexts in flight: the staging warp runs at most NBUF chunks (>= items) ahead
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {   // release at CTA scope: the arriving thread's prior writes are visible to whoever observes the phase flip
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1, %2;\n"   // suspends up to the hint instead of spinning
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+        : "memory");
+}
+
+// One function column of a staging chunk, NB points x NR quadrature rows per step (see ws_stage_chunk).  Straight-line code: a step
+// that reaches past the last point or row clamps its indices for loads AND stores, i.e. it recomputes the last point / row and stores
+// the identical value again, so the body carries no guards.
+template <int NB, int NR>
+__device__ __forceinline__ void ws_stage_column(const double* __restrict__ colA, const double* __restrict__ colB, const double* __restrict__ rowA,
+                                                const double* __restrict__ rowB, double jj, double ps, bool scaled, int flip, double* __restrict__ sC,
+                                                double* __restrict__ sF, uint32_t stride, uint32_t nv, uint32_t nrow) {
+    for (uint32_t nb = 0; nb < nv; nb += NB) {
+        double ca[NB], cb[NB];
+        uint32_t noff[NB];   // slab offset of point n of a row
+#pragma unroll
+        for (int q = 0; q < NB; q++) { const uint32_t n = min(nb + q, nv - 1); ca[q] = colA[n]; cb[q] = colB[n]; noff[q] = n * stride; }
+        for (uint32_t r = 0; r < nrow; r += NR) {
+            double fa[NR], fb[NR], t[NR][NB], f[NR][NB];
+            uint32_t roff[NR];
+#pragma unroll
+            for (int k = 0; k < NR; k++) { const uint32_t rk = min(r + k, nrow - 1); fa[k] = rowA[rk]; fb[k] = jj * rowB[rk]; roff[k] = rk * nv * stride; }
+#pragma unroll
+            for (int k = 0; k < NR; k++)
+#pragma unroll
+                for (int q = 0; q < NB; q++) t[k][q] = fa[k] * ca[q];
+#pragma unroll
+            for (int k = 0; k < NR; k++)
+#pragma unroll
+                for (int q = 0; q < NB; q++) t[k][q] = jj * t[k][q];
+            if (scaled) {
+#pragma unroll
+                for (int k = 0; k < NR; k++)
+#pragma unroll
+                    for (int q = 0; q < NB; q++) t[k][q] = t[k][q] * ps;
+            }
+#pragma unroll
+            for (int k = 0; k < NR; k++)
+#pragma unroll
+                for (int q = 0; q < NB; q++) f[k][q] = fb[k] * cb[q];
+#pragma unroll
+            for (int k = 0; k < NR; k++)
+#pragma unroll
+                for (int q = 0; q < NB; q++) {
+                    sC[roff[k] + noff[q]] = __hiloint2double(__double2hiint(t[k][q]) ^ flip, __double2loint(t[k][q]));
+                    sF[roff[k] + noff[q]] = f[k][q];
+                }
+        }
+    }
+}
+
+// Stages the slab columns an item needs for the quadrature rows [m0, m0 + nrow) with the 32 lanes of one warp (same values, same
+// operation order as the staging pass of k2_exact_kernel).  One task = one function column for the whole chunk: its (i, j) orders
+// are looked up once, the v-axis table values of WS_NB points are held in registers while the rows m run inside, so the inner body
+// is four FP64 operations and two shared-memory stores per (function, point) with no loads in the dependent chain.
+__device__ __forceinline__ void ws_stage_chunk(const K2Args& g, const WsCtx& c, const ClassDesc& cd, double jiuP, double jivP, double jiuQ, double jivQ,
+                                               const double* s_tab, const uint8_t* s_spec, double* buf, uint32_t m0, uint32_t nrow, uint32_t lane) {
+    const uint32_t nv = g.nv, AS = g.NO * g.NPT;
+    const uint32_t chunk = c.chunk_rows * nv;
+    double* s_CP = buf; double* s_FP = s_CP + (size_t)chunk * c.strideP;
+    double* s_CQ = c.local ? s_CP : s_FP + (size_t)chunk * c.strideP;
+    double* s_FQ = c.local ? s_FP : s_CQ + (size_t)chunk * c.strideQ;
+    for (int side = 0; side < (c.local ? 1 : 2); side++) {
+        const uint32_t stride = side ? c.strideQ : c.strideP, nF = side ? c.nQ : c.nP, nUF = side ? c.nUQ : c.nUP;
+        // table cache slots: 0 / 1 = the scaled u / v tables of a non-local P side, 2 / 3 = the unscaled tables (every Q side, local P sides)
+        const uint32_t slot_u = (side || c.local) ? 2u : 0u;
+        const double* tu = s_tab + (size_t)slot_u * 4 * AS;
+        const double* tv = s_tab + (size_t)(slot_u + 1) * 4 * AS;
+        const uint8_t* sp_i = s_spec + (size_t)(2 * side) * g.list_cap; const uint8_t* sp_j = sp_i + g.list_cap;
+        const double jiu = side ? jiuQ : jiuP, jiv = side ? jivQ : jivP;
+        // derivative scale = the OTHER function's para_scale (integrals.rs:44,47); Q's is (1,1), P's is (su,sv)
+        const double ps0 = side ? cd.su : 1.0, ps1 = side ? cd.sv : 1.0;
+        double* sC = side ? s_CQ : s_CP; double* sF = side ? s_FQ : s_FP;
+        const uint32_t padU = pad4(nUF);
+        for (int grp = 0; grp < 2; grp++) {
+            const uint32_t c_lo = c.it.stage[side][grp][0], c_hi = c.it.stage[side][grp][1];   // only the functions this item's tiles touch
+            for (uint32_t col = c_lo + lane; col < c_hi; col += 32) {
+                // a padding column of a 4-wide tile row takes the values of the group's last function: only pairs beyond the block's last
+                // row / column read it, and their results are never stored
+                const bool isU = col < padU;
+                const uint32_t a = isU ? min(col, nUF - 1) : nUF + min(col - padU, nF - nUF - 1);
+                const uint32_t i = sp_i[a], j = sp_j[a];
+                // U-directed: curl = -((jiu * (N_i(m) * T'_j(n))) * ps0), val = (jiu * N_i(m)) * T_j(n)        (basis.rs:225-242)
+                // V-directed: curl =   (jiv * (T'_i(m) * N_j(n))) * ps1,  val = (jiv * T_i(m)) * N_j(n)        (basis.rs:230-252)
+                const double* rowA = tu + (isU ? 0 : 3) * AS + i * g.NPT;   // factor of the curl taken at m: N_i | T'_i
+                const double* rowB = tu + (isU ? 0 : 2) * AS + i * g.NPT;   // factor of the value taken at m: N_i | T_i
+                const double* colA = tv + (isU ? 3 : 0) * AS + j * g.NPT;   // factor of the curl taken at n: T'_j | N_j
+                const double* colB = tv + (isU ? 2 : 0) * AS + j * g.NPT;   // factor of the value taken at n: T_j | N_j
+                const double jj = isU ? jiu : jiv, ps = isU ? ps0 : ps1;
+                const bool scaled = ps != 1.0;                 // x * 1.0 == x bit for bit: the product is skipped
+                const int flip = isU ? (int)0x80000000 : 0;    // IEEE negation = sign-bit flip, done in the integer pipe
+                // eight independent chains per step, written stage by stage so that the in-order issue of the single staging warp never
+                // waits on the 8-cycle FP64 latency: 4 points x 2 quadrature rows, then 4 points x the odd last row
+                const uint32_t npair = nrow & ~1u;
+                if (npair) ws_stage_column<4, 2>(colA, colB, rowA + m0, rowB + m0, jj, ps, scaled, flip, sC + col, sF + col, stride, nv, npair);
+                if (nrow & 1u) ws_stage_column<4, 1>(colA, colB, rowA + m0 + npair, rowB + m0 + npair, jj, ps, scaled, flip,
+                                                     sC + col + (size_t)npair * nv * stride, sF + col + (size_t)npair * nv * stride, stride, nv, 1u);
+            }
+        }
+    }
+}
+
+// One pass of a TP x 2 sub-tile over one quadrature row: inner += ((p * q) [* scale]) * v_w[n] for n = 0 .. nv-1 (glq.rs:24-28), then
+// solution += inner * u_w[m] (glq.rs:29).  A same-direction tile runs it twice per row (curl slabs with the uv / vu ratio for A, value
+// slabs with max(det) for B), a cross-direction tile twice on the curl slabs (columns 0-1, columns 2-3; no ratio factor,
+// integrals.rs:53-84).  Running the passes one after the other keeps a single set of inner accumulators live, which leaves the
+// scheduler the registers to interleave all eight chains of a pass and to fetch the next points' operands early.
+template <bool SCALE, int TP>
+__device__ __forceinline__ void ws_row_pass(const double* __restrict__ p, const double* __restrict__ q, uint32_t strideP, uint32_t strideQ,
+                                            const double* __restrict__ vw, uint32_t nv, double scale, double uw, double (&sol)[TP][MT_Q]) {
+    double in[TP][MT_Q];
+#pragma unroll
+    for (int r = 0; r < TP; r++)
+#pragma unroll
+        for (int c = 0; c < MT_Q; c++) in[r][c] = 0.0;
+#pragma unroll 4
+    for (uint32_t n = 0; n < nv; n++) {
+        double pv[TP], qv[MT_Q], t[TP][MT_Q];
+        load_rows<TP>(p, pv); load_rows<MT_Q>(q, qv);
+        const double w = vw[n];
+#pragma unroll
+        for (int r = 0; r < TP; r++)
+#pragma unroll
+            for (int c = 0; c < MT_Q; c++) t[r][c] = pv[r] * qv[c];
+        if (SCALE) {
+#pragma unroll
+            for (int r = 0; r < TP; r++)
+#pragma unroll
+                for (int c = 0; c < MT_Q; c++) t[r][c] = t[r][c] * scale;
+        }
+#pragma unroll
+        for (int r = 0; r < TP; r++)
+#pragma unroll
+            for (int c = 0; c < MT_Q; c++) t[r][c] = t[r][c] * w;
+#pragma unroll
+        for (int r = 0; r < TP; r++)
+#pragma unroll
+            for (int c = 0; c < MT_Q; c++) in[r][c] = in[r][c] + t[r][c];
+        p += strideP; q += strideQ;
+    }
+#pragma unroll
+    for (int r = 0; r < TP; r++)
+#pragma unroll
+        for (int c = 0; c < MT_Q; c++) sol[r][c] = sol[r][c] + in[r][c] * uw;
+}
+
+#ifdef FEM2D_WS_PROFILE
+// tuning build only: cycle counts summed over CTAs. 0 staging warp: item setup, 1 waiting for an empty buffer, 2 staging;
+// 3 contraction warp 0: waiting for a full buffer, 4 contracting (+ epilogue, decode); 5 items; 6 chunks
+__device__ unsigned long long g_ws_prof[8];
+#define WS_T(var) const long long var = clock64()
+#define WS_ADD(k, v) do { if (lane == 0) atomicAdd(&g_ws_prof[k], (unsigned long long)(v)); } while (0)
+#else
+#define WS_T(var)
+#define WS_ADD(k, v)
+#endif
+
+template <int TP>
+__global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const uint32_t n_items, uint32_t* __restrict__ work_counter) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr uint32_t CONS = K2_WS_CONS_WARPS * 32;
+    double* s_uw = smem;                       // [128]
+    double* s_vw = smem + 128;                 // [128]
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + 256);   // [NBUF]
+    uint64_t* s_empty = s_full + K2_WS_NBUF;                      // [NBUF]
+    WsCtx* s_ctx = reinterpret_cast<WsCtx*>(smem + 256 + 2 * K2_WS_NBUF);
+    static_assert(sizeof(WsCtx) % 16 == 0, "context ring keeps the slabs 16-byte aligned");
+    // staging-warp caches: four sampled tables (slots 0 / 1: scaled u / v tables of a non-local P side; 2 / 3: the unscaled u / v tables)
+    // and the (i, j) order lists of the current item's P and Q sides
+    const uint32_t AS4 = 4 * g.NO * g.NPT;
+    double* s_tab = smem + 256 + 2 * K2_WS_NBUF + K2_WS_NCTX * sizeof(WsCtx) / sizeof(double);
+    uint8_t* s_spec = reinterpret_cast<uint8_t*>(s_tab + 4 * (size_t)AS4);
+    double* s_slab = reinterpret_cast<double*>(s_spec + 4 * (size_t)g.list_cap);
+    const uint32_t buf_doubles = g.slab_doubles;   // per ring buffer
+    const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const uint32_t nu = g.nu, nv = g.nv, npts = nu * nv;
+
+    if (!g.follows_sampler) cudaTriggerProgrammaticLaunchCompletion();
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < K2_WS_NBUF; b++) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], K2_WS_CONS_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) s_uw[k] = g.glq[128 + k];
+    for (uint32_t k = threadIdx.x; k < nv; k += blockDim.x) s_vw[k] = g.glq[384 + k];
+    if (g.follows_sampler) {
+        cudaGridDependencySynchronize();   // the sampler's tables (and, transitively, the previous call's readers of V) are complete
+        cudaTriggerProgrammaticLaunchCompletion();
+    }
+    __syncthreads();
+
+    uint32_t stage = 0, phase = 0, ci = 0;
+    if (warp == 0) {
+        // ================================================================================================ staging warp
+        // (warp 0: the warp schedulers favour the oldest warp of a CTA, and staging must stay ahead of seven contraction warps)
+        for (uint32_t k = lane; k < 2 * AS4; k += 32) s_tab[2 * (size_t)AS4 + k] = g.tabs[k];   // tables 0 / 1: unscaled u / v points
+        uint32_t cached_u = 0xffffffffu, cached_v = 0xffffffffu;                                 // table ids held by slots 0 / 1
+        for (;;) {
+            WS_T(t_item0);
+            uint32_t idx = 0;
+            if (lane == 0) idx = atomicAdd(work_counter, 1u);
+            idx = __shfl_sync(0xffffffffu, idx, 0);
+            WsCtx& c = s_ctx[ci];
+            if (idx >= n_items) {   // end marker: travels through the ring like a chunk
+                if (lane == 0) c.end = 1u;
+                mbar_wait(&s_empty[stage], phase ^ 1u);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_full[stage]);
+                break;
+            }
+            const WorkItem it = g.items[idx];
+            const ClassDesc cd = g.classes[it.cls];
+            const uint32_t nP = cd.lp.n, nUP = cd.lp.nU, nQ = cd.lq.n, nUQ = cd.lq.nU;
+            const uint32_t strideP = pad4(nUP) + pad4(nP - nUP);
+            const uint32_t strideQ = cd.local ? strideP : pad4(nUQ) + pad4(nQ - nUQ);
+            // whole quadrature rows per chunk (the launch makes sure one row of the widest class fits a ring buffer)
+            const uint32_t chunk_rows = min(nu, buf_doubles / (2 * nv * (strideP + (cd.local ? 0u : strideQ))));
+            // per-class constants (HierCurlBasisFn::defined_over, basis.rs:395-413; M2D::det / inverse, space.rs:138-147): the nine
+            // FP64 quotients, one per lane
+            const double detP = cd.dxP * cd.dyP - 0.0 * 0.0, detQ = cd.dxQ * cd.dyQ - 0.0 * 0.0;
+            double quot = 0.0;
+            if (lane < 9) {
+                const uint32_t k = lane;
+                const double num = k == 0 ? cd.dyP : k == 1 ? cd.dxP : k == 2 ? cd.dyQ : k == 3 ? cd.dxQ : k == 4 ? cd.dxP : k == 5 ? cd.dxQ : k == 6 ? cd.dyP : k == 7 ? cd.dyQ : 1.0;
+                const double den = k < 2 ? detP : k < 4 ? detQ : k == 4 ? cd.dyP : k == 5 ? cd.dyQ : k == 6 ? cd.dxP : k == 7 ? cd.dxQ : cd.mu;
+                quot = num / den;
+            }
+            const double jiuP = __shfl_sync(0xffffffffu, quot, 0), jivP = __shfl_sync(0xffffffffu, quot, 1);   // jac_inv.u[0] = dy_dv / det, jac_inv.v[1] = dx_du / det
+            const double jiuQ = __shfl_sync(0xffffffffu, quot, 2), jivQ = __shfl_sync(0xffffffffu, quot, 3);
+            const double q4 = __shfl_sync(0xffffffffu, quot, 4), q5 = __shfl_sync(0xffffffffu, quot, 5), q6 = __shfl_sync(0xffffffffu, quot, 6);
+            const double q7 = __shfl_sync(0xffffffffu, quot, 7), q8 = __shfl_sync(0xffffffffu, quot, 8);
+            const uint32_t gap = item_gap(it.n_same, it.mt_count), n_slots = it.mt_count + gap;
+            if (lane == 0) {
+                c.it = it;
+                c.sb = make_subblocks(nP, nUP, nQ, nUQ, cd.local, TP);
+                const double ge = (double)(detP >= detQ), lt = (double)(detP < detQ);
+                c.ratio_uv = ge * q4 + lt * q5;   // max_uv_ratios integrals.rs:250-259, basis.rs:341-343: ge * (dxP / dyP) + lt * (dxQ / dyQ)
+                c.ratio_vu = ge * q6 + lt * q7;   // max_vu_ratios integrals.rs:262-271, basis.rs:346-348: ge * (dyP / dxP) + lt * (dyQ / dxQ)
+                c.maxdet = detP > detQ ? detP : detQ;                   // partial_max integrals.rs:421-423
+                c.coefA = q8;                                           // 1.0 / mu, integrals.rs:37
+                c.coefB = cd.eps * (cd.su * cd.sv) * (1.0 * 1.0);       // eps * p.glq_scale() * q.glq_scale() integrals.rs:303-305
+                c.v_off = cd.v_off;
+                c.nP = nP; c.nUP = nUP; c.nQ = nQ; c.nUQ = nUQ; c.strideP = strideP; c.strideQ = strideQ; c.local = cd.local;
+                c.chunk_rows = chunk_rows; c.n_slots = n_slots; c.gap = gap; c.end = 0u;
+            }
+            // caches: the P side's scaled tables of a local-desc class (the ancestor sampled over the descendant, basis.rs:372-393) and
+            // the order lists of both sides
+            if (!cd.local) {
+                if (cached_u != cd.tabPu) {
+                    const double* src = g.tabs + (size_t)cd.tabPu * AS4;
+#pragma unroll 4
+                    for (uint32_t k = lane; k < AS4; k += 32) s_tab[k] = src[k];
+                    cached_u = cd.tabPu;
+                }
+                if (cached_v != cd.tabPv) {
+                    const double* src = g.tabs + (size_t)cd.tabPv * AS4;
+#pragma unroll 4
+                    for (uint32_t k = lane; k < AS4; k += 32) s_tab[AS4 + k] = src[k];
+                    cached_v = cd.tabPv;
+                }
+            }
+#pragma unroll 4
+            for (uint32_t k = lane; k < nP; k += 32) { s_spec[k] = g.spec_i[cd.lp.off + k]; s_spec[g.list_cap + k] = g.spec_j[cd.lp.off + k]; }
+            if (!cd.local) {
+#pragma unroll 4
+                for (uint32_t k = lane; k < nQ; k += 32) { s_spec[2 * g.list_cap + k] = g.spec_i[cd.lq.off + k]; s_spec[3 * g.list_cap + k] = g.spec_j[cd.lq.off + k]; }
+            }
+            __syncwarp();
+            WS_T(t_item1); WS_ADD(0, t_item1 - t_item0); WS_ADD(5, 1);
+            for (uint32_t round0 = 0; round0 < n_slots; round0 += K2_WS_TPT * CONS) {
+                for (uint32_t m0 = 0; m0 < nu; m0 += chunk_rows) {
+                    const uint32_t nrow = min(chunk_rows, nu - m0);
+                    WS_T(t_w0);
+                    mbar_wait(&s_empty[stage], phase ^ 1u);     // the contraction warps are done with what this buffer held
+                    WS_T(t_w1);
+                    ws_stage_chunk(g, c, cd, jiuP, jivP, jiuQ, jivQ, s_tab, s_spec, s_slab + (size_t)stage * buf_doubles, m0, nrow, lane);
+                    __syncwarp();
+                    WS_T(t_w2); WS_ADD(1, t_w1 - t_w0); WS_ADD(2, t_w2 - t_w1); WS_ADD(6, 1);
+                    if (lane == 0) mbar_arrive(&s_full[stage]);
+                    stage = stage + 1 == K2_WS_NBUF ? 0u : stage + 1; phase ^= (stage == 0u);
+                }
+            }
+            ci = ci + 1 == K2_WS_NCTX ? 0u : ci + 1;
+        }
+    } else {
+        // ============================================================================================ contraction warps
+        const uint32_t tid = threadIdx.x - 32;   // 0 .. CONS-1
+        for (;;) {
+            WS_T(t_f0);
+            mbar_wait(&s_full[stage], phase);   // first chunk of the next item (or the end marker); its context is complete
+            WS_T(t_f1);
+            if (warp == 1) WS_ADD(7, t_f1 - t_f0);
+            const WsCtx& c = s_ctx[ci];
+            if (c.end) break;
+            const uint32_t n_slots = c.n_slots, gap = c.gap, n_same = c.it.n_same;
+            const uint32_t nUP = c.nUP, nUQ = c.nUQ, nQ = c.nQ, strideP = c.strideP, strideQ = c.strideQ, chunk_rows = c.chunk_rows;
+            const uint32_t chunk = chunk_rows * nv;
+            const double maxdet = c.maxdet, coefA = c.coefA, coefB = c.coefB;
+            double2* out = g.V + c.v_off;
+            bool first = true;
+            // K2_WS_TPT micro-tiles per thread and round: every staged chunk feeds TPT x CONS tiles
+            for (uint32_t round0 = 0; round0 < n_slots; round0 += K2_WS_TPT * CONS) {
+                // ---- my micro-tiles of this round: code = sub | row tile << 2 | column tile << 17, 0xffffffff = none
+                uint32_t code[K2_WS_TPT], prow[K2_WS_TPT], pcol[K2_WS_TPT];
+#pragma unroll
+                for (int t = 0; t < K2_WS_TPT; t++) {
+                    const uint32_t slot = round0 + t * CONS + tid;
+                    code[t] = 0xffffffffu; prow[t] = 0; pcol[t] = 0;
+                    if (slot < n_slots && !(slot >= n_same && slot < n_same + gap)) {
+                        uint32_t li = slot < n_same ? slot : slot - gap, r = 0, sub, rt, ct;
+                        while (li >= c.it.rcount[r]) { li -= c.it.rcount[r]; r++; }        // which of the item's tile ranges
+                        decode_tile(c.sb, c.it.rbegin[r] + li, TP, sub, rt, ct);
+                        code[t] = sub | rt << 2 | ct << 17;
+                        prow[t] = (sub >= 2 ? pad4(nUP) - nUP : 0) + c.sb.row0[sub] + rt * TP;               // slab column of the canonical row index
+                        pcol[t] = ((sub & 1) ? pad4(nUQ) - nUQ : 0) + c.sb.col0[sub] + ct * mt_width(sub);
+                    }
+                }
+                // sol[t][0] / sol[t][1]: A / B of a same-direction tile; columns 0-1 / 2-3 (A only) of a cross-direction tile
+                double sol[K2_WS_TPT][2][TP][MT_Q];
+#pragma unroll
+                for (int t = 0; t < K2_WS_TPT; t++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++)
+#pragma unroll
+                        for (int r = 0; r < TP; r++)
+#pragma unroll
+                            for (int q = 0; q < MT_Q; q++) sol[t][h][r][q] = 0.0;
+                for (uint32_t m0 = 0; m0 < nu; m0 += chunk_rows) {
+                    const uint32_t nrow = min(chunk_rows, nu - m0);
+                    WS_T(t_c0);
+                    if (!first) mbar_wait(&s_full[stage], phase);
+                    first = false;
+                    WS_T(t_c1);
+                    if (warp == 1) WS_ADD(3, t_c1 - t_c0);
+                    const double* buf = s_slab + (size_t)stage * buf_doubles;
+                    const double* s_CP = buf; const double* s_FP = s_CP + (size_t)chunk * strideP;
+                    const double* s_CQ = c.local ? s_CP : s_FP + (size_t)chunk * strideP;
+                    const double* s_FQ = c.local ? s_FP : s_CQ + (size_t)chunk * strideQ;
+#pragma unroll
+                    for (int t = 0; t < K2_WS_TPT; t++) {
+                        if (code[t] == 0xffffffffu) continue;
+                        const uint32_t sub = code[t] & 3u;
+                        const double* cp = s_CP + prow[t]; const double* cq = s_CQ + pcol[t];
+                        if (sub == 0 || sub == 3) {
+                            const double ratio = sub == 0 ? c.ratio_uv : c.ratio_vu;
+                            const double* fp = s_FP + prow[t]; const double* fq = s_FQ + pcol[t];
+                            for (uint32_t r = 0; r < nrow; r++) {
+                                const double uw = s_uw[m0 + r];
+                                ws_row_pass<true, TP>(cp, cq, strideP, strideQ, s_vw, nv, ratio, uw, sol[t][0]);      // A: (curl_p * curl_q) * ratio
+                                ws_row_pass<true, TP>(fp, fq, strideP, strideQ, s_vw, nv, maxdet, uw, sol[t][1]);     // B: (val_p * val_q) * max(det)
+                                cp += (size_t)nv * strideP; cq += (size_t)nv * strideQ; fp += (size_t)nv * strideP; fq += (size_t)nv * strideQ;
+                            }
+                        } else {
+                            for (uint32_t r = 0; r < nrow; r++) {
+                                const double uw = s_uw[m0 + r];
+                                ws_row_pass<false, TP>(cp, cq, strideP, strideQ, s_vw, nv, 1.0, uw, sol[t][0]);       // A, columns 0-1
+                                ws_row_pass<false, TP>(cp, cq + MT_Q, strideP, strideQ, s_vw, nv, 1.0, uw, sol[t][1]);   // A, columns 2-3
+                                cp += (size_t)nv * strideP; cq += (size_t)nv * strideQ;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    WS_T(t_c2);
+                    if (warp == 1) WS_ADD(4, t_c2 - t_c1);
+                    if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp is done reading the buffer
+                    stage = stage + 1 == K2_WS_NBUF ? 0u : stage + 1; phase ^= (stage == 0u);
+                }
+#pragma unroll
+                for (int t = 0; t < K2_WS_TPT; t++) {
+                    if (code[t] == 0xffffffffu) continue;
+                    const uint32_t sub = code[t] & 3u, rt = (code[t] >> 2) & 0x7fffu, ct = code[t] >> 17;
+                    const uint32_t row0 = c.sb.row0[sub] + rt * TP, col0 = c.sb.col0[sub] + ct * mt_width(sub);
+                    const uint32_t row_end = c.sb.row0[sub] + c.sb.rows[sub], col_end = c.sb.col0[sub] + c.sb.cols[sub];
+                    if (sub == 0 || sub == 3) {
+#pragma unroll
+                        for (int r = 0; r < TP; r++) {
+                            const uint32_t a = row0 + r;
+                            if (a >= row_end) continue;
+#pragma unroll
+                            for (int q = 0; q < MT_Q; q++) {
+                                const uint32_t b = col0 + q;
+                                if (b >= col_end) continue;
+                                out[(size_t)a * nQ + b] = make_double2(coefA * sol[t][0][r][q], coefB * sol[t][1][r][q]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < TP; r++) {
+                            const uint32_t a = row0 + r;
+                            if (a >= row_end) continue;
+#pragma unroll
+                            for (int q = 0; q < MT_QX; q++) {
+                                const uint32_t b = col0 + q;
+                                if (b >= col_end) continue;
+                                // cross-direction mass entries: every integrand term is a signed zero, the quadrature returns +0.0 (integrals.rs:318-339)
+                                out[(size_t)a * nQ + b] = make_double2(coefA * sol[t][q >> 1][r][q & 1], coefB * 0.0);
+                            }
+                        }
+                    }
+                }
+            }
+            ci = ci + 1 == K2_WS_NCTX ? 0u : ci + 1;
+        }
+    }
+    if (!g.follows_sampler) cudaGridDependencySynchronize();   // do not complete before the first integrator grid has
+}
+
 // ---------------------------------------------------------------------------------------------------------------- FP64 peak
 template <int KIND>
 __global__ void fp64_peak_kernel(double* out, int iters) {
@@ -361,7 +804,8 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
 }  // namespace
 
 cudaError_t launch_k1_tables(const Plan& P, int basis_kind, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st) {
-    k1_tables_kernel<<<(unsigned)P.host.tables.size(), 64, 0, st>>>(P.d_tables, P.d_tabs, NO, NPT, P.d_glq, nu, nv, P.host.i_max, P.host.j_max, basis_kind);
+    k1_tables_kernel<<<(unsigned)P.host.tables.size(), 64, 0, st>>>(P.d_tables, P.d_tabs, NO, NPT, P.d_glq, nu, nv, P.host.i_max, P.host.j_max, basis_kind,
+                                                                      P.d_work_counter);
     return cudaGetLastError();
 }
 
@@ -389,7 +833,7 @@ static cudaError_t launch_k2_part(const Plan& P, const WorkItem* d_items, uint32
         if (e != cudaSuccess) return e;
         smem_set[P.device] = smem;
     }
-    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, slab_doubles, follows_sampler};
+    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, slab_doubles, follows_sampler, 0u};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(count); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -397,6 +841,48 @@ static cudaError_t launch_k2_part(const Plan& P, const WorkItem* d_items, uint32
     cfg.attrs = attr; cfg.numAttrs = 1;
     const cudaError_t e = P.host.tile_p == 1 ? cudaLaunchKernelEx(&cfg, k2_exact_kernel<1, NT>, g) : cudaLaunchKernelEx(&cfg, k2_exact_kernel<K2_TILE_P, NT>, g);
     return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+// Shared memory of the warp-specialised integrator in front of its slab ring: weights, mbarriers, item contexts, the staging warp's
+// table cache (4 tables) and order-list cache (4 lists).
+static size_t ws_fixed_smem(const Plan& P, uint32_t NO, uint32_t NPT) {
+    const size_t list_cap = (P.host.max_list_n + 15u) & ~(size_t)15;
+    return (256 + 2 * K2_WS_NBUF) * sizeof(double) + K2_WS_NCTX * sizeof(WsCtx) + 4 * (size_t)(4 * NO * NPT) * sizeof(double) + 4 * list_cap;
+}
+
+// Persistent, warp-specialised launch of the big items [0, count): two CTAs per SM, each with a ring of K2_WS_NBUF slab buffers.
+static cudaError_t launch_k2_ws(const Plan& P, const WorkItem* d_items, uint32_t count, uint32_t max_stride, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT,
+                                int follows_sampler, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    const uint32_t list_cap = (P.host.max_list_n + 15u) & ~15u;
+    const size_t fixed = ws_fixed_smem(P, NO, NPT);
+    const size_t per_row = (size_t)max_stride * 2 * sizeof(double) * nv;     // chunks are whole quadrature rows
+    const size_t hard = (size_t)P.max_smem_optin - 1024;
+    const size_t smem = std::min<size_t>(hard, (size_t)K2_WS_SMEM_KB * 1024);      // two CTAs per SM
+    if ((smem - fixed) / K2_WS_NBUF < per_row) return cudaErrorInvalidConfiguration;   // launch_k2_exact checks ws_fits() first
+    const uint32_t buf_doubles = (uint32_t)(((smem - fixed) / K2_WS_NBUF / sizeof(double)) & ~(size_t)1);   // even: buffers stay 16-byte aligned
+    static thread_local size_t smem_set[64] = {};
+    if (P.device >= 0 && P.device < 64 && smem > smem_set[P.device]) {
+        const cudaError_t e = cudaFuncSetAttribute(k2_ws_kernel<K2_TILE_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set[P.device] = smem;
+    }
+    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, buf_doubles, follows_sampler, list_cap};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(std::min<uint32_t>(count, (uint32_t)(K2_MIN_CTAS * std::max(P.sm_count, 1)))); cfg.blockDim = dim3(K2_WS_THREADS);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k2_ws_kernel<K2_TILE_P>, g, count, P.d_work_counter);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+// The warp-specialised integrator stages whole quadrature rows: one row (nv points) of the widest class must fit a ring buffer.
+static bool ws_fits(const Plan& P, uint32_t max_stride, uint32_t nv, uint32_t NO, uint32_t NPT) {
+    const size_t fixed = ws_fixed_smem(P, NO, NPT);
+    const size_t smem = std::min<size_t>((size_t)P.max_smem_optin - 1024, (size_t)K2_WS_SMEM_KB * 1024);
+    return smem > fixed && (smem - fixed) / K2_WS_NBUF >= (size_t)max_stride * 2 * sizeof(double) * nv;
 }
 
 // Items are ordered by size (largest first); the first n_big of them run in K2_THREADS-wide CTAs, the rest in K2_SMALL_THREADS-wide
@@ -414,9 +900,22 @@ cudaError_t launch_k2_exact(const Plan& P, const WorkItem* d_items, uint32_t n_i
     cudaError_t e = launch_k2_part<K2_SMALL_THREADS>(P, d_items + n_big, n_small, stride_small, 27 * 1024, nu, nv, NO, NPT, 1, st);
     if (e != cudaSuccess) return e;
     if (launches && n_small) (*launches)++;
-    e = launch_k2_part<K2_THREADS>(P, d_items, n_big, stride_big, (K2_MIN_CTAS == 2 ? 100 : 216 / K2_MIN_CTAS) * 1024, nu, nv, NO, NPT, n_small == 0, st);
+    if (P.host.tile_p == K2_TILE_P && P.host.use_ws && ws_fits(P, stride_big, nv, NO, NPT)) e = launch_k2_ws(P, d_items, n_big, stride_big, nu, nv, NO, NPT, n_small == 0, st);
+    else e = launch_k2_part<K2_THREADS>(P, d_items, n_big, stride_big, (K2_MIN_CTAS == 2 ? 100 : 216 / K2_MIN_CTAS) * 1024, nu, nv, NO, NPT, n_small == 0, st);
     if (launches && n_big) (*launches)++;
     return e;
+}
+
+cudaError_t ws_profile(unsigned long long out[8], int reset) {
+#ifdef FEM2D_WS_PROFILE
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_ws_prof, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess && reset) { unsigned long long z[8] = {}; e = cudaMemcpyToSymbol(g_ws_prof, z, sizeof(z)); }
+    return e;
+#else
+    for (int k = 0; k < 8; k++) out[k] = 0;
+    (void)reset;
+    return cudaSuccess;
+#endif
 }
 
 cudaError_t fp64_peak(int kind, double* gflops) {

@@ -2,6 +2,7 @@
 #include "plan_host.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <thread>
@@ -380,7 +381,8 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
     std::stable_sort(cls_order.begin(), cls_order.end(), [&](uint32_t a, uint32_t b) { return P.classes[a].n_mt > P.classes[b].n_mt; });
     // Few, heavily deduplicated classes would leave most of the 148 SMs idle: shrink the item size until there are about two
     // CTAs per SM (each item re-stages its class's slabs, which is cheap next to an idle machine).
-    uint32_t cap = K2_ROUNDS * K2_THREADS;
+    if (const char* ev = std::getenv("FEM2D_K2_WS")) P.use_ws = std::atoi(ev) != 0;   // tuning: 0 = every item in k2_exact_kernel
+    uint32_t cap = K2_ROUNDS * (P.use_ws && P.tile_p == (uint32_t)K2_TILE_P ? K2_WS_CONS_WARPS * 32 : K2_THREADS);
     const uint32_t min_cap = P.tile_p == 1 ? 256u : 64u;   // latency shape: one full round per CTA measured best (128: +10 %, 512: +30 %)
     for (; cap > min_cap; cap /= 2) {
         uint64_t n = 0;

@@ -28,6 +28,7 @@ struct HostPlan {
     uint64_t n_values = 0;   // entries of V
     uint32_t max_list_n = 0;
     uint32_t tile_p = 4;            // micro-tile height chosen for the exact integrator (4: throughput, 1: latency)
+    bool use_ws = true;             // throughput shape: big items run in the warp-specialised persistent integrator (FEM2D_K2_WS=0: tuning)
     uint32_t max_slab_stride = 0;   // max over classes of pad4(nU)+pad4(nV) of P (+ the same of Q for non-local classes)
 };
 

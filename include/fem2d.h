@@ -98,6 +98,12 @@ int fem2d_plan_info(const fem2d_plan* plan, uint64_t info[16]);
  * cross-direction ones in every item, and the staged function ranges of an item cover the functions its tiles read.
  * out[]: 0 tiles, 1 same-direction tiles, 2 thread slots (tiles + warp-alignment gaps), 3 violations found (0 = consistent). */
 int fem2d_plan_check_work_items(const fem2d_plan* plan, uint64_t out[4]);
+/* Work of one numeric call of the integrator, counted on the plan's classes (every class is integrated once per call): out[0] same-direction
+ * pairs (U-U, V-V: A and B, 8 FP64 operations per pair and quadrature point + 4 per pair and quadrature row in the reference's order,
+ * integrals.rs:36-91,302-353, glq.rs:19-32), out[1] cross-direction pairs (U-V, V-U: A only, 3 per point + 2 per row), out[2] / out[3] micro-tiles of
+ * the two kinds, out[4] / out[5] pairs per micro-tile of the two kinds, out[6] function columns staged (P side + Q side of every class),
+ * out[7] work items.  Host logic; works on host-only plans. */
+int fem2d_plan_work_info(const fem2d_plan* plan, uint64_t out[8]);
 /* Size of the per-slot source map the scatter kernel reads.  The map is packed per chunk of slots as 16-bit offsets from the
  * chunk's smallest source; chunks that do not fit keep plain 32-bit indices.  info[]: 0 chunks in plain form, 1 slots per chunk,
  * 2 bytes of the map one full scatter reads, 3 bytes of an all-plain map (4 per slot).  Device plans only. */
@@ -193,6 +199,16 @@ void fem2d_host_free(void* p);
  * x_out / y_out: HOST [n_leaves][d][d] (reference indexing quirk: square densities only). leaf_ids: [n_leaves]. */
 int fem2d_xy_fields(const fem2d_domain_view* view, int device, int basis_kind, uint32_t density, const double* solution,
                     uint64_t leaf_capacity, uint64_t* n_leaves, uint32_t* leaf_ids, double* x_out, double* y_out);
+
+/* SparseMatrix -> PETSc AIJ binary (the SLEPc route: `impl From<SparseMatrix> for AIJMatrixBinary` + print_to_petsc_binary_file,
+ * sparse_matrix.rs:184-264; GEP::print_to_petsc_binary_files, linalg.rs:44-52), emitted from the device arrays: the plan's upper-triangular
+ * pattern is mirrored into full symmetric rows on the GPU (per-row counts, sorted columns, big-endian byte swap) and the finished byte
+ * image crosses PCIe once.  d_vals: DEVICE array of nnz_upper doubles (the d_a or d_b of fem2d_assemble_device).
+ * fem2d_petsc_aij_size: size of the image in bytes and number of entries of the full matrix.  fem2d_petsc_aij_image: the bytes into a host
+ * buffer.  fem2d_write_petsc_aij: the same bytes into a file (what `{dir}/tmp/{prefix}_a.dat` holds in the reference). */
+int fem2d_petsc_aij_size(fem2d_plan* plan, uint64_t* bytes, uint64_t* nnz_full);
+int fem2d_petsc_aij_image(fem2d_plan* plan, const double* d_vals, void* host_image, uint64_t capacity);
+int fem2d_write_petsc_aij(fem2d_plan* plan, const double* d_vals, const char* path);
 
 /* FP64 pipe micro-benchmark (roofline denominator for the EXACT integrator): returns achieved GFLOP/s of a DFMA chain
  * (kind 0) or of a DMUL+DADD non-fused chain (kind 1) on `device`. */

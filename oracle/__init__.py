@@ -428,3 +428,29 @@ def nalgebra_solve_surrogate(gep: GEP, target: float) -> float:
     S = np.tril(M) + np.tril(M, -1).T
     ev = np.linalg.eigvalsh(S)
     return float(ev[np.argmin(np.abs(ev - target))])
+
+
+def petsc_aij_bytes(dimension: int, rows, cols, values) -> bytes:
+    """CPU restatement (numpy, test infrastructure) of `impl From<SparseMatrix> for AIJMatrixBinary` and
+    `AIJMatrixBinary::print_to_petsc_binary_file` (sparse_matrix.rs:184-264): the bytes the reference writes for a matrix whose
+    upper-triangular entries are (rows, cols, values).
+      :187-197  row_counts: +1 on the diagonal, +1 for both rows otherwise
+      :200-206  full_matrix = {[c, r]: v} of every entry, then .append(entries): keys ascending, an equal key ([r, r]) is overwritten
+      :209-212  j = column of every key in that order, a = its value
+      :228-262  header b"\\0\\x12{P" (= 1211216 as u32 BE), dim, dim, len(a); counts, j as u32 BE; a as f64 BE"""
+    rows = np.ascontiguousarray(rows, dtype=np.int64); cols = np.ascontiguousarray(cols, dtype=np.int64)
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    counts = np.zeros(dimension, dtype=np.int64)
+    np.add.at(counts, rows, 1)
+    off = rows != cols
+    np.add.at(counts, cols[off], 1)
+    # the mirrored map first, the original entries appended after it: on equal keys (the diagonal) the appended value wins -- same value
+    key_r = np.concatenate([cols, rows]); key_c = np.concatenate([rows, cols]); val = np.concatenate([values, values])
+    order = np.lexsort((np.arange(len(key_r)), key_c, key_r))          # by (row, col), insertion order last
+    key_r, key_c, val = key_r[order], key_c[order], val[order]
+    last = np.ones(len(key_r), dtype=bool)
+    last[:-1] = (key_r[:-1] != key_r[1:]) | (key_c[:-1] != key_c[1:])  # keep the LAST of equal keys (the appended one)
+    j, a = key_c[last], val[last]
+    head = np.array([1211216, dimension, dimension, len(a)], dtype=">u4").tobytes()
+    assert head[:4] == b"\x00\x12{P"
+    return head + counts.astype(">u4").tobytes() + j.astype(">u4").tobytes() + a.astype(">f8").tobytes()

@@ -237,3 +237,15 @@ def test_petsc_aij_writer(tmp_path):
     assert counts == (2, 1, 2) and js == (0, 2, 1, 0, 2) and a == (1.0, 2.5, -3.0, 2.5, 4.0)
     dense = sm.to_dense()
     assert np.array_equal(dense, dense.T) and dense[2, 0] == 2.5
+
+
+def test_petsc_aij_writer_matches_oracle_restatement(tmp_path):
+    """Host writer of the mirror vs the oracle-side restatement of sparse_matrix.rs:184-264 on a real (small) assembled pattern."""
+    import oracle as O
+    import recipes
+    mo = recipes.RECIPES["nalg"](recipes.api("oracle"))
+    do = O.Domain.from_mesh(mo)
+    gep = O.galerkin_sample_gep_hcurl(do, [4, 4])
+    path = str(tmp_path / "m.dat")
+    F.SparseMatrix(do.num_dofs, gep.rows, gep.cols, gep.a).print_to_petsc_binary_file(path)
+    assert open(path, "rb").read() == O.petsc_aij_bytes(do.num_dofs, gep.rows, gep.cols, gep.a)
