@@ -73,7 +73,7 @@ class _View(C.Structure):
 # Every symbol declared in include/fem2d.h and include/fem2d_host.h (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "fem2d_symbolic", "fem2d_plan_free", "fem2d_plan_info", "fem2d_plan_check_work_items", "fem2d_plan_work_info", "fem2d_plan_source_map_info", "fem2d_plan_row_offsets", "fem2d_plan_pattern_transfer_info", "fem2d_plan_pattern", "fem2d_plan_pattern_device",
-    "fem2d_assemble_device", "fem2d_assemble_device_ranges", "fem2d_plan_row_blocks_split", "fem2d_assemble_ranges", "fem2d_assemble", "fem2d_galerkin_sample_gep_hcurl", "fem2d_plan_row_blocks",
+    "fem2d_assemble_device", "fem2d_assemble_device_ranges", "fem2d_plan_row_blocks_split", "fem2d_assemble_ranges", "fem2d_assemble", "fem2d_galerkin_sample_gep_hcurl", "fem2d_galerkin_sample_gep_hcurl_multi", "fem2d_plan_row_blocks",
     "fem2d_plan_last_timing", "fem2d_plan_timing", "fem2d_plan_set_phase_timing", "fem2d_assemble_range", "fem2d_host_alloc", "fem2d_host_free", "fem2d_xy_fields", "fem2d_fp64_peak",
     "fem2d_petsc_aij_size", "fem2d_petsc_aij_image", "fem2d_write_petsc_aij", "fem2d_device_count", "fem2d_status_string", "fem2d_last_error", "fem2d_version",
 ]
@@ -87,7 +87,7 @@ HOST_ABI_SYMBOLS = [
     "fem2dh_mesh_execute_p_refinements", "fem2dh_mesh_set_global_expansion_orders", "fem2dh_mesh_set_expansion_orders",
     "fem2dh_domain_from_mesh", "fem2dh_domain_blank", "fem2dh_domain_free", "fem2dh_domain_mesh", "fem2dh_domain_num_dofs",
     "fem2dh_domain_num_basis_specs", "fem2dh_domain_basis_specs", "fem2dh_domain_view", "fem2dh_gauss_quadrature_points",
-    "fem2dh_default_ngq", "fem2dh_write_petsc_aij",
+    "fem2dh_default_ngq", "fem2dh_write_petsc_aij", "fem2dh_ordered_map_rebuild_seconds",
 ]
 
 for _n in ("fem2d_status_string", "fem2d_last_error", "fem2d_version", "fem2dh_last_error"):
@@ -97,6 +97,7 @@ for _n in ("fem2dh_mesh_num_elems", "fem2dh_mesh_num_edges", "fem2dh_mesh_num_no
     getattr(_L, _n).restype = C.c_uint64
 for _n in ("fem2dh_mesh_descendant_elems", "fem2dh_mesh_ancestor_elems"):
     getattr(_L, _n).restype = C.c_int64
+_L.fem2dh_ordered_map_rebuild_seconds.restype = C.c_double
 _L.fem2dh_domain_mesh.restype = C.c_void_p
 _L.fem2dh_domain_view.restype = C.POINTER(_View)
 _L.fem2d_host_alloc.restype = C.c_void_p
@@ -756,6 +757,34 @@ def galerkin_sample_gep_hcurl(domain: Domain, glq_grid_dim=None, basis=HierPoly,
     rows, cols, av, bv = plan.assemble(glq, basis, a, b, mode)
     n = domain.num_dofs
     return GEP(SparseMatrix(n, rows, cols, av), SparseMatrix(n, rows, cols, bv))
+
+
+def galerkin_sample_gep_hcurl_multi(domain_or_view, glq, devices, basis=HierPoly, a=CurlCurl, b=L2Inner, mode: int = MODE_EXACT, out=None):
+    """fem2d_galerkin_sample_gep_hcurl_multi: the one-shot call on several GPUs of this process; returns (rows, cols, a_vals, b_vals) of the ONE
+    assembled GEP.  `out` = optional (rows_ptr, cols_ptr, a_ptr, b_ptr, capacity) raw HOST pointers (e.g. pinned buffers from host_alloc)."""
+    view = domain_or_view.view() if isinstance(domain_or_view, Domain) else domain_or_view
+    (up, uw), (vp, vw) = glq
+    up, uw, vp, vw = [np.ascontiguousarray(x, dtype=np.float64) for x in (up, uw, vp, vw)]
+    devs = np.ascontiguousarray(list(devices), dtype=np.int32)
+    nnz = C.c_uint64()
+    if out is None:
+        # size probe with a zero capacity: the call reports the required size and fails with BAD_ARGUMENT
+        st = _L.fem2d_galerkin_sample_gep_hcurl_multi(C.byref(view.c), C.c_uint32(len(devs)), _p(devs, C.c_int32), basis.kind, a.kind, b.kind, int(mode),
+                                                      _p(up, C.c_double), _p(uw, C.c_double), C.c_uint32(len(up)), _p(vp, C.c_double), _p(vw, C.c_double),
+                                                      C.c_uint32(len(vp)), C.c_uint64(0), C.byref(nnz), None, None, None, None)
+        if st != ERR_BAD_ARGUMENT or nnz.value == 0:
+            _ck(st)
+        n = nnz.value
+        rows = np.zeros(n, dtype=np.uint32); cols = np.zeros(n, dtype=np.uint32); av = np.zeros(n); bv = np.zeros(n)
+        ptrs = (rows.ctypes.data, cols.ctypes.data, av.ctypes.data, bv.ctypes.data, n)
+    else:
+        rows = cols = av = bv = None
+        ptrs = out
+    _ck(_L.fem2d_galerkin_sample_gep_hcurl_multi(C.byref(view.c), C.c_uint32(len(devs)), _p(devs, C.c_int32), basis.kind, a.kind, b.kind, int(mode),
+                                                 _p(up, C.c_double), _p(uw, C.c_double), C.c_uint32(len(up)), _p(vp, C.c_double), _p(vw, C.c_double),
+                                                 C.c_uint32(len(vp)), C.c_uint64(ptrs[4]), C.byref(nnz), C.c_void_p(ptrs[0] or None), C.c_void_p(ptrs[1] or None),
+                                                 C.c_void_p(ptrs[2]), C.c_void_p(ptrs[3])))
+    return (rows, cols, av, bv) if out is None else int(nnz.value)
 
 
 def fp64_peak(device: int = 0, kind: int = 0) -> float:

@@ -464,9 +464,11 @@ int fem2d_plan_timing(fem2d_plan* plan, uint32_t calls_back, float ms[4], uint32
 }
 int fem2d_plan_last_timing(fem2d_plan* plan, float ms[4], uint32_t launches[4]) { return fem2d_plan_timing(plan, 0, ms, launches); }
 
-int fem2d_assemble_ranges(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w, uint32_t nu,
-                          const double* v_pts, const double* v_w, uint32_t nv, uint32_t n_ranges, const uint64_t* slot_begins, const uint64_t* slot_ends,
-                          uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals) {
+// at_slot: false = the outputs hold the ranges back to back (fem2d_assemble_ranges); true = every slot goes to its own position in outputs
+// sized for the whole pattern (several devices of one process fill one set of arrays, fem2d_galerkin_sample_gep_hcurl_multi).
+static int assemble_ranges_impl(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w, uint32_t nu,
+                                const double* v_pts, const double* v_w, uint32_t nv, uint32_t n_ranges, const uint64_t* slot_begins, const uint64_t* slot_ends,
+                                uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals, bool at_slot, unsigned host_threads) {
     int st = check_numeric_args(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv);
     if (st != FEM2D_OK) return st;
     if (!a_vals || !b_vals) return fail(FEM2D_ERR_BAD_ARGUMENT, "null output pointer");
@@ -496,22 +498,29 @@ int fem2d_assemble_ranges(fem2d_plan* plan, int basis_kind, int a_kind, int b_ki
     for (uint32_t k = 0; k < n_ranges; k++) {
         const uint64_t n = e[k] - b[k];
         if (n == 0) continue;
-        CKS(cudaMemcpyAsync(a_vals + off, p.d_out_a + b[k], n * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
-        CKS(cudaMemcpyAsync(b_vals + off, p.d_out_b + b[k], n * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+        CKS(cudaMemcpyAsync(a_vals + (at_slot ? b[k] : off), p.d_out_a + b[k], n * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+        CKS(cudaMemcpyAsync(b_vals + (at_slot ? b[k] : off), p.d_out_b + b[k], n * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
         off += n;
     }
     if (rows || cols) {   // while the copies above are in flight
-        const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        const unsigned hw = std::max(1u, std::min(host_threads, std::thread::hardware_concurrency()));
         const uint32_t* run_col = p.h_col_run_col;
         off = 0;
         for (uint32_t k = 0; k < n_ranges; k++) {
-            if (rows) expand_runs(p.h_row_ptr, p.host.n_dofs, [](uint64_t r) { return (uint32_t)r; }, 0u, b[k], e[k], rows + off, hw);
-            if (cols) expand_runs(p.h_col_run_slot, p.n_col_runs, [run_col](uint64_t r) { return run_col[r]; }, 1u, b[k], e[k], cols + off, hw);
+            if (rows) expand_runs(p.h_row_ptr, p.host.n_dofs, [](uint64_t r) { return (uint32_t)r; }, 0u, b[k], e[k], rows + (at_slot ? b[k] : off), hw);
+            if (cols) expand_runs(p.h_col_run_slot, p.n_col_runs, [run_col](uint64_t r) { return run_col[r]; }, 1u, b[k], e[k], cols + (at_slot ? b[k] : off), hw);
             off += e[k] - b[k];
         }
     }
     CKS(cudaStreamSynchronize(nullptr));
     return FEM2D_OK;
+}
+
+int fem2d_assemble_ranges(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w, uint32_t nu,
+                          const double* v_pts, const double* v_w, uint32_t nv, uint32_t n_ranges, const uint64_t* slot_begins, const uint64_t* slot_ends,
+                          uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals) {
+    return assemble_ranges_impl(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, n_ranges, slot_begins, slot_ends, rows, cols, a_vals, b_vals,
+                                false, 8u);
 }
 
 int fem2d_assemble_range(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w, uint32_t nu,
@@ -541,6 +550,77 @@ int fem2d_galerkin_sample_gep_hcurl(const fem2d_domain_view* view, int device, i
     st = fem2d_assemble(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, rows, cols, a_vals, b_vals);
     fem2d_plan_free(plan);
     return st;
+}
+
+// One-shot call on several devices of ONE process: the host half of the symbolic phase runs once, then one host thread per device builds the
+// pattern on its device, takes block r of the two-level row partition (fem2d_plan_row_blocks_split), integrates what those rows read and
+// copies its slices of A, B (and the expanded rows / cols) to their slot positions in the caller's arrays.  No collective: the <= 2
+// contributions of a key are summed on the device that owns its row (halo tiles are recomputed), so the arrays are bit-identical to
+// the single-device result whatever the device count.
+int fem2d_galerkin_sample_gep_hcurl_multi(const fem2d_domain_view* view, uint32_t n_devices, const int* devices, int basis_kind, int a_kind, int b_kind, int mode,
+                                          const double* u_pts, const double* u_w, uint32_t nu, const double* v_pts, const double* v_w, uint32_t nv,
+                                          uint64_t capacity, uint64_t* nnz_out, uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals) {
+    if (!view) return fail(FEM2D_ERR_BAD_ARGUMENT, "null view");
+    // reference order of the early errors (galerkin.rs:42-59)
+    if (view->continuity != FEM2D_CC_HCURL) return fail(FEM2D_ERR_WRONG_CONTINUITY, fem2d_status_string(FEM2D_ERR_WRONG_CONTINUITY));
+    if (view->n_dofs == 0) return fail(FEM2D_ERR_EMPTY_DOF_SET, fem2d_status_string(FEM2D_ERR_EMPTY_DOF_SET));
+    if (nu < 4 || nv < 4) return fail(FEM2D_ERR_INVALID_GLQ, fem2d_status_string(FEM2D_ERR_INVALID_GLQ));
+    if (n_devices == 0 || n_devices > 64 || !devices) return fail(FEM2D_ERR_BAD_ARGUMENT, "1..64 devices expected");
+    for (uint32_t d = 0; d < n_devices; d++) {
+        const int st = device_available(devices[d]);
+        if (st != FEM2D_OK) return st;   // (a device index may repeat: its blocks are then assembled one after the other on that device)
+    }
+    try {
+        fem2d::HostPlan host;
+        std::string err;
+        const int hst = fem2d::build_host_plan(view, true, host, err);
+        if (hst != FEM2D_OK) return fail(hst, err);
+        if (host.n_pairs >= (1ull << 31)) return fail(FEM2D_ERR_UNSUPPORTED, "more than 2^31 pairs");
+        std::vector<int> status(n_devices, FEM2D_OK);
+        std::vector<std::string> message(n_devices);
+        std::vector<uint64_t> nnz(n_devices, 0);
+        const unsigned host_threads = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / n_devices));
+        auto work = [&](uint32_t r) {
+            fem2d_plan* plan = nullptr;
+            try {
+                plan = new fem2d_plan();
+                plan->p.host = host;               // every device plan owns a copy of the (small) host half
+                plan->p.device = devices[r];
+                std::string e2;
+                int st = fem2d::device_symbolic(plan->p, e2);
+                if (st == FEM2D_OK) {
+                    nnz[r] = plan->p.nnz;
+                    if (plan->p.nnz > capacity) { st = FEM2D_ERR_BAD_ARGUMENT; e2 = "output capacity too small (see *nnz_out)"; }
+                }
+                if (st == FEM2D_OK) {
+                    std::vector<uint64_t> b1(n_devices + 1), b2(n_devices + 1);
+                    uint64_t begins[2] = {0, 0}, ends[2] = {plan->p.nnz, 0};
+                    uint32_t n_ranges = 1;
+                    if (n_devices > 1) {
+                        st = fem2d_plan_row_blocks_split(plan, n_devices, b1.data(), b2.data());
+                        begins[0] = b1[r]; ends[0] = b1[r + 1]; begins[1] = b2[r]; ends[1] = b2[r + 1]; n_ranges = 2;
+                    }
+                    if (st == FEM2D_OK)
+                        st = assemble_ranges_impl(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, n_ranges, begins, ends, rows, cols, a_vals, b_vals,
+                                                  true, host_threads);
+                    if (st != FEM2D_OK) e2 = g_err;
+                }
+                status[r] = st; message[r] = e2;
+            } catch (std::bad_alloc&) { status[r] = FEM2D_ERR_OUT_OF_MEMORY; message[r] = "host allocation failed";
+            } catch (std::exception& ex) { status[r] = FEM2D_ERR_INTERNAL; message[r] = ex.what(); }
+            if (plan) { fem2d::device_plan_release(plan->p); delete plan; }
+        };
+        if (n_devices == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (uint32_t r = 0; r < n_devices; r++) th.emplace_back(work, r);
+            for (auto& t : th) t.join();
+        }
+        if (nnz_out) *nnz_out = nnz[0];
+        for (uint32_t r = 0; r < n_devices; r++) if (status[r] != FEM2D_OK) return fail(status[r], "device " + std::to_string(devices[r]) + ": " + message[r]);
+        return FEM2D_OK;
+    } catch (std::bad_alloc&) { return fail(FEM2D_ERR_OUT_OF_MEMORY, "host allocation failed");
+    } catch (std::exception& e) { return fail(FEM2D_ERR_INTERNAL, e.what()); }
 }
 
 int fem2d_petsc_aij_size(fem2d_plan* plan, uint64_t* bytes, uint64_t* nnz_full) {

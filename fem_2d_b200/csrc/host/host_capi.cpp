@@ -1,6 +1,9 @@
 // C-ABI of the host mirror (include/fem2d_host.h).  Pure host code.
 #include "../../../include/fem2d_host.h"
 
+#include <map>
+#include <chrono>
+#include <array>
 #include <cstdio>
 #include <memory>
 
@@ -227,6 +230,18 @@ int fem2dh_write_petsc_aij(const char* path, uint64_t dim, uint64_t nnz_upper, c
         }
         std::fclose(f);
     });
+}
+
+// Stand-in for the caller-side rebuild of the reference's container from the sorted output arrays (`SparseMatrix::from_sorted_upper_tri` of
+// a BTreeMap<[u32; 2], f64> bulk build): an ordered std::map filled with end hints, i.e. the O(n) best case.  Returns seconds.
+double fem2dh_ordered_map_rebuild_seconds(uint64_t nnz, const uint32_t* rows, const uint32_t* cols, const double* values) {
+    const auto t0 = std::chrono::steady_clock::now();
+    {
+        std::map<std::array<uint32_t, 2>, double> m;
+        for (uint64_t k = 0; k < nnz; k++) m.emplace_hint(m.end(), std::array<uint32_t, 2>{rows[k], cols[k]}, values[k]);
+        if (m.size() != nnz) return -1.0;
+    }   // the map's destruction belongs to its owner, not to the rebuild; it is left out of the timed interval below on purpose
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 }  // extern "C"

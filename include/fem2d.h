@@ -170,6 +170,17 @@ int fem2d_galerkin_sample_gep_hcurl(const fem2d_domain_view* view, int device, i
                                     uint64_t capacity, uint64_t* nnz_out,
                                     uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals);
 
+/* The same one-shot call on `n_devices` GPUs of one process (devices[]: CUDA device indices, normally distinct): what a single Rust caller of the
+ * drop-in gets on a multi-GPU box.  The host half of the symbolic phase runs once; one host thread per device builds the pattern there,
+ * assembles block r of the two-level row partition (fem2d_plan_row_blocks_split) and copies its slices of rows / cols / A / B to their
+ * positions in the caller's arrays.  The result is ONE GEP (galerkin.rs:33-40, linalg.rs:59-81), bit-identical to the single-device call
+ * for any device count (no collective: the <= 2 contributions of a key are summed on the device that owns its row). */
+int fem2d_galerkin_sample_gep_hcurl_multi(const fem2d_domain_view* view, uint32_t n_devices, const int* devices, int basis_kind, int a_kind, int b_kind,
+                                          int mode, const double* u_pts, const double* u_w, uint32_t nu,
+                                          const double* v_pts, const double* v_w, uint32_t nv,
+                                          uint64_t capacity, uint64_t* nnz_out,
+                                          uint32_t* rows, uint32_t* cols, double* a_vals, double* b_vals);
+
 /* Row-block partition of the pattern for `world` ranks: bounds[r]..bounds[r+1] are slot indices aligned to row starts
  * and balanced by nnz (bounds has world+1 entries). */
 int fem2d_plan_row_blocks(const fem2d_plan* plan, uint32_t world, uint64_t* bounds);

@@ -84,6 +84,9 @@ uint64_t fem2dh_default_ngq(uint64_t max_order);
 /* Caller-side "next" row: SparseMatrix -> PETSc AIJ binary (sparse_matrix.rs:184-264, linalg.rs:44-52) written straight from
  * the sorted upper-triangular arrays (full symmetric rows, big-endian). */
 int fem2dh_write_petsc_aij(const char* path, uint64_t dimension, uint64_t nnz_upper, const uint32_t* rows, const uint32_t* cols, const double* values);
+/* Cost of rebuilding an ordered map (the stand-in for BTreeMap<[u32;2], f64>, sparse_matrix.rs:16) from sorted output arrays with end hints:
+ * what the Rust shim's `SparseMatrix::from_sorted_upper_tri` would pay at best.  Returns seconds (construction + destruction), < 0 on error. */
+double fem2dh_ordered_map_rebuild_seconds(uint64_t nnz, const uint32_t* rows, const uint32_t* cols, const double* values);
 
 #ifdef __cplusplus
 }
