@@ -223,10 +223,14 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
+    cpu_group = None
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group(backend="nccl", device_id=dev)
+        # CPU-side group: ranks > 0 wait on it while rank 0 drives all N GPUs from one process in the end-to-end leg (an NCCL barrier
+        # would keep a kernel spinning on their GPUs and time-slice against rank 0's work there)
+        cpu_group = dist.new_group(backend="gloo")
 
     def barrier():
         if dist is not None:
@@ -402,7 +406,7 @@ def run_ours(args):
     # ---- end to end through the reference-facing call: host Domain view -> host CSR arrays ------------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz)
+        e2e = run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz, cpu_group)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -558,7 +562,7 @@ def rank_ranges(plan, world, rank):
     return [(int(b1[rank]), int(b1[rank + 1])), (int(b2[rank]), int(b2[rank + 1]))]
 
 
-def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz):
+def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz, cpu_group=None):
     """The reference-facing call with HOST buffers, every step: fem2d_galerkin_sample_gep_hcurl_multi = host planner + symbolic phase on
     every device + K1/K2/K3 + D2H of A, B and the compressed pattern + host expansion of rows[] / cols[], ONE process driving all N GPUs
     (what a single Rust caller of the drop-in gets).  Under torchrun rank 0 makes the call on devices 0..N-1 while the other ranks wait at
@@ -572,6 +576,9 @@ def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz):
              "bs_dir", "bs_dof"]
     steps = max(1, min(args.steps, args.e2e_steps))
     out = None
+    if dist is not None:
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)      # every rank's GPU is idle from here on
     if rank == 0:
         # inputs: the flattened Domain arrays in pinned host memory
         pinned = {}
@@ -608,6 +615,11 @@ def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz):
             one()
             per_step.append(round(1e3 * (time.perf_counter() - t1), 2))
         sec = time.perf_counter() - t0
+        tm = (C.c_double * (4 + 4 * world))()
+        F._L.fem2d_debug_multi_timing(tm, C.c_uint32(4 + 4 * world))
+        breakdown = {"host_planner_ms": round(tm[0], 2), "call_ms": round(tm[1], 2),
+                     "per_device_ms": [{"symbolic": round(tm[4 + 4 * r], 2), "row_block_split": round(tm[5 + 4 * r], 2), "numeric_d2h_expand": round(tm[6 + 4 * r], 2),
+                                        "plan_release": round(tm[7 + 4 * r], 2)} for r in range(world)]}
         # what crosses PCIe device -> host per step: A, B and the compressed pattern (CSR row offsets + column runs; rows[] / cols[] are expanded on host)
         probe = F.Plan(pview, device=local_rank, dedupe=True)
         xfer = probe.pattern_transfer_info()
@@ -617,7 +629,7 @@ def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz):
         out = {"value": 2.0 * nnz * steps / sec, "unit": "nnz/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * sec / steps,
                "steps": steps, "n_devices": world, "call": "fem2d_galerkin_sample_gep_hcurl_multi (one process, one host thread per device, pinned host buffers)",
                "includes": "host planner + symbolic phase (pattern + source map) on every device + K1/K2/K3 + D2H of A, B and the compressed pattern (CSR row offsets, column runs) into pinned host buffers + host expansion of rows[] and cols[]",
-               "per_step_ms": per_step, "symbolic_phase_of_one_device": t_sym}
+               "per_step_ms": per_step, "last_call_breakdown": breakdown, "symbolic_phase_of_one_device": t_sym}
         if world == 1 and not args.no_extras:
             # the buffers a caller following INTEGRATION.md's plain-vector listing has: pageable view arrays, pageable outputs
             n_rows = np.empty(nnz, dtype=np.uint32); n_cols = np.empty(nnz, dtype=np.uint32); n_a = np.empty(nnz); n_b = np.empty(nnz)
@@ -637,7 +649,7 @@ def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz):
             out["caller_side_rebuild"] = {"seconds_per_matrix": reb, "what": "std::map<[u32;2], f64> filled from the sorted arrays with end hints + its destruction: stand-in for SparseMatrix::from_sorted_upper_tri (BTreeMap bulk build) in the Rust shim; NOT inside e2e.value",
                                           "e2e_ms_including_two_rebuilds_pinned": 1e3 * sec / steps + 2e3 * reb}
     if dist is not None:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
     return out
 
 

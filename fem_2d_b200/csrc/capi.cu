@@ -552,6 +552,8 @@ int fem2d_galerkin_sample_gep_hcurl(const fem2d_domain_view* view, int device, i
     return st;
 }
 
+namespace { double g_multi_ms[4 + 4 * 64]; }   // last multi-device call: host plan, then per device symbolic / split / numeric + D2H / release (ms)
+
 // One-shot call on several devices of ONE process: the host half of the symbolic phase runs once, then one host thread per device builds the
 // pattern on its device, takes block r of the two-level row partition (fem2d_plan_row_blocks_split), integrates what those rows read and
 // copies its slices of A, B (and the expanded rows / cols) to their slot positions in the caller's arrays.  No collective: the <= 2
@@ -573,8 +575,11 @@ int fem2d_galerkin_sample_gep_hcurl_multi(const fem2d_domain_view* view, uint32_
     try {
         fem2d::HostPlan host;
         std::string err;
+        const auto tm0 = std::chrono::steady_clock::now();
+        auto ms_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
         const int hst = fem2d::build_host_plan(view, true, host, err);
         if (hst != FEM2D_OK) return fail(hst, err);
+        g_multi_ms[0] = ms_since(tm0);
         if (host.n_pairs >= (1ull << 31)) return fail(FEM2D_ERR_UNSUPPORTED, "more than 2^31 pairs");
         std::vector<int> status(n_devices, FEM2D_OK);
         std::vector<std::string> message(n_devices);
@@ -587,7 +592,9 @@ int fem2d_galerkin_sample_gep_hcurl_multi(const fem2d_domain_view* view, uint32_
                 plan->p.host = host;               // every device plan owns a copy of the (small) host half
                 plan->p.device = devices[r];
                 std::string e2;
+                auto tw = std::chrono::steady_clock::now();
                 int st = fem2d::device_symbolic(plan->p, e2);
+                g_multi_ms[4 + 4 * r] = ms_since(tw); tw = std::chrono::steady_clock::now();
                 if (st == FEM2D_OK) {
                     nnz[r] = plan->p.nnz;
                     if (plan->p.nnz > capacity) { st = FEM2D_ERR_BAD_ARGUMENT; e2 = "output capacity too small (see *nnz_out)"; }
@@ -600,15 +607,19 @@ int fem2d_galerkin_sample_gep_hcurl_multi(const fem2d_domain_view* view, uint32_
                         st = fem2d_plan_row_blocks_split(plan, n_devices, b1.data(), b2.data());
                         begins[0] = b1[r]; ends[0] = b1[r + 1]; begins[1] = b2[r]; ends[1] = b2[r + 1]; n_ranges = 2;
                     }
+                    g_multi_ms[4 + 4 * r + 1] = ms_since(tw); tw = std::chrono::steady_clock::now();
                     if (st == FEM2D_OK)
                         st = assemble_ranges_impl(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, n_ranges, begins, ends, rows, cols, a_vals, b_vals,
                                                   true, host_threads);
                     if (st != FEM2D_OK) e2 = g_err;
+                    g_multi_ms[4 + 4 * r + 2] = ms_since(tw);
                 }
                 status[r] = st; message[r] = e2;
             } catch (std::bad_alloc&) { status[r] = FEM2D_ERR_OUT_OF_MEMORY; message[r] = "host allocation failed";
             } catch (std::exception& ex) { status[r] = FEM2D_ERR_INTERNAL; message[r] = ex.what(); }
+            const auto tr = std::chrono::steady_clock::now();
             if (plan) { fem2d::device_plan_release(plan->p); delete plan; }
+            g_multi_ms[4 + 4 * r + 3] = ms_since(tr);
         };
         if (n_devices == 1) work(0);
         else {
@@ -616,6 +627,7 @@ int fem2d_galerkin_sample_gep_hcurl_multi(const fem2d_domain_view* view, uint32_
             for (uint32_t r = 0; r < n_devices; r++) th.emplace_back(work, r);
             for (auto& t : th) t.join();
         }
+        g_multi_ms[1] = ms_since(tm0);
         if (nnz_out) *nnz_out = nnz[0];
         for (uint32_t r = 0; r < n_devices; r++) if (status[r] != FEM2D_OK) return fail(status[r], "device " + std::to_string(devices[r]) + ": " + message[r]);
         return FEM2D_OK;
@@ -681,6 +693,13 @@ int fem2d_fp64_peak(int device, int kind, double* gflops) {
     if (st != FEM2D_OK) return st;
     CKS(cudaSetDevice(device));
     CKS(fem2d::fp64_peak(kind, gflops));
+    return FEM2D_OK;
+}
+
+/* wall-clock breakdown of the last fem2d_galerkin_sample_gep_hcurl_multi call in ms: out[0] host planner, out[1] whole call, then per device
+ * r at out[4 + 4 r ..]: symbolic phase on the device, row-block split, numeric + D2H + host expansion, plan release.  Diagnostic, not in fem2d.h. */
+int fem2d_debug_multi_timing(double* out, uint32_t n) {
+    for (uint32_t k = 0; k < n && k < 4 + 4 * 64; k++) out[k] = g_multi_ms[k];
     return FEM2D_OK;
 }
 

@@ -309,7 +309,7 @@ void* pinned_acquire(size_t bytes, size_t* cap) {
 void pinned_release(void* p, size_t cap) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(g_pin_mu);
-    if (g_pin_free.size() < 8) { g_pin_free.push_back({p, cap}); return; }
+    if (g_pin_free.size() < 64) { g_pin_free.push_back({p, cap}); return; }   // (8 buffers per plan-building thread of a multi-device call)
     cudaFreeHost(p);
 }
 }  // namespace
