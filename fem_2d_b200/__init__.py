@@ -74,7 +74,7 @@ class _View(C.Structure):
 ABI_SYMBOLS = [
     "fem2d_symbolic", "fem2d_plan_free", "fem2d_plan_info", "fem2d_plan_check_work_items", "fem2d_plan_work_info", "fem2d_plan_source_map_info", "fem2d_plan_row_offsets", "fem2d_plan_pattern_transfer_info", "fem2d_plan_pattern", "fem2d_plan_pattern_device",
     "fem2d_assemble_device", "fem2d_assemble_device_ranges", "fem2d_plan_row_blocks_split", "fem2d_assemble_ranges", "fem2d_assemble", "fem2d_galerkin_sample_gep_hcurl", "fem2d_galerkin_sample_gep_hcurl_multi", "fem2d_plan_row_blocks",
-    "fem2d_plan_last_timing", "fem2d_plan_timing", "fem2d_plan_set_phase_timing", "fem2d_assemble_range", "fem2d_host_alloc", "fem2d_host_free", "fem2d_xy_fields", "fem2d_fp64_peak",
+    "fem2d_plan_last_timing", "fem2d_plan_timing", "fem2d_plan_set_phase_timing", "fem2d_assemble_range", "fem2d_host_alloc", "fem2d_host_free", "fem2d_trim_cache", "fem2d_xy_fields", "fem2d_fp64_peak",
     "fem2d_petsc_aij_size", "fem2d_petsc_aij_image", "fem2d_write_petsc_aij", "fem2d_device_count", "fem2d_status_string", "fem2d_last_error", "fem2d_version",
 ]
 HOST_ABI_SYMBOLS = [
@@ -799,6 +799,11 @@ def host_alloc(nbytes: int) -> int:
     if not p:
         raise BackendError(ERR_OUT_OF_MEMORY, "cudaMallocHost failed")
     return p
+
+
+def trim_cache() -> None:
+    """fem2d_trim_cache: hand the cached device blocks and pinned staging buffers back to the driver."""
+    _L.fem2d_trim_cache()
 
 
 def host_free(ptr: int) -> None:

@@ -680,6 +680,8 @@ int fem2d_write_petsc_aij(fem2d_plan* plan, const double* d_vals, const char* pa
     return st;
 }
 
+void fem2d_trim_cache(void) { fem2d::dev_cache_trim(); }
+
 void* fem2d_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }

@@ -237,6 +237,8 @@ constexpr size_t DEV_CACHE_BYTES = (size_t)8 << 30;   // at most this much memor
 constexpr size_t DEV_CACHE_BLOCKS = 96;
 }  // namespace
 
+namespace { extern cudaMemPool_t g_pool[64]; void pinned_trim(); }
+
 cudaError_t dev_malloc(void** p, size_t bytes, cudaStream_t st) {
     bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
     int dev = 0;
@@ -257,7 +259,8 @@ cudaError_t dev_malloc(void** p, size_t bytes, cudaStream_t st) {
             return cudaSuccess;
         }
     }
-    const cudaError_t e = cudaMallocAsync(p, bytes, st);
+    cudaMemPool_t pool = (dev >= 0 && dev < 64) ? g_pool[dev] : nullptr;
+    const cudaError_t e = pool ? cudaMallocFromPoolAsync(p, bytes, pool, st) : cudaMallocAsync(p, bytes, st);
     if (e == cudaSuccess) { std::lock_guard<std::mutex> lk(g_dev_mu); g_dev_live.push_back(DevBlk{*p, bytes, dev}); }
     return e;
 }
@@ -276,15 +279,41 @@ void dev_free(void* p, cudaStream_t st) {
     if (!cache) cudaFreeAsync(p, st);
 }
 
+namespace {
+cudaMemPool_t g_pool[64] = {};   // the library's own stream-ordered pool per device: the application's default pool keeps its settings
+}
+
 void dev_pool_init(int device) {
-    static bool done[64] = {};
-    if (device < 0 || device >= 64 || done[device]) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        unsigned long long thr = ~0ull;
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (device < 0 || device >= 64 || g_pool[device]) return;
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+        unsigned long long thr = ~0ull;   // keep freed memory in the pool: a one-shot caller builds and frees a plan per call
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        g_pool[device] = pool;
+    } else cudaGetLastError();
+}
+
+// Returns the cached device blocks and pinned staging buffers to the driver (fem2d_trim_cache).
+void dev_cache_trim() {
+    std::vector<DevBlk> blocks;
+    {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        blocks.swap(g_dev_free);
+        g_dev_cached = 0;
     }
-    done[device] = true;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (const DevBlk& b : blocks) { cudaSetDevice(b.dev); cudaFreeAsync(b.p, nullptr); }
+    for (int d = 0; d < 64; d++)
+        if (g_pool[d]) { cudaSetDevice(d); cudaStreamSynchronize(nullptr); cudaMemPoolTrimTo(g_pool[d], 0); }
+    cudaSetDevice(cur);
+    pinned_trim();
 }
 
 namespace {
@@ -305,6 +334,11 @@ void* pinned_acquire(size_t bytes, size_t* cap) {
     if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     *cap = bytes;
     return p;
+}
+void pinned_trim() {
+    std::vector<std::pair<void*, size_t>> bufs;
+    { std::lock_guard<std::mutex> lk(g_pin_mu); bufs.swap(g_pin_free); }
+    for (auto& b : bufs) cudaFreeHost(b.first);
 }
 void pinned_release(void* p, size_t cap) {
     if (!p) return;
@@ -562,6 +596,9 @@ int device_range_items(Plan& P, uint32_t n_ranges, const uint64_t* begins, const
     for (uint32_t k = 0; same && k < n_ranges; k++) same = begins[k] == P.range_begin[k] && ends[k] == P.range_end[k];
     if (same) { *d_items = P.d_range_items; *n_items = P.n_range_items; *split = P.range_split; return FEM2D_OK; }
     CK(cudaSetDevice(P.device));
+    // the previous restricted list may still be read by an integrator launched on the caller's stream: nothing below is ordered
+    // against that stream (null-stream kernels, blocking copies), so wait for the device before the list is replaced
+    CK(cudaDeviceSynchronize());
     unsigned char* d_flags = nullptr;
     CK(dev_malloc((void**)&d_flags, P.total_mt));
     CK(cudaMemsetAsync(d_flags, 0, P.total_mt, nullptr));

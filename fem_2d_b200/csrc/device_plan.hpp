@@ -100,6 +100,7 @@ struct Plan {
 cudaError_t dev_malloc(void** p, size_t bytes, cudaStream_t st = nullptr);
 void dev_free(void* p, cudaStream_t st = nullptr);
 void dev_pool_init(int device);
+void dev_cache_trim();   // give every cached device block and pinned staging buffer back to the driver
 
 constexpr uint32_t MAX_SLOT_RANGES = 4;   // slot ranges one numeric call can cover (multi-GPU: a rank's Elem-type rows + its edge-type rows)
 constexpr uint32_t SRC_CHUNK = 64;                     // slots per chunk of the packed source map

@@ -18,6 +18,8 @@
 // or 4 x 4 cross-direction pairs (A only; B is an exact zero) -- the same accumulator registers and about the same work.
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include "basis_device.cuh"
 #include "device_plan.hpp"
 
@@ -826,12 +828,18 @@ static cudaError_t launch_k2_part(const Plan& P, const WorkItem* d_items, uint32
     if ((smem - fixed) / per_pt < std::min<uint32_t>(npts, nv)) smem = std::min(hard, fixed + (size_t)std::min<uint32_t>(npts, nv) * per_pt);
     if ((smem - fixed) / per_pt == 0) return cudaErrorInvalidConfiguration;
     const uint32_t slab_doubles = (uint32_t)((smem - fixed) / sizeof(double));
-    static thread_local size_t smem_set[64] = {};   // per device: largest dynamic shared memory size already opted in (per NT)
-    if (P.device >= 0 && P.device < 64 && smem > smem_set[P.device]) {
-        cudaError_t e = cudaFuncSetAttribute(k2_exact_kernel<K2_TILE_P, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_exact_kernel<1, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        smem_set[P.device] = smem;
+    // Opt in to the device's full dynamic shared memory once per device (per NT), never less: the attribute is process-wide per
+    // kernel, so raising it on demand from several host threads (multi-device calls) could lower it under another thread's launch.
+    {
+        static std::mutex mu;
+        static bool done[64] = {};
+        std::lock_guard<std::mutex> lk(mu);
+        if (P.device >= 0 && P.device < 64 && !done[P.device]) {
+            cudaError_t e = cudaFuncSetAttribute(k2_exact_kernel<K2_TILE_P, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hard);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_exact_kernel<1, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hard);
+            if (e != cudaSuccess) return e;
+            done[P.device] = true;
+        }
     }
     K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, slab_doubles, follows_sampler, 0u};
     cudaLaunchConfig_t cfg = {};
@@ -861,11 +869,15 @@ static cudaError_t launch_k2_ws(const Plan& P, const WorkItem* d_items, uint32_t
     const size_t smem = std::min<size_t>(hard, (size_t)K2_WS_SMEM_KB * 1024);      // two CTAs per SM
     if ((smem - fixed) / K2_WS_NBUF < per_row) return cudaErrorInvalidConfiguration;   // launch_k2_exact checks ws_fits() first
     const uint32_t buf_doubles = (uint32_t)(((smem - fixed) / K2_WS_NBUF / sizeof(double)) & ~(size_t)1);   // even: buffers stay 16-byte aligned
-    static thread_local size_t smem_set[64] = {};
-    if (P.device >= 0 && P.device < 64 && smem > smem_set[P.device]) {
-        const cudaError_t e = cudaFuncSetAttribute(k2_ws_kernel<K2_TILE_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        smem_set[P.device] = smem;
+    {
+        static std::mutex mu;
+        static bool done[64] = {};
+        std::lock_guard<std::mutex> lk(mu);
+        if (P.device >= 0 && P.device < 64 && !done[P.device]) {
+            const cudaError_t e = cudaFuncSetAttribute(k2_ws_kernel<K2_TILE_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hard);
+            if (e != cudaSuccess) return e;
+            done[P.device] = true;
+        }
     }
     K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, buf_doubles, follows_sampler, list_cap};
     cudaLaunchConfig_t cfg = {};

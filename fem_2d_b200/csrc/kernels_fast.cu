@@ -312,7 +312,7 @@ cudaError_t launch_k2_dmma(Plan& P, uint32_t nu, uint32_t nv, uint32_t NO, uint3
     if (bytes_of(chunk) > hard) return cudaErrorInvalidConfiguration;
     const uint32_t PS = ps_of(chunk);
     const size_t smem = bytes_of(chunk);
-    cudaError_t e = cudaFuncSetAttribute(k2_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k2_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hard);   // always the full opt-in: never lowered under another thread's launch
     if (e != cudaSuccess) return e;
     DMArgs g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, (const DmmaItem*)P.d_dmma_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, chunk, PS};
     k2_dmma_kernel<<<P.n_dmma_items, DM_WARPS * 32, smem, st>>>(g);

@@ -119,6 +119,8 @@ int fem2d_plan_pattern_transfer_info(fem2d_plan* plan, uint64_t info[4]);
 /* Device pointers of the pattern (uint32 rows, cols; length nnz_upper). */
 int fem2d_plan_pattern_device(const fem2d_plan* plan, const uint32_t** d_rows, const uint32_t** d_cols);
 
+/* Concurrency: a plan supports ONE numeric call in flight on ONE stream at a time (its scratch -- tables, value buffer, restricted work-item
+ * list -- is shared by all calls).  The first call with a new set of slot ranges rebuilds the restricted list and synchronises the device. */
 /* Numeric phase (same replacement as fem2d_assemble below) into caller-provided DEVICE buffers d_a / d_b (nnz_upper doubles each, on the plan's device),
  * asynchronous on `stream` (a cudaStream_t, may be NULL).  GLQ nodes / weights are HOST inputs so the caller can pass
  * the exact values of gauss_quadrature_points (glq.rs:179-222, basis.rs:83-90).
@@ -201,6 +203,12 @@ int fem2d_plan_set_phase_timing(fem2d_plan* plan, int on);
 int fem2d_plan_last_timing(fem2d_plan* plan, float ms[4], uint32_t launches[4]);
 /* Same for the numeric call `calls_back` calls ago (0 = last; the plan keeps the events of its last 64 calls). */
 int fem2d_plan_timing(fem2d_plan* plan, uint32_t calls_back, float ms[4], uint32_t launches[4]);
+
+/* Memory kept by the library between calls: freed device blocks are parked in a process-wide cache (at most 8 GB / 96 blocks, served by the
+ * library's OWN stream-ordered pool per device -- the application's default pool keeps its settings) and a few pinned staging buffers are
+ * kept, so that a one-shot caller (one plan per call) does not pay the driver allocator every time.  fem2d_trim_cache returns all of it to
+ * the driver, e.g. before a downstream GPU eigensolver needs the memory.  Call it with no numeric call in flight. */
+void fem2d_trim_cache(void);
 
 /* Pinned host memory for outputs (so the D2H copy of a 1 GB value array runs at PCIe speed). */
 void* fem2d_host_alloc(size_t bytes);

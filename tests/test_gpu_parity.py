@@ -254,3 +254,20 @@ def test_swapped_integrals_and_slices():
     torch.cuda.synchronize()
     _assert_bit_identical(da.cpu().numpy(), a, "sliced A")
     _assert_bit_identical(db.cpu().numpy(), b, "sliced B")
+
+
+def test_trim_cache_returns_memory_and_the_library_keeps_working():
+    """fem2d_trim_cache hands the parked device blocks / pinned staging buffers back to the driver; the next plan allocates afresh and the
+    results do not change."""
+    import torch
+    mo, mf = recipes.build_pair("cfg4_small")
+    do, df = O.Domain.from_mesh(mo), F.Domain.from_mesh(mf)
+    glq = _glq(8, 8)
+    ref = O.galerkin_sample_gep_hcurl(do, glq=glq)
+    for _ in range(2):
+        rows, cols, a, b = F.Plan(df.view(), device=0).assemble(glq)
+        _assert_bit_identical(a, ref.a, "A"); _assert_bit_identical(b, ref.b, "B")
+        torch.cuda.synchronize()
+        free0 = torch.cuda.mem_get_info()[0]
+        F.trim_cache()
+        assert torch.cuda.mem_get_info()[0] >= free0
