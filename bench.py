@@ -71,6 +71,21 @@ def _ncu_traffic(workload, dedupe, world):
     return None if e is None else float(e["dram_bytes_read"] + e["dram_bytes_write"])
 
 
+def _ncu_traffic_k2(workload, dedupe, world):
+    """DRAM bytes of the integrator's kernels (persistent grid + small-item grid) of one launch, from the committed ncu captures."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if world != 1 or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    tot, seen = 0.0, False
+    for k in ("k2_ws_kernel", "k2_exact_kernel<4,64>"):
+        e = t.get(f"{k}/{workload}/dedupe{int(dedupe)}")
+        if e is not None:
+            tot += e["dram_bytes_read"] + e["dram_bytes_write"]; seen = True
+    return tot if seen else None
+
+
 def build_product_domain(workload: str):
     import fem_2d_b200 as F
     import recipes
@@ -313,7 +328,7 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": alg, "source_map_bytes_per_launch": map_bytes, "source_map_plain_chunks": smi["plain_chunks"],
                 "survey_8d_bytes_per_launch": 20.0 * n_slots, "kernel_ms": float(k3_ms), "share_of_step": float(k3_ms / tot_ms)}
 
-    def fp64_roofline(plan, g, k2_ms, tot_ms):
+    def fp64_roofline(plan, g, k2_ms, tot_ms, wl=None, dedupe=1):
         """Integrator roofline: algorithmic FP64 lane-operations of the reference's per-pair quadrature (fem2d_plan_work_info: 8 per same-
         direction pair and point + 4 per row, 3 + 2 for cross-direction pairs; nothing fusable, tile padding and slab staging not counted)
         over the integrator's device time, against the DMUL+DADD issue rate measured in this run.  At N > 1 every rank is charged 1/N of the
@@ -322,7 +337,7 @@ def run_ours(args):
         rate = ops / (k2_ms * 1e-3) / 1e9
         w = plan.work_info()
         return {"bound": "fp64_issue", "kernel": "k2_ws_kernel<4> + k2_exact_kernel<4,64> (exact per-pair integrator)", "achieved": rate, "peak": fp64_peak_gops,
-                "unit": "G lane-ops/s", "frac": rate / fp64_peak_gops, "traffic": None,
+                "unit": "G lane-ops/s", "frac": rate / fp64_peak_gops, "traffic": _ncu_traffic_k2(wl, dedupe, world) if wl else None,
                 "peak_source": "non-fused DMUL+DADD chain measured in this run (fem2d_fp64_peak kind 1); DFMA peak is 2x and unusable: every operation of the reference order is separately rounded",
                 "algorithmic_lane_ops_per_launch": ops, "same_pairs": w["same_pairs"], "cross_pairs": w["cross_pairs"],
                 "kernel_ms": float(k2_ms), "share_of_step": float(k2_ms / tot_ms)}
@@ -374,7 +389,7 @@ def run_ours(args):
                 "workload": WORKLOAD_TEXT["hp1m"], "n_dofs": hp.n_dofs, "nnz_upper_per_matrix": hp.nnz, "n_pairs": hp.info["n_pairs"],
                 "n_blocks": hp.info["n_blocks"], "n_classes": hp.info["n_classes"], "dedupe": 1, "glq": [g, g], "steps": n_hp, "n_gpus": world,
                 "ms_per_step": ms_hp, "value": 2.0 * hp.nnz / (ms_hp * 1e-3), "unit": "nnz/s", "phases_ms_rank0": hph,
-                "roofline": fp64_roofline(hp, g, k2_max, tot_max),
+                "roofline": fp64_roofline(hp, g, k2_max, tot_max, "hp1m", 1),
                 "roofline_hbm": hbm_roofline(hp, hr, hph["scatter_k3"], hph["sum"], "hp1m", 1),
             }
             del hp, ha, hb, hp_dom
@@ -393,7 +408,7 @@ def run_ours(args):
                 key = f"{workload}_dedupe{int(not bool(args.dedupe))}"
                 workloads[key] = {"workload": WORKLOAD_TEXT.get(workload, workload), "dedupe": int(not bool(args.dedupe)), "n_classes": pn.info["n_classes"],
                                   "ms_per_step": ms_nd, "value": 2.0 * nnz / (ms_nd * 1e-3), "unit": "nnz/s", "phases_ms": nph,
-                                  "roofline": fp64_roofline(pn, w["glq"], nph["integrator_k2"], nph["sum"]),
+                                  "roofline": fp64_roofline(pn, w["glq"], nph["integrator_k2"], nph["sum"], workload, int(not bool(args.dedupe))),
                                   "roofline_hbm": hbm_roofline(pn, [(0, nnz)], nph["scatter_k3"], nph["sum"], workload, int(not bool(args.dedupe)))}
                 del pn
             except Exception as ex:  # pragma: no cover
