@@ -210,9 +210,31 @@ int fem2d_plan_check_work_items(const fem2d_plan* plan, uint64_t out[4]) {
             }
         for (uint32_t t = 0; t < n_mt; t++) if (cover[t] == 0) bad++;   // no empty tiles in the numbering
     }
-    bool small_seen = false;   // launch order: the items that need the wide CTAs form a prefix (order_items)
+    // launch order: packs cover the item list exactly once, a pack of several items fits one round of contraction threads, stays within
+    // K2_PACK_STRIDE functions and holds non-local segments of one table pair only (pack_items); without packs the items that need the
+    // wide CTAs form a prefix (order_items)
+    if (!H.packs.empty()) {
+        uint32_t next = 0;
+        for (const PackDesc& pk : H.packs) {
+            if (pk.first != next || pk.n == 0 || pk.n > (uint32_t)K2_PACK_MAX || pk.first + pk.n > H.items.size()) { bad++; break; }
+            next = pk.first + pk.n;
+            if (pk.n > 1) {
+                uint32_t same = 0, cross = 0, stride = 0; uint64_t key = ~0ull;
+                for (uint32_t k = 0; k < pk.n; k++) {
+                    const WorkItem& it = H.items[pk.first + k];
+                    if (it.cls >= H.classes.size()) { bad++; continue; }
+                    same += it.n_same; cross += it.mt_count - it.n_same; stride += item_slab_stride(H, it);
+                    const ClassDesc& c = H.classes[it.cls];
+                    if (!c.local) { const uint64_t kk = (uint64_t)c.tabPu << 32 | c.tabPv; if (key != ~0ull && key != kk) bad++; key = kk; }
+                }
+                if (item_slots(same, same + cross) > (uint32_t)(K2_WS_CONS_WARPS * 32 * K2_WS_TPT) || stride > (uint32_t)K2_PACK_STRIDE) bad++;
+            }
+        }
+        if (next != H.items.size()) bad++;
+    }
+    bool small_seen = false;
     for (const WorkItem& it : H.items) {
-        if (it.cls < H.classes.size()) { const bool big = item_is_big(H, it); if (big && small_seen) bad++; small_seen |= !big; }
+        if (H.packs.empty() && it.cls < H.classes.size()) { const bool big = item_is_big(H, it); if (big && small_seen) bad++; small_seen |= !big; }
         if (it.cls >= H.classes.size() || it.n_ranges == 0 || it.n_ranges > (uint32_t)ITEM_MAX_RANGES) { bad++; continue; }
         const ClassDesc& c = H.classes[it.cls];
         const ListDesc& LP = H.lists[c.listP]; const ListDesc& LQ = H.lists[c.listQ];
@@ -418,11 +440,12 @@ int fem2d_assemble_device_ranges(fem2d_plan* plan, int basis_kind, int a_kind, i
     if (timed) CKS(cudaEventRecord(ev[1], s));
     if (mode == FEM2D_MODE_EXACT) {
         const fem2d::WorkItem* items = nullptr; uint32_t n_items = 0;
+        const fem2d::PackDesc* packs = nullptr;
         fem2d::ItemSplit split;
         std::string ierr;
-        const int ist = fem2d::device_range_items(p, n_ranges, slot_begins, slot_ends, &items, &n_items, &split, ierr);
+        const int ist = fem2d::device_range_items(p, n_ranges, slot_begins, slot_ends, &items, &n_items, &packs, &split, ierr);
         if (ist != FEM2D_OK) return fail(ist, ierr);
-        CKS(fem2d::launch_k2_exact(p, items, n_items, split.n_big, split.stride_big, split.stride_small, nu, nv, NO, NPT, s, &p.last_launches[1]));
+        CKS(fem2d::launch_k2_exact(p, items, n_items, packs, split, nu, nv, NO, NPT, s, &p.last_launches[1]));
     }
     else if (mode == FEM2D_MODE_SUMFACT) CKS(fem2d::launch_k2_sumfact(p, nu, nv, NO, NPT, s, &p.last_launches[1]));
     else CKS(fem2d::launch_k2_dmma(p, nu, nv, NO, NPT, s, &p.last_launches[1]));

@@ -366,7 +366,7 @@ int device_symbolic(Plan& P, std::string& err) {
     dev_pool_init(P.device);
     CK(cudaDeviceGetAttribute(&P.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, P.device));
     CK(cudaDeviceGetAttribute(&P.sm_count, cudaDevAttrMultiProcessorCount, P.device));
-    P.split = split_items(H, H.items);
+    P.split = split_items(H, H.items, H.packs);
 
     // ---- descriptor blob (plan-owned part first, then the scratch-only part), laid out identically on host and device
     std::vector<DevBlock> hb(H.blocks.size());
@@ -380,6 +380,7 @@ int device_symbolic(Plan& P, std::string& err) {
     const size_t o_si = desc.reserve(H.spec_i.size()), o_sj = desc.reserve(H.spec_j.size());
     const size_t o_tabs = desc.reserve(H.tables.size() * sizeof(TableDesc)), o_grams = desc.reserve(H.grams.size() * sizeof(GramDesc));
     const size_t o_items = desc.reserve(H.items.size() * sizeof(WorkItem));
+    const size_t o_packs = desc.reserve(H.packs.size() * sizeof(PackDesc));
     const size_t o_glq = desc.reserve(4 * 128 * sizeof(double));
     const size_t o_ctr = desc.reserve(256);
     std::vector<uint32_t> h_voff(H.classes.size() + 1), h_mtoff(H.classes.size() + 1);
@@ -403,6 +404,7 @@ int device_symbolic(Plan& P, std::string& err) {
     put(o_si, H.spec_i.data(), H.spec_i.size()); put(o_sj, H.spec_j.data(), H.spec_j.size());
     put(o_tabs, H.tables.data(), H.tables.size() * sizeof(TableDesc)); put(o_grams, H.grams.data(), H.grams.size() * sizeof(GramDesc));
     put(o_items, H.items.data(), H.items.size() * sizeof(WorkItem));
+    put(o_packs, H.packs.data(), H.packs.size() * sizeof(PackDesc));
     put(o_voff, h_voff.data(), h_voff.size() * 4); put(o_mtoff, h_mtoff.data(), h_mtoff.size() * 4);
     put(o_blocks, hb.data(), hb.size() * sizeof(DevBlock)); put(o_canon, H.canon_dof.data(), H.canon_dof.size() * 4);
 
@@ -434,6 +436,7 @@ int device_symbolic(Plan& P, std::string& err) {
     P.d_tables = at<TableDesc>(P.d_desc_arena, o_tabs); P.d_grams = at<GramDesc>(P.d_desc_arena, o_grams);
     P.d_items = at<WorkItem>(P.d_desc_arena, o_items); P.d_glq = at<double>(P.d_desc_arena, o_glq);
     P.d_work_counter = at<uint32_t>(P.d_desc_arena, o_ctr);
+    P.d_packs = at<PackDesc>(P.d_desc_arena, o_packs);
     P.d_class_voff = at<uint32_t>(P.d_desc_arena, o_voff); P.d_class_mtoff = at<uint32_t>(P.d_desc_arena, o_mtoff);
     DevBlock* d_blocks = at<DevBlock>(scratch, s_desc + (o_blocks - desc_plan_bytes));
     uint32_t* d_canon = at<uint32_t>(scratch, s_desc + (o_canon - desc_plan_bytes));
@@ -575,26 +578,32 @@ __global__ void mark_tiles_kernel(const uint32_t* __restrict__ src1, const uint3
 }
 }  // namespace
 
-ItemSplit split_items(const HostPlan& H, const std::vector<WorkItem>& items) {
-    // `items` is in launch order (plan_host.cpp order_items): the big items form a prefix
+ItemSplit split_items(const HostPlan& H, const std::vector<WorkItem>& items, const std::vector<PackDesc>& packs) {
+    // `items` is in launch order: packs (pack_items) or, without them, the big items as a prefix (order_items)
     ItemSplit sp;
     for (const WorkItem& it : items) {
         const uint32_t s = item_slab_stride(H, it);
         if (item_is_big(H, it)) { sp.n_big++; sp.stride_big = std::max(sp.stride_big, s); }
         else sp.stride_small = std::max(sp.stride_small, s);
     }
+    sp.n_packs = (uint32_t)packs.size();
+    for (const PackDesc& pk : packs) {
+        uint32_t s = 0;
+        for (uint32_t k = 0; k < pk.n; k++) s += item_slab_stride(H, items[pk.first + k]);
+        sp.stride_pack = std::max(sp.stride_pack, s);
+    }
     return sp;
 }
 
-int device_range_items(Plan& P, uint32_t n_ranges, const uint64_t* begins, const uint64_t* ends, const WorkItem** d_items, uint32_t* n_items, ItemSplit* split,
-                       std::string& err) {
+int device_range_items(Plan& P, uint32_t n_ranges, const uint64_t* begins, const uint64_t* ends, const WorkItem** d_items, uint32_t* n_items,
+                       const PackDesc** d_packs, ItemSplit* split, std::string& err) {
     if (n_ranges > MAX_SLOT_RANGES) { err = "too many slot ranges"; return FEM2D_ERR_BAD_ARGUMENT; }
     const bool full = n_ranges == 1 && begins[0] == 0 && ends[0] >= P.nnz;
     // restricting is pointless when the whole integrator is a single wave of CTAs anyway
-    if (full || P.total_mt < (uint64_t)4 * 148 * K2_THREADS) { *d_items = P.d_items; *n_items = (uint32_t)P.host.items.size(); *split = P.split; return FEM2D_OK; }
+    if (full || P.total_mt < (uint64_t)4 * 148 * K2_THREADS) { *d_items = P.d_items; *n_items = (uint32_t)P.host.items.size(); *d_packs = P.d_packs; *split = P.split; return FEM2D_OK; }
     bool same = P.d_range_items && n_ranges == P.range_n;
     for (uint32_t k = 0; same && k < n_ranges; k++) same = begins[k] == P.range_begin[k] && ends[k] == P.range_end[k];
-    if (same) { *d_items = P.d_range_items; *n_items = P.n_range_items; *split = P.range_split; return FEM2D_OK; }
+    if (same) { *d_items = P.d_range_items; *n_items = P.n_range_items; *d_packs = P.d_range_packs; *split = P.range_split; return FEM2D_OK; }
     CK(cudaSetDevice(P.device));
     // the previous restricted list may still be read by an integrator launched on the caller's stream: nothing below is ordered
     // against that stream (null-stream kernels, blocking copies), so wait for the device before the list is replaced
@@ -660,13 +669,18 @@ int device_range_items(Plan& P, uint32_t n_ranges, const uint64_t* begins, const
         }
         flush();
     }
-    order_items(P.host, items);
-    dev_free(P.d_range_items); P.d_range_items = nullptr;
-    CK(dev_malloc((void**)&P.d_range_items, std::max<size_t>(items.size(), 1) * sizeof(WorkItem)));
+    std::vector<PackDesc> packs;
+    pack_items(P.host, items, packs);
+    dev_free(P.d_range_items); P.d_range_items = nullptr; P.d_range_packs = nullptr;
+    const size_t item_bytes = (std::max<size_t>(items.size(), 1) * sizeof(WorkItem) + 255) & ~(size_t)255;
+    CK(dev_malloc((void**)&P.d_range_items, item_bytes + std::max<size_t>(packs.size(), 1) * sizeof(PackDesc)));
+    P.d_range_packs = reinterpret_cast<PackDesc*>(reinterpret_cast<char*>(P.d_range_items) + item_bytes);
     CK(cudaMemcpy(P.d_range_items, items.data(), items.size() * sizeof(WorkItem), cudaMemcpyHostToDevice));
+    if (!packs.empty()) CK(cudaMemcpy(P.d_range_packs, packs.data(), packs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice));
     P.n_range_items = (uint32_t)items.size(); P.range_n = n_ranges; P.range_mt_needed = needed;
-    P.range_split = split_items(P.host, items); *split = P.range_split;
+    P.range_split = split_items(P.host, items, packs); *split = P.range_split;
     for (uint32_t k = 0; k < n_ranges; k++) { P.range_begin[k] = begins[k]; P.range_end[k] = ends[k]; }
+    *d_packs = P.d_range_packs;
     *d_items = P.d_range_items; *n_items = P.n_range_items;
     return FEM2D_OK;
 }

@@ -8,7 +8,7 @@
 
 namespace fem2d {
 
-struct ItemSplit { uint32_t n_big = 0, stride_big = 0, stride_small = 0; };
+struct ItemSplit { uint32_t n_big = 0, stride_big = 0, stride_small = 0, n_packs = 0, stride_pack = 0; };   // stride_pack: widest slab row (all segments) of a pack
 
 struct Plan {
     int device = -1;   // -1: host-only plan (pattern + partitioning available, numeric entry points refuse)
@@ -68,6 +68,8 @@ struct Plan {
     // row-block restricted item list (multi-GPU sharding of the integrator), valid for [range_begin, range_end)
     uint32_t range_n = 0;
     uint64_t range_begin[4] = {0, 0, 0, 0}, range_end[4] = {0, 0, 0, 0};
+    PackDesc* d_packs = nullptr;         // packs of host.items (desc arena)
+    PackDesc* d_range_packs = nullptr;   // packs of the restricted item list (same allocation as d_range_items)
     WorkItem* d_range_items = nullptr;
     uint32_t n_range_items = 0;
     ItemSplit split, range_split;        // size split of host.items / of the restricted item list
@@ -116,8 +118,8 @@ int device_symbolic(Plan& plan, std::string& err);
 int device_row_block_bounds(const Plan& plan, uint32_t world, uint64_t* bounds, std::string& err);
 // Work items of the exact integrator restricted to the micro-tiles that the slots [begin, end) read (cached per plan for the last
 // range; the full item list is returned for the full range and for plans too small to be worth restricting).
-int device_range_items(Plan& plan, uint32_t n_ranges, const uint64_t* begins, const uint64_t* ends, const WorkItem** d_items, uint32_t* n_items, ItemSplit* split,
-                       std::string& err);
+int device_range_items(Plan& plan, uint32_t n_ranges, const uint64_t* begins, const uint64_t* ends, const WorkItem** d_items, uint32_t* n_items,
+                       const PackDesc** d_packs, ItemSplit* split, std::string& err);
 // First slot whose row is >= `row` (binary search over the device pattern).
 int device_first_slot_of_row(const Plan& plan, uint32_t row, uint64_t* slot, std::string& err);
 int device_row_block_bounds_range(const Plan& plan, uint64_t lo, uint64_t hi, uint32_t world, uint64_t* bounds, std::string& err);
@@ -129,11 +131,11 @@ void device_plan_release(Plan& plan);
 
 // kernels_exact.cu  (compiled with -fmad=false)
 cudaError_t launch_k1_tables(const Plan& plan, int basis_kind, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st);
-cudaError_t launch_k2_exact(const Plan& plan, const WorkItem* d_items, uint32_t n_items, uint32_t n_big, uint32_t stride_big, uint32_t stride_small,
+cudaError_t launch_k2_exact(const Plan& plan, const WorkItem* d_items, uint32_t n_items, const PackDesc* d_packs, const ItemSplit& split,
                             uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches);
 // Size split of an item list ordered by mt_count (largest first): number of items that need K2_THREADS-wide CTAs and the widest
 // slab row (pad4(U) + pad4(V) functions of P, + of Q unless local) among the classes of each part.
-ItemSplit split_items(const HostPlan& host, const std::vector<WorkItem>& items);
+ItemSplit split_items(const HostPlan& host, const std::vector<WorkItem>& items, const std::vector<PackDesc>& packs);
 cudaError_t fp64_peak(int kind, double* gflops);
 cudaError_t ws_profile(unsigned long long out[8], int reset);   // tuning builds (-DFEM2D_WS_PROFILE): cycle counters of k2_ws_kernel
 

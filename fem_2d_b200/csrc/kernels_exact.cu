@@ -58,6 +58,7 @@ struct K2Args {
     // before exiting, so that a grid waiting on this one has transitively waited on both.
     int follows_sampler;
     uint32_t list_cap;   // warp-specialised integrator: bytes reserved per cached BasisSpec order list (>= the longest list, multiple of 16)
+    uint32_t col_cap;    // ... and entries of its column table (>= the widest pack's slab row, multiple of 4)
 };
 
 __device__ __forceinline__ uint32_t pad4(uint32_t x) { return (x + 3u) & ~3u; }
@@ -356,14 +357,24 @@ __global__ void __launch_bounds__(NT, NT == K2_THREADS ? K2_MIN_CTAS : K2_SMALL_
 // stage and never meet a CTA-wide barrier: while they contract chunk k the staging warp prepares chunk k+1 -- of the same round, of
 // the next round, or of the next work item (its descriptor loads, FP64 quotients and first slab included).  Same tiles, same
 // per-pair operation order as k2_exact_kernel: results are bit-identical.
-struct alignas(16) WsCtx {
+// One work unit of the persistent kernel is a PACK of up to K2_PACK_MAX work items (segments) that share a round: small items of
+// different classes whose micro-tiles together fill the contraction threads (plan_types.h PackDesc).  A big item is a pack of one.
+struct alignas(16) WsSeg {
     WorkItem it;
     SubBlocks sb;
     double ratio_uv, ratio_vu, maxdet, coefA, coefB;
+    double jiuP, jivP, jiuQ, jivQ, su, sv;       // staging: jac_inv entries and P's para_scale
     unsigned long long v_off;
-    uint32_t nP, nUP, nQ, nUQ, strideP, strideQ, local, chunk_rows, n_slots, gap, end, pad;
+    uint32_t nP, nUP, nQ, nUQ, strideP, strideQ, local;
+    uint32_t slab_off;                           // doubles per chunk POINT in front of this segment's slabs
+    uint32_t same_off, cross_off;                // first thread slot of the segment inside the same- / cross-direction group of the round
+    uint32_t listP_off, listQ_off, tabPu, tabPv; // staging: order lists and P-side tables
 };
-constexpr int K2_WS_NCTX = K2_WS_NBUF + 2;   // item contexts in flight: the staging warp runs at most NBUF chunks (>= items) ahead
+struct alignas(16) WsCtx {
+    WsSeg seg[K2_PACK_MAX];
+    uint32_t n_seg, chunk_rows, n_slots, gap, n_same, end, pad0, pad1;   // n_same: same-direction tiles of all segments (they come first)
+};
+constexpr int K2_WS_NCTX = K2_WS_NBUF + 2;   // pack contexts in flight: the staging warp runs at most NBUF chunks (>= packs) ahead
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -437,55 +448,61 @@ __device__ __forceinline__ void ws_stage_column(const double* __restrict__ colA,
     }
 }
 
-// Stages the slab columns an item needs for the quadrature rows [m0, m0 + nrow) with the 32 lanes of one warp (same values, same
-// operation order as the staging pass of k2_exact_kernel).  One task = one function column for the whole chunk: its (i, j) orders
-// are looked up once, the v-axis table values of WS_NB points are held in registers while the rows m run inside, so the inner body
-// is four FP64 operations and two shared-memory stores per (function, point) with no loads in the dependent chain.
-__device__ __forceinline__ void ws_stage_chunk(const K2Args& g, const WsCtx& c, const ClassDesc& cd, double jiuP, double jivP, double jiuQ, double jivQ,
-                                               const double* s_tab, const uint8_t* s_spec, double* buf, uint32_t m0, uint32_t nrow, uint32_t lane) {
+// Stages the slab columns a pack needs for the quadrature rows [m0, m0 + nrow) with the 32 lanes of one warp (same values, same
+// operation order as the staging pass of k2_exact_kernel).  One task = one function column of one segment for the whole chunk, taken
+// from the pack's column table (segment | side | column), so the lanes stay busy whatever the widths of the segments: the column's
+// (i, j) orders are looked up once, the v-axis table values of four points are held in registers while the rows m run inside, and the
+// inner body is four FP64 operations and two shared-memory stores per (function, point) with no loads in the dependent chain.
+__device__ __forceinline__ void ws_stage_chunk(const K2Args& g, const WsCtx& c, const uint32_t* s_cols, uint32_t n_cols, const double* s_tab, const uint8_t* s_spec,
+                                               double* buf, uint32_t chunk, uint32_t m0, uint32_t nrow, uint32_t lane) {
     const uint32_t nv = g.nv, AS = g.NO * g.NPT;
-    const uint32_t chunk = c.chunk_rows * nv;
-    double* s_CP = buf; double* s_FP = s_CP + (size_t)chunk * c.strideP;
-    double* s_CQ = c.local ? s_CP : s_FP + (size_t)chunk * c.strideP;
-    double* s_FQ = c.local ? s_FP : s_CQ + (size_t)chunk * c.strideQ;
-    for (int side = 0; side < (c.local ? 1 : 2); side++) {
-        const uint32_t stride = side ? c.strideQ : c.strideP, nF = side ? c.nQ : c.nP, nUF = side ? c.nUQ : c.nUP;
+    for (uint32_t t = lane; t < n_cols; t += 32) {
+        const uint32_t e = s_cols[t], col = e & 0xffffu, side = (e >> 16) & 1u;
+        const WsSeg& sg = c.seg[e >> 17];
+        const uint32_t strideP = sg.strideP, strideQ = sg.strideQ;
+        const uint32_t stride = side ? strideQ : strideP, nF = side ? sg.nQ : sg.nP, nUF = side ? sg.nUQ : sg.nUP;
+        double* seg_buf = buf + (size_t)chunk * sg.slab_off;
+        // slabs of a segment: C_P [chunk][strideP], F_P, then (non-local) C_Q [chunk][strideQ], F_Q
+        double* sC = seg_buf + (side ? (size_t)chunk * 2 * strideP : 0);
+        double* sF = sC + (size_t)chunk * stride;
         // table cache slots: 0 / 1 = the scaled u / v tables of a non-local P side, 2 / 3 = the unscaled tables (every Q side, local P sides)
-        const uint32_t slot_u = (side || c.local) ? 2u : 0u;
-        const double* tu = s_tab + (size_t)slot_u * 4 * AS;
-        const double* tv = s_tab + (size_t)(slot_u + 1) * 4 * AS;
-        const uint8_t* sp_i = s_spec + (size_t)(2 * side) * g.list_cap; const uint8_t* sp_j = sp_i + g.list_cap;
-        const double jiu = side ? jiuQ : jiuP, jiv = side ? jivQ : jivP;
-        // derivative scale = the OTHER function's para_scale (integrals.rs:44,47); Q's is (1,1), P's is (su,sv)
-        const double ps0 = side ? cd.su : 1.0, ps1 = side ? cd.sv : 1.0;
-        double* sC = side ? s_CQ : s_CP; double* sF = side ? s_FQ : s_FP;
+        const uint32_t slot_u = (side || sg.local) ? 2u : 0u;
+        const double* tu = s_tab + (size_t)slot_u * 3 * AS;          // cached tables hold N, T, T' (N' is never sampled on this path)
+        const double* tv = s_tab + (size_t)(slot_u + 1) * 3 * AS;
+        const uint8_t* sp_i = s_spec + ((size_t)(e >> 17) * 4 + 2 * side) * g.list_cap; const uint8_t* sp_j = sp_i + g.list_cap;
         const uint32_t padU = pad4(nUF);
-        for (int grp = 0; grp < 2; grp++) {
-            const uint32_t c_lo = c.it.stage[side][grp][0], c_hi = c.it.stage[side][grp][1];   // only the functions this item's tiles touch
-            for (uint32_t col = c_lo + lane; col < c_hi; col += 32) {
-                // a padding column of a 4-wide tile row takes the values of the group's last function: only pairs beyond the block's last
-                // row / column read it, and their results are never stored
-                const bool isU = col < padU;
-                const uint32_t a = isU ? min(col, nUF - 1) : nUF + min(col - padU, nF - nUF - 1);
-                const uint32_t i = sp_i[a], j = sp_j[a];
-                // U-directed: curl = -((jiu * (N_i(m) * T'_j(n))) * ps0), val = (jiu * N_i(m)) * T_j(n)        (basis.rs:225-242)
-                // V-directed: curl =   (jiv * (T'_i(m) * N_j(n))) * ps1,  val = (jiv * T_i(m)) * N_j(n)        (basis.rs:230-252)
-                const double* rowA = tu + (isU ? 0 : 3) * AS + i * g.NPT;   // factor of the curl taken at m: N_i | T'_i
-                const double* rowB = tu + (isU ? 0 : 2) * AS + i * g.NPT;   // factor of the value taken at m: N_i | T_i
-                const double* colA = tv + (isU ? 3 : 0) * AS + j * g.NPT;   // factor of the curl taken at n: T'_j | N_j
-                const double* colB = tv + (isU ? 2 : 0) * AS + j * g.NPT;   // factor of the value taken at n: T_j | N_j
-                const double jj = isU ? jiu : jiv, ps = isU ? ps0 : ps1;
-                const bool scaled = ps != 1.0;                 // x * 1.0 == x bit for bit: the product is skipped
-                const int flip = isU ? (int)0x80000000 : 0;    // IEEE negation = sign-bit flip, done in the integer pipe
-                // eight independent chains per step, written stage by stage so that the in-order issue of the single staging warp never
-                // waits on the 8-cycle FP64 latency: 4 points x 2 quadrature rows, then 4 points x the odd last row
-                const uint32_t npair = nrow & ~1u;
-                if (npair) ws_stage_column<4, 2>(colA, colB, rowA + m0, rowB + m0, jj, ps, scaled, flip, sC + col, sF + col, stride, nv, npair);
-                if (nrow & 1u) ws_stage_column<4, 1>(colA, colB, rowA + m0 + npair, rowB + m0 + npair, jj, ps, scaled, flip,
-                                                     sC + col + (size_t)npair * nv * stride, sF + col + (size_t)npair * nv * stride, stride, nv, 1u);
-            }
-        }
+        // a padding column of a 4-wide tile row takes the values of the group's last function: only pairs beyond the block's last
+        // row / column read it, and their results are never stored
+        const bool isU = col < padU;
+        const uint32_t a = isU ? min(col, nUF - 1) : nUF + min(col - padU, nF - nUF - 1);
+        const uint32_t i = sp_i[a], j = sp_j[a];
+        // U-directed: curl = -((jiu * (N_i(m) * T'_j(n))) * ps0), val = (jiu * N_i(m)) * T_j(n)        (basis.rs:225-242)
+        // V-directed: curl =   (jiv * (T'_i(m) * N_j(n))) * ps1,  val = (jiv * T_i(m)) * N_j(n)        (basis.rs:230-252)
+        // cache layout: [N | T | T'] x order x point
+        const double* rowA = tu + (isU ? 0 : 2) * AS + i * g.NPT;   // factor of the curl taken at m: N_i | T'_i
+        const double* rowB = tu + (isU ? 0 : 1) * AS + i * g.NPT;   // factor of the value taken at m: N_i | T_i
+        const double* colA = tv + (isU ? 2 : 0) * AS + j * g.NPT;   // factor of the curl taken at n: T'_j | N_j
+        const double* colB = tv + (isU ? 1 : 0) * AS + j * g.NPT;   // factor of the value taken at n: T_j | N_j
+        const double jj = isU ? (side ? sg.jiuQ : sg.jiuP) : (side ? sg.jivQ : sg.jivP);
+        // derivative scale = the OTHER function's para_scale (integrals.rs:44,47); Q's is (1,1), P's is (su,sv)
+        const double ps = side ? (isU ? sg.su : sg.sv) : 1.0;
+        const bool scaled = ps != 1.0;                 // x * 1.0 == x bit for bit: the product is skipped
+        const int flip = isU ? (int)0x80000000 : 0;    // IEEE negation = sign-bit flip, done in the integer pipe
+        // eight independent chains per step, written stage by stage so that the in-order issue of the single staging warp never
+        // waits on the 8-cycle FP64 latency: 4 points x 2 quadrature rows, then 4 points x the odd last row
+        const uint32_t npair = nrow & ~1u;
+        if (npair) ws_stage_column<4, 2>(colA, colB, rowA + m0, rowB + m0, jj, ps, scaled, flip, sC + col, sF + col, stride, nv, npair);
+        if (nrow & 1u) ws_stage_column<4, 1>(colA, colB, rowA + m0 + npair, rowB + m0 + npair, jj, ps, scaled, flip,
+                                             sC + col + (size_t)npair * nv * stride, sF + col + (size_t)npair * nv * stride, stride, nv, 1u);
     }
+}
+
+// Copies the N, T, T' arrays of sampled table `id` (K1 layout [N | N' | T | T'] x order x point) into a cache slot.
+__device__ __forceinline__ void ws_cache_table(const K2Args& g, uint32_t id, double* dst, uint32_t lane) {
+    const uint32_t AS = g.NO * g.NPT;
+    const double* src = g.tabs + (size_t)id * 4 * AS;
+#pragma unroll 4
+    for (uint32_t k = lane; k < AS; k += 32) { dst[k] = src[k]; dst[AS + k] = src[2 * AS + k]; dst[2 * AS + k] = src[3 * AS + k]; }
 }
 
 // One pass of a TP x 2 sub-tile over one quadrature row: inner += ((p * q) [* scale]) * v_w[n] for n = 0 .. nv-1 (glq.rs:24-28), then
@@ -544,7 +561,7 @@ __device__ unsigned long long g_ws_prof[8];
 #endif
 
 template <int TP>
-__global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const uint32_t n_items, uint32_t* __restrict__ work_counter) {
+__global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const PackDesc* __restrict__ packs, const uint32_t n_packs, uint32_t* __restrict__ work_counter) {
     extern __shared__ __align__(16) double smem[];
     constexpr uint32_t CONS = K2_WS_CONS_WARPS * 32;
     double* s_uw = smem;                       // [128]
@@ -553,15 +570,16 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const uin
     uint64_t* s_empty = s_full + K2_WS_NBUF;                      // [NBUF]
     WsCtx* s_ctx = reinterpret_cast<WsCtx*>(smem + 256 + 2 * K2_WS_NBUF);
     static_assert(sizeof(WsCtx) % 16 == 0, "context ring keeps the slabs 16-byte aligned");
-    // staging-warp caches: four sampled tables (slots 0 / 1: scaled u / v tables of a non-local P side; 2 / 3: the unscaled u / v tables)
-    // and the (i, j) order lists of the current item's P and Q sides
-    const uint32_t AS4 = 4 * g.NO * g.NPT;
+    // staging-warp caches: four sampled tables (slots 0 / 1: scaled u / v tables of the non-local P sides of the current pack; 2 / 3: the
+    // unscaled u / v tables) and the (i, j) order lists of the P and Q sides of every segment of the current pack
+    const uint32_t AS3 = 3 * g.NO * g.NPT;
     double* s_tab = smem + 256 + 2 * K2_WS_NBUF + K2_WS_NCTX * sizeof(WsCtx) / sizeof(double);
-    uint8_t* s_spec = reinterpret_cast<uint8_t*>(s_tab + 4 * (size_t)AS4);
-    double* s_slab = reinterpret_cast<double*>(s_spec + 4 * (size_t)g.list_cap);
+    uint8_t* s_spec = reinterpret_cast<uint8_t*>(s_tab + 4 * (size_t)AS3);
+    uint32_t* s_cols = reinterpret_cast<uint32_t*>(s_spec + (size_t)K2_PACK_MAX * 4 * g.list_cap);   // column table of the current pack
+    double* s_slab = reinterpret_cast<double*>(s_cols + g.col_cap);
     const uint32_t buf_doubles = g.slab_doubles;   // per ring buffer
     const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const uint32_t nu = g.nu, nv = g.nv, npts = nu * nv;
+    const uint32_t nu = g.nu, nv = g.nv;
 
     if (!g.follows_sampler) cudaTriggerProgrammaticLaunchCompletion();
     if (threadIdx.x == 0) {
@@ -580,7 +598,7 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const uin
     if (warp == 0) {
         // ================================================================================================ staging warp
         // (warp 0: the warp schedulers favour the oldest warp of a CTA, and staging must stay ahead of seven contraction warps)
-        for (uint32_t k = lane; k < 2 * AS4; k += 32) s_tab[2 * (size_t)AS4 + k] = g.tabs[k];   // tables 0 / 1: unscaled u / v points
+        ws_cache_table(g, 0u, s_tab + 2 * (size_t)AS3, lane); ws_cache_table(g, 1u, s_tab + 3 * (size_t)AS3, lane);   // tables 0 / 1: unscaled u / v points
         uint32_t cached_u = 0xffffffffu, cached_v = 0xffffffffu;                                 // table ids held by slots 0 / 1
         for (;;) {
             WS_T(t_item0);
@@ -588,79 +606,88 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const uin
             if (lane == 0) idx = atomicAdd(work_counter, 1u);
             idx = __shfl_sync(0xffffffffu, idx, 0);
             WsCtx& c = s_ctx[ci];
-            if (idx >= n_items) {   // end marker: travels through the ring like a chunk
+            if (idx >= n_packs) {   // end marker: travels through the ring like a chunk
                 if (lane == 0) c.end = 1u;
                 mbar_wait(&s_empty[stage], phase ^ 1u);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_full[stage]);
                 break;
             }
-            const WorkItem it = g.items[idx];
-            const ClassDesc cd = g.classes[it.cls];
-            const uint32_t nP = cd.lp.n, nUP = cd.lp.nU, nQ = cd.lq.n, nUQ = cd.lq.nU;
-            const uint32_t strideP = pad4(nUP) + pad4(nP - nUP);
-            const uint32_t strideQ = cd.local ? strideP : pad4(nUQ) + pad4(nQ - nUQ);
-            // whole quadrature rows per chunk (the launch makes sure one row of the widest class fits a ring buffer)
-            const uint32_t chunk_rows = min(nu, buf_doubles / (2 * nv * (strideP + (cd.local ? 0u : strideQ))));
-            // per-class constants (HierCurlBasisFn::defined_over, basis.rs:395-413; M2D::det / inverse, space.rs:138-147): the nine
-            // FP64 quotients, one per lane
-            const double detP = cd.dxP * cd.dyP - 0.0 * 0.0, detQ = cd.dxQ * cd.dyQ - 0.0 * 0.0;
-            double quot = 0.0;
-            if (lane < 9) {
-                const uint32_t k = lane;
-                const double num = k == 0 ? cd.dyP : k == 1 ? cd.dxP : k == 2 ? cd.dyQ : k == 3 ? cd.dxQ : k == 4 ? cd.dxP : k == 5 ? cd.dxQ : k == 6 ? cd.dyP : k == 7 ? cd.dyQ : 1.0;
-                const double den = k < 2 ? detP : k < 4 ? detQ : k == 4 ? cd.dyP : k == 5 ? cd.dyQ : k == 6 ? cd.dxP : k == 7 ? cd.dxQ : cd.mu;
-                quot = num / den;
-            }
-            const double jiuP = __shfl_sync(0xffffffffu, quot, 0), jivP = __shfl_sync(0xffffffffu, quot, 1);   // jac_inv.u[0] = dy_dv / det, jac_inv.v[1] = dx_du / det
-            const double jiuQ = __shfl_sync(0xffffffffu, quot, 2), jivQ = __shfl_sync(0xffffffffu, quot, 3);
-            const double q4 = __shfl_sync(0xffffffffu, quot, 4), q5 = __shfl_sync(0xffffffffu, quot, 5), q6 = __shfl_sync(0xffffffffu, quot, 6);
-            const double q7 = __shfl_sync(0xffffffffu, quot, 7), q8 = __shfl_sync(0xffffffffu, quot, 8);
-            const uint32_t gap = item_gap(it.n_same, it.mt_count), n_slots = it.mt_count + gap;
-            if (lane == 0) {
-                c.it = it;
-                c.sb = make_subblocks(nP, nUP, nQ, nUQ, cd.local, TP);
+            const PackDesc pk = packs[idx];
+            // ---- one lane per segment: work item, class, the nine FP64 quotients, tile enumeration -> context
+            if (lane < pk.n) {
+                WsSeg& sg = c.seg[lane];
+                const WorkItem it = g.items[pk.first + lane];
+                const ClassDesc cd = g.classes[it.cls];
+                const uint32_t nP = cd.lp.n, nUP = cd.lp.nU, nQ = cd.lq.n, nUQ = cd.lq.nU;
+                // per-class constants (HierCurlBasisFn::defined_over, basis.rs:395-413; M2D::det / inverse, space.rs:138-147)
+                const double detP = cd.dxP * cd.dyP - 0.0 * 0.0, detQ = cd.dxQ * cd.dyQ - 0.0 * 0.0;
                 const double ge = (double)(detP >= detQ), lt = (double)(detP < detQ);
-                c.ratio_uv = ge * q4 + lt * q5;   // max_uv_ratios integrals.rs:250-259, basis.rs:341-343: ge * (dxP / dyP) + lt * (dxQ / dyQ)
-                c.ratio_vu = ge * q6 + lt * q7;   // max_vu_ratios integrals.rs:262-271, basis.rs:346-348: ge * (dyP / dxP) + lt * (dyQ / dxQ)
-                c.maxdet = detP > detQ ? detP : detQ;                   // partial_max integrals.rs:421-423
-                c.coefA = q8;                                           // 1.0 / mu, integrals.rs:37
-                c.coefB = cd.eps * (cd.su * cd.sv) * (1.0 * 1.0);       // eps * p.glq_scale() * q.glq_scale() integrals.rs:303-305
-                c.v_off = cd.v_off;
-                c.nP = nP; c.nUP = nUP; c.nQ = nQ; c.nUQ = nUQ; c.strideP = strideP; c.strideQ = strideQ; c.local = cd.local;
-                c.chunk_rows = chunk_rows; c.n_slots = n_slots; c.gap = gap; c.end = 0u;
+                sg.it = it;
+                sg.sb = make_subblocks(nP, nUP, nQ, nUQ, cd.local, TP);
+                sg.jiuP = cd.dyP / detP; sg.jivP = cd.dxP / detP;      // jac_inv.u[0] = dy_dv / det, jac_inv.v[1] = dx_du / det
+                sg.jiuQ = cd.dyQ / detQ; sg.jivQ = cd.dxQ / detQ;
+                sg.ratio_uv = ge * (cd.dxP / cd.dyP) + lt * (cd.dxQ / cd.dyQ);   // max_uv_ratios integrals.rs:250-259, basis.rs:341-343
+                sg.ratio_vu = ge * (cd.dyP / cd.dxP) + lt * (cd.dyQ / cd.dxQ);   // max_vu_ratios integrals.rs:262-271, basis.rs:346-348
+                sg.maxdet = detP > detQ ? detP : detQ;                           // partial_max integrals.rs:421-423
+                sg.coefA = 1.0 / cd.mu;                                          // integrals.rs:37
+                sg.coefB = cd.eps * (cd.su * cd.sv) * (1.0 * 1.0);               // eps * p.glq_scale() * q.glq_scale() integrals.rs:303-305
+                sg.su = cd.su; sg.sv = cd.sv;
+                sg.v_off = cd.v_off;
+                sg.nP = nP; sg.nUP = nUP; sg.nQ = nQ; sg.nUQ = nUQ; sg.local = cd.local;
+                sg.strideP = pad4(nUP) + pad4(nP - nUP);
+                sg.strideQ = cd.local ? sg.strideP : pad4(nUQ) + pad4(nQ - nUQ);
+                sg.listP_off = cd.lp.off; sg.listQ_off = cd.lq.off; sg.tabPu = cd.tabPu; sg.tabPv = cd.tabPv;
             }
-            // caches: the P side's scaled tables of a local-desc class (the ancestor sampled over the descendant, basis.rs:372-393) and
-            // the order lists of both sides
-            if (!cd.local) {
-                if (cached_u != cd.tabPu) {
-                    const double* src = g.tabs + (size_t)cd.tabPu * AS4;
+            __syncwarp();
+            // ---- slot / slab offsets of the segments, chunk size
+            uint32_t tot_stride = 0, n_same = 0, n_cross = 0, tab_u = 0xffffffffu, tab_v = 0xffffffffu;
+            for (uint32_t s2 = 0; s2 < pk.n; s2++) {
+                WsSeg& sg = c.seg[s2];
+                if (lane == 0) { sg.slab_off = 2 * tot_stride; sg.same_off = n_same; sg.cross_off = n_cross; }
+                tot_stride += sg.strideP + (sg.local ? 0u : sg.strideQ);
+                n_same += sg.it.n_same; n_cross += sg.it.mt_count - sg.it.n_same;
+                if (!sg.local) { tab_u = sg.tabPu; tab_v = sg.tabPv; }   // the planner packs non-local segments of one table pair only
+            }
+            // whole quadrature rows per chunk (the launch makes sure one row of the widest pack fits a ring buffer)
+            const uint32_t chunk_rows = min(nu, buf_doubles / (2 * nv * tot_stride));
+            const uint32_t gap = item_gap(n_same, n_same + n_cross), n_slots = n_same + n_cross + gap;
+            if (lane == 0) { c.n_seg = pk.n; c.chunk_rows = chunk_rows; c.n_slots = n_slots; c.gap = gap; c.n_same = n_same; c.end = 0u; }
+            // ---- caches: the scaled P-side tables (the ancestor sampled over the descendant, basis.rs:372-393) and the order lists
+            if (tab_u != 0xffffffffu && cached_u != tab_u) { ws_cache_table(g, tab_u, s_tab, lane); cached_u = tab_u; }
+            if (tab_v != 0xffffffffu && cached_v != tab_v) { ws_cache_table(g, tab_v, s_tab + AS3, lane); cached_v = tab_v; }
+            for (uint32_t s2 = 0; s2 < pk.n; s2++) {
+                const WsSeg& sg = c.seg[s2];
+                uint8_t* sp = s_spec + (size_t)s2 * 4 * g.list_cap;
 #pragma unroll 4
-                    for (uint32_t k = lane; k < AS4; k += 32) s_tab[k] = src[k];
-                    cached_u = cd.tabPu;
-                }
-                if (cached_v != cd.tabPv) {
-                    const double* src = g.tabs + (size_t)cd.tabPv * AS4;
+                for (uint32_t k = lane; k < sg.nP; k += 32) { sp[k] = g.spec_i[sg.listP_off + k]; sp[g.list_cap + k] = g.spec_j[sg.listP_off + k]; }
+                if (!sg.local) {
 #pragma unroll 4
-                    for (uint32_t k = lane; k < AS4; k += 32) s_tab[AS4 + k] = src[k];
-                    cached_v = cd.tabPv;
+                    for (uint32_t k = lane; k < sg.nQ; k += 32) { sp[2 * g.list_cap + k] = g.spec_i[sg.listQ_off + k]; sp[3 * g.list_cap + k] = g.spec_j[sg.listQ_off + k]; }
                 }
             }
-#pragma unroll 4
-            for (uint32_t k = lane; k < nP; k += 32) { s_spec[k] = g.spec_i[cd.lp.off + k]; s_spec[g.list_cap + k] = g.spec_j[cd.lp.off + k]; }
-            if (!cd.local) {
-#pragma unroll 4
-                for (uint32_t k = lane; k < nQ; k += 32) { s_spec[2 * g.list_cap + k] = g.spec_i[cd.lq.off + k]; s_spec[3 * g.list_cap + k] = g.spec_j[cd.lq.off + k]; }
+            // ---- column table: every slab column the pack's tiles touch, as segment | side | column
+            uint32_t n_cols = 0;
+            for (uint32_t s2 = 0; s2 < pk.n; s2++) {
+                const WsSeg& sg = c.seg[s2];
+                for (uint32_t side = 0; side < (sg.local ? 1u : 2u); side++)
+                    for (uint32_t grp = 0; grp < 2; grp++) {
+                        const uint32_t c_lo = sg.it.stage[side][grp][0], c_w = sg.it.stage[side][grp][1] - c_lo;   // only the functions this item's tiles touch
+                        for (uint32_t k = lane; k < c_w; k += 32) s_cols[n_cols + k] = s2 << 17 | side << 16 | (c_lo + k);
+                        n_cols += c_w;
+                    }
             }
             __syncwarp();
             WS_T(t_item1); WS_ADD(0, t_item1 - t_item0); WS_ADD(5, 1);
+            const uint32_t chunk = chunk_rows * nv;
             for (uint32_t round0 = 0; round0 < n_slots; round0 += K2_WS_TPT * CONS) {
                 for (uint32_t m0 = 0; m0 < nu; m0 += chunk_rows) {
                     const uint32_t nrow = min(chunk_rows, nu - m0);
                     WS_T(t_w0);
                     mbar_wait(&s_empty[stage], phase ^ 1u);     // the contraction warps are done with what this buffer held
                     WS_T(t_w1);
-                    ws_stage_chunk(g, c, cd, jiuP, jivP, jiuQ, jivQ, s_tab, s_spec, s_slab + (size_t)stage * buf_doubles, m0, nrow, lane);
+                    double* buf = s_slab + (size_t)stage * buf_doubles;
+                    ws_stage_chunk(g, c, s_cols, n_cols, s_tab, s_spec, buf, chunk, m0, nrow, lane);
                     __syncwarp();
                     WS_T(t_w2); WS_ADD(1, t_w1 - t_w0); WS_ADD(2, t_w2 - t_w1); WS_ADD(6, 1);
                     if (lane == 0) mbar_arrive(&s_full[stage]);
@@ -674,32 +701,35 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const uin
         const uint32_t tid = threadIdx.x - 32;   // 0 .. CONS-1
         for (;;) {
             WS_T(t_f0);
-            mbar_wait(&s_full[stage], phase);   // first chunk of the next item (or the end marker); its context is complete
+            mbar_wait(&s_full[stage], phase);   // first chunk of the next pack (or the end marker); its context is complete
             WS_T(t_f1);
             if (warp == 1) WS_ADD(7, t_f1 - t_f0);
             const WsCtx& c = s_ctx[ci];
             if (c.end) break;
-            const uint32_t n_slots = c.n_slots, gap = c.gap, n_same = c.it.n_same;
-            const uint32_t nUP = c.nUP, nUQ = c.nUQ, nQ = c.nQ, strideP = c.strideP, strideQ = c.strideQ, chunk_rows = c.chunk_rows;
+            const uint32_t n_slots = c.n_slots, gap = c.gap, n_same = c.n_same, n_seg = c.n_seg, chunk_rows = c.chunk_rows;
             const uint32_t chunk = chunk_rows * nv;
-            const double maxdet = c.maxdet, coefA = c.coefA, coefB = c.coefB;
-            double2* out = g.V + c.v_off;
             bool first = true;
             // K2_WS_TPT micro-tiles per thread and round: every staged chunk feeds TPT x CONS tiles
             for (uint32_t round0 = 0; round0 < n_slots; round0 += K2_WS_TPT * CONS) {
-                // ---- my micro-tiles of this round: code = sub | row tile << 2 | column tile << 17, 0xffffffff = none
+                // ---- my micro-tiles of this round: code = sub | segment << 2 | row tile << 4 | column tile << 18, 0xffffffff = none
                 uint32_t code[K2_WS_TPT], prow[K2_WS_TPT], pcol[K2_WS_TPT];
 #pragma unroll
                 for (int t = 0; t < K2_WS_TPT; t++) {
                     const uint32_t slot = round0 + t * CONS + tid;
                     code[t] = 0xffffffffu; prow[t] = 0; pcol[t] = 0;
                     if (slot < n_slots && !(slot >= n_same && slot < n_same + gap)) {
-                        uint32_t li = slot < n_same ? slot : slot - gap, r = 0, sub, rt, ct;
-                        while (li >= c.it.rcount[r]) { li -= c.it.rcount[r]; r++; }        // which of the item's tile ranges
-                        decode_tile(c.sb, c.it.rbegin[r] + li, TP, sub, rt, ct);
-                        code[t] = sub | rt << 2 | ct << 17;
-                        prow[t] = (sub >= 2 ? pad4(nUP) - nUP : 0) + c.sb.row0[sub] + rt * TP;               // slab column of the canonical row index
-                        pcol[t] = ((sub & 1) ? pad4(nUQ) - nUQ : 0) + c.sb.col0[sub] + ct * mt_width(sub);
+                        // segment: the same-direction tiles of all segments come first (segment by segment), then the cross-direction ones
+                        const bool is_same = slot < n_same;
+                        const uint32_t k = is_same ? slot : slot - n_same - gap;
+                        uint32_t sgi = 0;
+                        while (sgi + 1 < n_seg && k >= (is_same ? c.seg[sgi + 1].same_off : c.seg[sgi + 1].cross_off)) sgi++;
+                        const WsSeg& sg = c.seg[sgi];
+                        uint32_t li = is_same ? k - sg.same_off : sg.it.n_same + (k - sg.cross_off), r = 0, sub, rt, ct;
+                        while (li >= sg.it.rcount[r]) { li -= sg.it.rcount[r]; r++; }        // which of the item's tile ranges
+                        decode_tile(sg.sb, sg.it.rbegin[r] + li, TP, sub, rt, ct);
+                        code[t] = sub | sgi << 2 | rt << 4 | ct << 18;
+                        prow[t] = (sub >= 2 ? pad4(sg.nUP) - sg.nUP : 0) + sg.sb.row0[sub] + rt * TP;               // slab column of the canonical row index
+                        pcol[t] = ((sub & 1) ? pad4(sg.nUQ) - sg.nUQ : 0) + sg.sb.col0[sub] + ct * mt_width(sub);
                     }
                 }
                 // sol[t][0] / sol[t][1]: A / B of a same-direction tile; columns 0-1 / 2-3 (A only) of a cross-direction tile
@@ -720,16 +750,18 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const uin
                     WS_T(t_c1);
                     if (warp == 1) WS_ADD(3, t_c1 - t_c0);
                     const double* buf = s_slab + (size_t)stage * buf_doubles;
-                    const double* s_CP = buf; const double* s_FP = s_CP + (size_t)chunk * strideP;
-                    const double* s_CQ = c.local ? s_CP : s_FP + (size_t)chunk * strideP;
-                    const double* s_FQ = c.local ? s_FP : s_CQ + (size_t)chunk * strideQ;
 #pragma unroll
                     for (int t = 0; t < K2_WS_TPT; t++) {
                         if (code[t] == 0xffffffffu) continue;
                         const uint32_t sub = code[t] & 3u;
+                        const WsSeg& sg = c.seg[(code[t] >> 2) & 3u];
+                        const uint32_t strideP = sg.strideP, strideQ = sg.strideQ;
+                        const double* s_CP = buf + (size_t)chunk * sg.slab_off; const double* s_FP = s_CP + (size_t)chunk * strideP;
+                        const double* s_CQ = sg.local ? s_CP : s_FP + (size_t)chunk * strideP;
                         const double* cp = s_CP + prow[t]; const double* cq = s_CQ + pcol[t];
                         if (sub == 0 || sub == 3) {
-                            const double ratio = sub == 0 ? c.ratio_uv : c.ratio_vu;
+                            const double* s_FQ = sg.local ? s_FP : s_CQ + (size_t)chunk * strideQ;
+                            const double ratio = sub == 0 ? sg.ratio_uv : sg.ratio_vu, maxdet = sg.maxdet;
                             const double* fp = s_FP + prow[t]; const double* fq = s_FQ + pcol[t];
                             for (uint32_t r = 0; r < nrow; r++) {
                                 const double uw = s_uw[m0 + r];
@@ -755,9 +787,13 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const uin
 #pragma unroll
                 for (int t = 0; t < K2_WS_TPT; t++) {
                     if (code[t] == 0xffffffffu) continue;
-                    const uint32_t sub = code[t] & 3u, rt = (code[t] >> 2) & 0x7fffu, ct = code[t] >> 17;
-                    const uint32_t row0 = c.sb.row0[sub] + rt * TP, col0 = c.sb.col0[sub] + ct * mt_width(sub);
-                    const uint32_t row_end = c.sb.row0[sub] + c.sb.rows[sub], col_end = c.sb.col0[sub] + c.sb.cols[sub];
+                    const uint32_t sub = code[t] & 3u, rt = (code[t] >> 4) & 0x3fffu, ct = code[t] >> 18;
+                    const WsSeg& sg = c.seg[(code[t] >> 2) & 3u];
+                    const uint32_t row0 = sg.sb.row0[sub] + rt * TP, col0 = sg.sb.col0[sub] + ct * mt_width(sub);
+                    const uint32_t row_end = sg.sb.row0[sub] + sg.sb.rows[sub], col_end = sg.sb.col0[sub] + sg.sb.cols[sub];
+                    const uint32_t nQ = sg.nQ;
+                    const double coefA = sg.coefA, coefB = sg.coefB;
+                    double2* out = g.V + sg.v_off;
                     if (sub == 0 || sub == 3) {
 #pragma unroll
                         for (int r = 0; r < TP; r++) {
@@ -847,7 +883,7 @@ static cudaError_t launch_k2_part(const Plan& P, const WorkItem* d_items, uint32
             done[P.device] = true;
         }
     }
-    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, slab_doubles, follows_sampler, 0u};
+    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, slab_doubles, follows_sampler, 0u, 0u};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(count); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -859,17 +895,18 @@ static cudaError_t launch_k2_part(const Plan& P, const WorkItem* d_items, uint32
 
 // Shared memory of the warp-specialised integrator in front of its slab ring: weights, mbarriers, item contexts, the staging warp's
 // table cache (4 tables) and order-list cache (4 lists).
-static size_t ws_fixed_smem(const Plan& P, uint32_t NO, uint32_t NPT) {
+static size_t ws_fixed_smem(const Plan& P, uint32_t NO, uint32_t NPT, uint32_t max_stride) {
     const size_t list_cap = (P.host.max_list_n + 15u) & ~(size_t)15;
-    return (256 + 2 * K2_WS_NBUF) * sizeof(double) + K2_WS_NCTX * sizeof(WsCtx) + 4 * (size_t)(4 * NO * NPT) * sizeof(double) + 4 * list_cap;
+    return (256 + 2 * K2_WS_NBUF) * sizeof(double) + K2_WS_NCTX * sizeof(WsCtx) + 4 * (size_t)(3 * NO * NPT) * sizeof(double) + (size_t)K2_PACK_MAX * 4 * list_cap +
+           (size_t)((max_stride + 3u) & ~3u) * sizeof(uint32_t);
 }
 
-// Persistent, warp-specialised launch of the big items [0, count): two CTAs per SM, each with a ring of K2_WS_NBUF slab buffers.
-static cudaError_t launch_k2_ws(const Plan& P, const WorkItem* d_items, uint32_t count, uint32_t max_stride, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT,
-                                int follows_sampler, cudaStream_t st) {
+// Persistent, warp-specialised launch over the packs [0, count) of an item list: two CTAs per SM, each with a ring of K2_WS_NBUF slab buffers.
+static cudaError_t launch_k2_ws(const Plan& P, const WorkItem* d_items, const PackDesc* d_packs, uint32_t count, uint32_t max_stride, uint32_t nu, uint32_t nv,
+                                uint32_t NO, uint32_t NPT, int follows_sampler, cudaStream_t st) {
     if (count == 0) return cudaSuccess;
     const uint32_t list_cap = (P.host.max_list_n + 15u) & ~15u;
-    const size_t fixed = ws_fixed_smem(P, NO, NPT);
+    const size_t fixed = ws_fixed_smem(P, NO, NPT, max_stride);
     const size_t per_row = (size_t)max_stride * 2 * sizeof(double) * nv;     // chunks are whole quadrature rows
     const size_t hard = (size_t)P.max_smem_optin - 1024;
     const size_t smem = std::min<size_t>(hard, (size_t)K2_WS_SMEM_KB * 1024);      // two CTAs per SM
@@ -885,41 +922,51 @@ static cudaError_t launch_k2_ws(const Plan& P, const WorkItem* d_items, uint32_t
             done[P.device] = true;
         }
     }
-    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, buf_doubles, follows_sampler, list_cap};
+    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, buf_doubles, follows_sampler, list_cap, (max_stride + 3u) & ~3u};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(std::min<uint32_t>(count, (uint32_t)(K2_MIN_CTAS * std::max(P.sm_count, 1)))); cfg.blockDim = dim3(K2_WS_THREADS);
     cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, k2_ws_kernel<K2_TILE_P>, g, count, P.d_work_counter);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k2_ws_kernel<K2_TILE_P>, g, d_packs, count, P.d_work_counter);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // The warp-specialised integrator stages whole quadrature rows: one row (nv points) of the widest class must fit a ring buffer.
 static bool ws_fits(const Plan& P, uint32_t max_stride, uint32_t nv, uint32_t NO, uint32_t NPT) {
-    const size_t fixed = ws_fixed_smem(P, NO, NPT);
+    const size_t fixed = ws_fixed_smem(P, NO, NPT, max_stride);
     const size_t smem = std::min<size_t>((size_t)P.max_smem_optin - 1024, (size_t)K2_WS_SMEM_KB * 1024);
     return smem > fixed && (smem - fixed) / K2_WS_NBUF >= (size_t)max_stride * 2 * sizeof(double) * nv;
 }
 
-// Items are ordered by size (largest first); the first n_big of them run in K2_THREADS-wide CTAs, the rest in K2_SMALL_THREADS-wide
+// Without packs (latency shape, FEM2D_K2_WS=0) the items are ordered by size (largest first); the first n_big of them run in K2_THREADS-wide CTAs, the rest in K2_SMALL_THREADS-wide
 // ones.  The small-item grid goes first: its CTAs (8 per SM) fill the whole machine for about one wave, and the big-item CTAs move
 // in as they drain (measured on cfg 4: 0.464 -> 0.452 ms against big-first, where the small grid ran in the big grid's tail at low
 // occupancy).  Both launches carry the programmatic-dependent-launch attribute: the second grid starts once every CTA of the first has
 // passed its wait for the sampler, runs alongside it and waits for its completion before exiting, so that whoever waits on the
 // second grid (the scatter kernel) transitively waits on the first.
-cudaError_t launch_k2_exact(const Plan& P, const WorkItem* d_items, uint32_t n_items, uint32_t n_big, uint32_t stride_big, uint32_t stride_small,
+cudaError_t launch_k2_exact(const Plan& P, const WorkItem* d_items, uint32_t n_items, const PackDesc* d_packs, const ItemSplit& sp,
                             uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches) {
     if (n_items == 0) return cudaSuccess;
-    n_big = std::min(n_big, n_items);
+    if (sp.n_packs) {
+        // throughput shape: every item runs in the persistent warp-specialised grid, small items packed several to a round.  Fallback when
+        // one quadrature row of the widest pack does not fit a ring buffer (very high orders, very many GLQ points): k2_exact_kernel
+        // with 256-thread CTAs for every item (it chunks by points, not rows).
+        if (ws_fits(P, sp.stride_pack, nv, NO, NPT)) {
+            if (launches) (*launches)++;
+            return launch_k2_ws(P, d_items, d_packs, sp.n_packs, sp.stride_pack, nu, nv, NO, NPT, 1, st);
+        }
+        if (launches) (*launches)++;
+        return launch_k2_part<K2_THREADS>(P, d_items, n_items, std::max(sp.stride_big, sp.stride_small), (K2_MIN_CTAS == 2 ? 100 : 216 / K2_MIN_CTAS) * 1024, nu, nv, NO, NPT, 1, st);
+    }
+    const uint32_t n_big = std::min(sp.n_big, n_items);
     const uint32_t n_small = n_items - n_big;
     // small CTAs: 1/8 of an SM's shared memory each; big CTAs: prefer <= ~100 KB of shared memory so two share an SM
-    cudaError_t e = launch_k2_part<K2_SMALL_THREADS>(P, d_items + n_big, n_small, stride_small, 27 * 1024, nu, nv, NO, NPT, 1, st);
+    cudaError_t e = launch_k2_part<K2_SMALL_THREADS>(P, d_items + n_big, n_small, sp.stride_small, 27 * 1024, nu, nv, NO, NPT, 1, st);
     if (e != cudaSuccess) return e;
     if (launches && n_small) (*launches)++;
-    if (P.host.tile_p == K2_TILE_P && P.host.use_ws && ws_fits(P, stride_big, nv, NO, NPT)) e = launch_k2_ws(P, d_items, n_big, stride_big, nu, nv, NO, NPT, n_small == 0, st);
-    else e = launch_k2_part<K2_THREADS>(P, d_items, n_big, stride_big, (K2_MIN_CTAS == 2 ? 100 : 216 / K2_MIN_CTAS) * 1024, nu, nv, NO, NPT, n_small == 0, st);
+    e = launch_k2_part<K2_THREADS>(P, d_items, n_big, sp.stride_big, (K2_MIN_CTAS == 2 ? 100 : 216 / K2_MIN_CTAS) * 1024, nu, nv, NO, NPT, n_small == 0, st);
     if (launches && n_big) (*launches)++;
     return e;
 }

@@ -134,6 +134,59 @@ void order_items(const HostPlan& H, std::vector<WorkItem>& items) {
     std::stable_partition(items.begin(), items.end(), [&](const WorkItem& it) { return item_is_big(H, it); });
 }
 
+void pack_items(const HostPlan& H, std::vector<WorkItem>& items, std::vector<PackDesc>& packs) {
+    packs.clear();
+    if (!(H.use_ws && H.tile_p == (uint32_t)K2_TILE_P)) { order_items(H, items); return; }
+    const uint32_t round_slots = (uint32_t)(K2_WS_CONS_WARPS * 32 * K2_WS_TPT);
+    struct Bin { std::vector<uint32_t> seg; uint32_t same = 0, cross = 0, stride = 0; uint64_t key = ~0ull; };
+    auto slots_of = [](uint32_t same, uint32_t cross) { return item_slots(same, same + cross); };
+    auto key_of = [&](const WorkItem& it) {   // scaled tables of a non-local item's P side; ~0 for local items (they only use the unscaled tables)
+        const ClassDesc& c = H.classes[it.cls];
+        return c.local ? ~0ull : ((uint64_t)c.tabPu << 32 | c.tabPv);
+    };
+    std::vector<uint32_t> order(items.size());
+    for (uint32_t k = 0; k < items.size(); k++) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return items[a].mt_count > items[b].mt_count; });
+    std::vector<Bin> bins;
+    std::vector<uint32_t> open;   // bins that may still take a segment (a bounded window keeps the first-fit search linear)
+    for (uint32_t k : order) {
+        const WorkItem& it = items[k];
+        const uint32_t same = it.n_same, cross = it.mt_count - it.n_same, stride = item_slab_stride(H, it);
+        const uint64_t key = key_of(it);
+        int target = -1;
+        if (slots_of(same, cross) < round_slots && stride <= (uint32_t)K2_PACK_STRIDE) {
+            for (uint32_t b : open) {
+                const Bin& B = bins[b];
+                if (B.seg.size() >= (size_t)K2_PACK_MAX || B.stride + stride > (uint32_t)K2_PACK_STRIDE) continue;
+                if (slots_of(B.same + same, B.cross + cross) > round_slots) continue;
+                if (key != ~0ull && B.key != ~0ull && B.key != key) continue;
+                target = (int)b; break;
+            }
+        }
+        if (target < 0) {
+            bins.push_back(Bin());
+            target = (int)bins.size() - 1;
+            if (slots_of(same, cross) + 16 < round_slots && stride < (uint32_t)K2_PACK_STRIDE) {
+                open.push_back((uint32_t)target);
+                if (open.size() > 64) open.erase(open.begin());
+            }
+        }
+        Bin& B = bins[target];
+        B.seg.push_back(k); B.same += same; B.cross += cross; B.stride += stride;
+        if (key != ~0ull) B.key = key;
+    }
+    std::vector<uint32_t> bo(bins.size());
+    for (uint32_t k = 0; k < bins.size(); k++) bo[k] = k;
+    std::stable_sort(bo.begin(), bo.end(), [&](uint32_t a, uint32_t b) { return bins[a].same + bins[a].cross > bins[b].same + bins[b].cross; });
+    std::vector<WorkItem> out;
+    out.reserve(items.size());
+    for (uint32_t b : bo) {
+        packs.push_back(PackDesc{(uint32_t)out.size(), (uint32_t)bins[b].seg.size()});
+        for (uint32_t k : bins[b].seg) out.push_back(items[k]);
+    }
+    items.swap(out);
+}
+
 int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::string& err) {
     if (!v) { err = "null view"; return FEM2D_ERR_BAD_ARGUMENT; }
     // Reference error order: continuity condition, then empty DoF set (galerkin.rs:42-50).
@@ -410,7 +463,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
             if (e > b) P.items.push_back(make_item(P, c, {{b, e - b}}, nullptr));
         }
     }
-    order_items(P, P.items);
+    pack_items(P, P.items, P.packs);
     return FEM2D_OK;
 }
 

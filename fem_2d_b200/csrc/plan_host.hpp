@@ -23,6 +23,7 @@ struct HostPlan {
     std::vector<ClassDesc> classes;
     std::vector<BlockDesc> blocks;
     std::vector<WorkItem> items;
+    std::vector<PackDesc> packs;        // throughput shape: consecutive items the persistent integrator runs together (empty otherwise)
     std::vector<double> elem_dx, elem_dy;   // dx_du, dy_dv per Elem
     uint64_t n_pairs = 0;    // == number of (p,q) integrations the reference performs (x2 for A and B)
     uint64_t n_values = 0;   // entries of V
@@ -42,6 +43,11 @@ WorkItem make_item(const HostPlan& plan, uint32_t cls, const std::vector<std::pa
 uint32_t item_slab_stride(const HostPlan& plan, const WorkItem& it);
 bool item_is_big(const HostPlan& plan, const WorkItem& it);
 void order_items(const HostPlan& plan, std::vector<WorkItem>& items);
+// Throughput shape with the persistent integrator: groups the items into packs (plan_types.h PackDesc) -- items that fill a round on their
+// own stay alone, smaller ones are packed first-fit (largest first) while their micro-tiles fit one round of contraction threads, their
+// slab rows stay within K2_PACK_STRIDE functions and their non-local segments share one pair of scaled tables -- and reorders `items` so
+// that every pack is contiguous, packs with the most micro-tiles first.  Leaves `packs` empty (and `items` in order_items order) otherwise.
+void pack_items(const HostPlan& plan, std::vector<WorkItem>& items, std::vector<PackDesc>& packs);
 
 // Returns FEM2D_OK or a status from include/fem2d.h; err receives a detail message.
 int build_host_plan(const fem2d_domain_view* view, bool dedupe, HostPlan& plan, std::string& err);

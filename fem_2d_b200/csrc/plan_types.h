@@ -43,7 +43,7 @@ constexpr int MT_QX = 4;           // cross-direction micro-tile (both shapes; 1
 #define FEM2D_K2_WS_NBUF 2
 #endif
 #ifndef FEM2D_K2_WS_SMEM_KB
-#define FEM2D_K2_WS_SMEM_KB 110
+#define FEM2D_K2_WS_SMEM_KB 112
 #endif
 #ifndef FEM2D_K2_WS_TPT
 #define FEM2D_K2_WS_TPT 1
@@ -110,6 +110,15 @@ struct WorkItem {
     uint32_t rbegin[ITEM_MAX_RANGES];     // first micro-tile of each range (class-local numbering)
     uint16_t rcount[ITEM_MAX_RANGES];
     uint16_t stage[2][2][2];              // [side: P, Q][direction group: U, V][begin, end): slab columns to stage
+};
+
+// A pack: K2_PACK_MAX or fewer consecutive work items that the persistent integrator processes together (their micro-tiles share the
+// contraction threads of one round, their slabs share a ring buffer).  Items with more tiles than one round holds are packs of one.
+constexpr int K2_PACK_MAX = 4;
+constexpr int K2_PACK_STRIDE = 224;   // widest slab row (functions of all segments, P + Q sides) of a pack of several items
+struct PackDesc {
+    uint32_t first;   // first work item
+    uint32_t n;       // number of work items (segments)
 };
 
 struct BlockDesc {
