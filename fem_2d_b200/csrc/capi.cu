@@ -227,7 +227,7 @@ int fem2d_plan_check_work_items(const fem2d_plan* plan, uint64_t out[4]) {
                     const ClassDesc& c = H.classes[it.cls];
                     if (!c.local) { const uint64_t kk = (uint64_t)c.tabPu << 32 | c.tabPv; if (key != ~0ull && key != kk) bad++; key = kk; }
                 }
-                if (item_slots(same, same + cross) > (uint32_t)(K2_WS_CONS_WARPS * 32 * K2_WS_TPT) || stride > (uint32_t)K2_PACK_STRIDE) bad++;
+                if (item_slots(same, same + cross) > H.ws_round_slots() || stride > (uint32_t)K2_PACK_STRIDE) bad++;
             }
         }
         if (next != H.items.size()) bad++;
@@ -281,7 +281,8 @@ int fem2d_plan_work_info(const fem2d_plan* plan, uint64_t out[8]) {
         out[2] += sb.cnt[0] + sb.cnt[3]; out[3] += sb.cnt[1] + sb.cnt[2];
         out[6] += (uint64_t)LP.n + (c.local ? 0u : LQ.n);
     }
-    out[4] = (uint64_t)H.tile_p * MT_Q; out[5] = (uint64_t)H.tile_p * MT_QX; out[7] = H.items.size();
+    out[4] = (uint64_t)H.tile_p * MT_Q; out[5] = (uint64_t)H.tile_p * MT_QX;
+    out[7] = (H.use_ws && H.tile_p == (uint32_t)K2_TILE_P) ? H.ws_prod : 0u;
     return FEM2D_OK;
 }
 

@@ -625,7 +625,7 @@ int device_range_items(Plan& P, uint32_t n_ranges, const uint64_t* begins, const
     // items: per class, the runs of needed tiles (gaps of up to 2 tiles are bridged) packed into CTAs of <= ITEM_MAX_RANGES runs and
     // <= 2 * K2_THREADS tiles; every item records which function columns its tiles touch so it stages only those.
     std::vector<WorkItem> items;
-    const uint32_t cap = K2_ROUNDS * (P.host.use_ws && P.host.tile_p == (uint32_t)K2_TILE_P ? K2_WS_CONS_WARPS * 32 : K2_THREADS) - 31, gap = 2, tp = P.host.tile_p;   // tiles; + up to 31 slots of warp alignment (item_slots)
+    const uint32_t cap = K2_ROUNDS * (P.host.use_ws && P.host.tile_p == (uint32_t)K2_TILE_P ? P.host.ws_round_slots() / K2_WS_TPT : (uint32_t)K2_THREADS) - 31, gap = 2, tp = P.host.tile_p;   // tiles; + up to 31 slots of warp alignment (item_slots)
     uint64_t needed = 0, off = 0;
     std::vector<std::pair<uint32_t, uint32_t>> runs, cur;
     for (uint32_t c = 0; c < P.host.classes.size(); c++) {

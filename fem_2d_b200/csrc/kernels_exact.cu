@@ -453,10 +453,11 @@ __device__ __forceinline__ void ws_stage_column(const double* __restrict__ colA,
 // from the pack's column table (segment | side | column), so the lanes stay busy whatever the widths of the segments: the column's
 // (i, j) orders are looked up once, the v-axis table values of four points are held in registers while the rows m run inside, and the
 // inner body is four FP64 operations and two shared-memory stores per (function, point) with no loads in the dependent chain.
+template <int PROD>
 __device__ __forceinline__ void ws_stage_chunk(const K2Args& g, const WsCtx& c, const uint32_t* s_cols, uint32_t n_cols, const double* s_tab, const uint8_t* s_spec,
                                                double* buf, uint32_t chunk, uint32_t m0, uint32_t nrow, uint32_t lane) {
     const uint32_t nv = g.nv, AS = g.NO * g.NPT;
-    for (uint32_t t = lane; t < n_cols; t += 32) {
+    for (uint32_t t = lane; t < n_cols; t += PROD * 32) {   // `lane`: index across the staging warps
         const uint32_t e = s_cols[t], col = e & 0xffffu, side = (e >> 16) & 1u;
         const WsSeg& sg = c.seg[e >> 17];
         const uint32_t strideP = sg.strideP, strideQ = sg.strideQ;
@@ -560,9 +561,10 @@ __device__ unsigned long long g_ws_prof[8];
 #define WS_ADD(k, v)
 #endif
 
-template <int TP>
+template <int TP, int PROD>
 __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const PackDesc* __restrict__ packs, const uint32_t n_packs, uint32_t* __restrict__ work_counter) {
     extern __shared__ __align__(16) double smem[];
+    constexpr int K2_WS_PROD_WARPS = PROD, K2_WS_CONS_WARPS = K2_WS_WARPS - PROD;   // staging / contraction warps of this instantiation
     constexpr uint32_t CONS = K2_WS_CONS_WARPS * 32;
     double* s_uw = smem;                       // [128]
     double* s_vw = smem + 128;                 // [128]
@@ -583,7 +585,7 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
 
     if (!g.follows_sampler) cudaTriggerProgrammaticLaunchCompletion();
     if (threadIdx.x == 0) {
-        for (int b = 0; b < K2_WS_NBUF; b++) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], K2_WS_CONS_WARPS); }
+        for (int b = 0; b < K2_WS_NBUF; b++) { mbar_init(&s_full[b], K2_WS_PROD_WARPS); mbar_init(&s_empty[b], K2_WS_CONS_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) s_uw[k] = g.glq[128 + k];
@@ -595,25 +597,32 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
     __syncthreads();
 
     uint32_t stage = 0, phase = 0, ci = 0;
-    if (warp == 0) {
-        // ================================================================================================ staging warp
-        // (warp 0: the warp schedulers favour the oldest warp of a CTA, and staging must stay ahead of seven contraction warps)
-        ws_cache_table(g, 0u, s_tab + 2 * (size_t)AS3, lane); ws_cache_table(g, 1u, s_tab + 3 * (size_t)AS3, lane);   // tables 0 / 1: unscaled u / v points
+    if (warp < K2_WS_PROD_WARPS) {
+        // ================================================================================================ staging warps
+        // (the first warps of the CTA: the warp schedulers favour the oldest warps, and staging must stay ahead of the contraction warps)
+        // With more than one staging warp the pack set-up is done by warp 0 and the staging tasks of every chunk are dealt round-robin;
+        // the staging warps meet at a named barrier after the set-up and before the next set-up overwrites the caches.
+        const uint32_t plane = warp * 32 + lane;   // lane index across the staging warps
+        auto prod_sync = [] { if (K2_WS_PROD_WARPS > 1) asm volatile("bar.sync 1, %0;" ::"r"(K2_WS_PROD_WARPS * 32) : "memory"); else __syncwarp(); };
+        __shared__ uint32_t s_pack_idx, s_n_cols;
+        if (warp == 0) { ws_cache_table(g, 0u, s_tab + 2 * (size_t)AS3, lane); ws_cache_table(g, 1u, s_tab + 3 * (size_t)AS3, lane); }   // tables 0 / 1: unscaled u / v points
         uint32_t cached_u = 0xffffffffu, cached_v = 0xffffffffu;                                 // table ids held by slots 0 / 1
         for (;;) {
             WS_T(t_item0);
-            uint32_t idx = 0;
-            if (lane == 0) idx = atomicAdd(work_counter, 1u);
-            idx = __shfl_sync(0xffffffffu, idx, 0);
+            prod_sync();   // every staging warp is done with the previous pack's caches and context
+            if (plane == 0) s_pack_idx = atomicAdd(work_counter, 1u);
+            prod_sync();
+            const uint32_t idx = s_pack_idx;
             WsCtx& c = s_ctx[ci];
             if (idx >= n_packs) {   // end marker: travels through the ring like a chunk
-                if (lane == 0) c.end = 1u;
+                if (plane == 0) c.end = 1u;
                 mbar_wait(&s_empty[stage], phase ^ 1u);
-                __syncwarp();
+                prod_sync();
                 if (lane == 0) mbar_arrive(&s_full[stage]);
                 break;
             }
             const PackDesc pk = packs[idx];
+            if (warp == 0) {
             // ---- one lane per segment: work item, class, the nine FP64 quotients, tile enumeration -> context
             if (lane < pk.n) {
                 WsSeg& sg = c.seg[lane];
@@ -677,8 +686,11 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
                         n_cols += c_w;
                     }
             }
-            __syncwarp();
-            WS_T(t_item1); WS_ADD(0, t_item1 - t_item0); WS_ADD(5, 1);
+            if (lane == 0) s_n_cols = n_cols;
+            }   // warp == 0
+            prod_sync();
+            const uint32_t n_cols = s_n_cols, chunk_rows = c.chunk_rows, n_slots = c.n_slots;
+            WS_T(t_item1); if (warp == 0) { WS_ADD(0, t_item1 - t_item0); WS_ADD(5, 1); }
             const uint32_t chunk = chunk_rows * nv;
             for (uint32_t round0 = 0; round0 < n_slots; round0 += K2_WS_TPT * CONS) {
                 for (uint32_t m0 = 0; m0 < nu; m0 += chunk_rows) {
@@ -687,9 +699,9 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
                     mbar_wait(&s_empty[stage], phase ^ 1u);     // the contraction warps are done with what this buffer held
                     WS_T(t_w1);
                     double* buf = s_slab + (size_t)stage * buf_doubles;
-                    ws_stage_chunk(g, c, s_cols, n_cols, s_tab, s_spec, buf, chunk, m0, nrow, lane);
+                    ws_stage_chunk<PROD>(g, c, s_cols, n_cols, s_tab, s_spec, buf, chunk, m0, nrow, plane);
                     __syncwarp();
-                    WS_T(t_w2); WS_ADD(1, t_w1 - t_w0); WS_ADD(2, t_w2 - t_w1); WS_ADD(6, 1);
+                    WS_T(t_w2); if (warp == 0) { WS_ADD(1, t_w1 - t_w0); WS_ADD(2, t_w2 - t_w1); WS_ADD(6, 1); }
                     if (lane == 0) mbar_arrive(&s_full[stage]);
                     stage = stage + 1 == K2_WS_NBUF ? 0u : stage + 1; phase ^= (stage == 0u);
                 }
@@ -698,12 +710,12 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
         }
     } else {
         // ============================================================================================ contraction warps
-        const uint32_t tid = threadIdx.x - 32;   // 0 .. CONS-1
+        const uint32_t tid = threadIdx.x - K2_WS_PROD_WARPS * 32;   // 0 .. CONS-1
         for (;;) {
             WS_T(t_f0);
             mbar_wait(&s_full[stage], phase);   // first chunk of the next pack (or the end marker); its context is complete
             WS_T(t_f1);
-            if (warp == 1) WS_ADD(7, t_f1 - t_f0);
+            if (warp == K2_WS_PROD_WARPS) WS_ADD(7, t_f1 - t_f0);
             const WsCtx& c = s_ctx[ci];
             if (c.end) break;
             const uint32_t n_slots = c.n_slots, gap = c.gap, n_same = c.n_same, n_seg = c.n_seg, chunk_rows = c.chunk_rows;
@@ -748,7 +760,7 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
                     if (!first) mbar_wait(&s_full[stage], phase);
                     first = false;
                     WS_T(t_c1);
-                    if (warp == 1) WS_ADD(3, t_c1 - t_c0);
+                    if (warp == K2_WS_PROD_WARPS) WS_ADD(3, t_c1 - t_c0);
                     const double* buf = s_slab + (size_t)stage * buf_doubles;
 #pragma unroll
                     for (int t = 0; t < K2_WS_TPT; t++) {
@@ -780,7 +792,7 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
                     }
                     __syncwarp();
                     WS_T(t_c2);
-                    if (warp == 1) WS_ADD(4, t_c2 - t_c1);
+                    if (warp == K2_WS_PROD_WARPS) WS_ADD(4, t_c2 - t_c1);
                     if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp is done reading the buffer
                     stage = stage + 1 == K2_WS_NBUF ? 0u : stage + 1; phase ^= (stage == 0u);
                 }
@@ -917,7 +929,8 @@ static cudaError_t launch_k2_ws(const Plan& P, const WorkItem* d_items, const Pa
         static bool done[64] = {};
         std::lock_guard<std::mutex> lk(mu);
         if (P.device >= 0 && P.device < 64 && !done[P.device]) {
-            const cudaError_t e = cudaFuncSetAttribute(k2_ws_kernel<K2_TILE_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hard);
+            cudaError_t e = cudaFuncSetAttribute(k2_ws_kernel<K2_TILE_P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hard);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_ws_kernel<K2_TILE_P, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hard);
             if (e != cudaSuccess) return e;
             done[P.device] = true;
         }
@@ -929,7 +942,8 @@ static cudaError_t launch_k2_ws(const Plan& P, const WorkItem* d_items, const Pa
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, k2_ws_kernel<K2_TILE_P>, g, d_packs, count, P.d_work_counter);
+    const cudaError_t e = P.host.ws_prod == 2 ? cudaLaunchKernelEx(&cfg, k2_ws_kernel<K2_TILE_P, 2>, g, d_packs, count, P.d_work_counter)
+                                              : cudaLaunchKernelEx(&cfg, k2_ws_kernel<K2_TILE_P, 1>, g, d_packs, count, P.d_work_counter);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 

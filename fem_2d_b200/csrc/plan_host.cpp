@@ -137,7 +137,7 @@ void order_items(const HostPlan& H, std::vector<WorkItem>& items) {
 void pack_items(const HostPlan& H, std::vector<WorkItem>& items, std::vector<PackDesc>& packs) {
     packs.clear();
     if (!(H.use_ws && H.tile_p == (uint32_t)K2_TILE_P)) { order_items(H, items); return; }
-    const uint32_t round_slots = (uint32_t)(K2_WS_CONS_WARPS * 32 * K2_WS_TPT);
+    const uint32_t round_slots = H.ws_round_slots();
     struct Bin { std::vector<uint32_t> seg; uint32_t same = 0, cross = 0, stride = 0; uint64_t key = ~0ull; };
     auto slots_of = [](uint32_t same, uint32_t cross) { return item_slots(same, same + cross); };
     auto key_of = [&](const WorkItem& it) {   // scaled tables of a non-local item's P side; ~0 for local items (they only use the unscaled tables)
@@ -435,7 +435,19 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
     // Few, heavily deduplicated classes would leave most of the 148 SMs idle: shrink the item size until there are about two
     // CTAs per SM (each item re-stages its class's slabs, which is cheap next to an idle machine).
     if (const char* ev = std::getenv("FEM2D_K2_WS")) P.use_ws = std::atoi(ev) != 0;   // tuning: 0 = every item in k2_exact_kernel
-    uint32_t cap = K2_ROUNDS * (P.use_ws && P.tile_p == (uint32_t)K2_TILE_P ? K2_WS_CONS_WARPS * 32 : K2_THREADS);
+    if (P.use_ws && P.tile_p == (uint32_t)K2_TILE_P) {
+        // staging warps of the persistent integrator: by the slab columns staged per micro-tile (every round of a class stages its columns)
+        double cols = 0, tiles = 0;
+        for (const ClassDesc& c : P.classes) {
+            const ListDesc& LP = P.lists[c.listP]; const ListDesc& LQ = P.lists[c.listQ];
+            uint32_t s = slab_pad4(LP.nU) + slab_pad4(LP.n - LP.nU);
+            if (!c.local) s += slab_pad4(LQ.nU) + slab_pad4(LQ.n - LQ.nU);
+            cols += (double)std::max(1u, (c.n_mt + 223u) / 224u) * s; tiles += c.n_mt;
+        }
+        P.ws_prod = cols > K2_WS_TWO_STAGERS_ABOVE * tiles ? 2u : 1u;
+        if (const char* ev = std::getenv("FEM2D_K2_WS_PROD")) P.ws_prod = std::atoi(ev) == 2 ? 2u : 1u;   // tuning
+    }
+    uint32_t cap = K2_ROUNDS * (P.use_ws && P.tile_p == (uint32_t)K2_TILE_P ? P.ws_round_slots() / K2_WS_TPT : (uint32_t)K2_THREADS);
     const uint32_t min_cap = P.tile_p == 1 ? 256u : 64u;   // latency shape: one full round per CTA measured best (128: +10 %, 512: +30 %)
     for (; cap > min_cap; cap /= 2) {
         uint64_t n = 0;

@@ -36,9 +36,7 @@ constexpr int MT_QX = 4;           // cross-direction micro-tile (both shapes; 1
 #define FEM2D_K2_ROUNDS 2
 #endif
 // warp-specialised persistent integrator (kernels_exact.cu k2_ws_kernel): contraction warps + one staging warp per CTA
-#ifndef FEM2D_K2_WS_CONS_WARPS
-#define FEM2D_K2_WS_CONS_WARPS 7
-#endif
+// K2_WS_WARPS warps per CTA: the first `prod` (1 or 2, chosen per plan: HostPlan::ws_prod) stage slabs, the others contract
 #ifndef FEM2D_K2_WS_NBUF
 #define FEM2D_K2_WS_NBUF 2
 #endif
@@ -49,11 +47,15 @@ constexpr int MT_QX = 4;           // cross-direction micro-tile (both shapes; 1
 #define FEM2D_K2_WS_TPT 1
 #endif
 constexpr int K2_WS_TPT = FEM2D_K2_WS_TPT;         // micro-tiles per contraction thread and round (each staged chunk feeds TPT x CONS tiles)
-constexpr int K2_WS_CONS_WARPS = FEM2D_K2_WS_CONS_WARPS;
-constexpr int K2_WS_THREADS = (K2_WS_CONS_WARPS + 1) * 32;
+constexpr int K2_WS_WARPS = 8;
+constexpr int K2_WS_THREADS = K2_WS_WARPS * 32;
 constexpr int K2_WS_MAXREG = (65536 / (FEM2D_K2_CTAS * K2_WS_THREADS)) / 8 * 8 > 128 ? 128 : (65536 / (FEM2D_K2_CTAS * K2_WS_THREADS)) / 8 * 8;   // registers per thread that keep K2_MIN_CTAS CTAs on an SM
 constexpr int K2_WS_NBUF = FEM2D_K2_WS_NBUF;       // slab ring depth
 constexpr int K2_WS_SMEM_KB = FEM2D_K2_WS_SMEM_KB;
+// One staging warp keeps up while a pack's micro-tiles outnumber the slab columns staged for them (uniform-order meshes: 0.49 columns
+// per tile at BASELINE configs[2]); hp-meshes stage about 0.9 columns per tile and get two (measured: 9.1 -> 8.5 ms at 1.38 M DoFs,
+// while configs[2] without dedupe goes 2.08 -> 2.20 ms with two).
+constexpr double K2_WS_TWO_STAGERS_ABOVE = 0.7;    // staged columns per micro-tile
 constexpr int K2_TILE_P = FEM2D_TILE_P;
 constexpr int K2_THREADS = FEM2D_K2_THREADS;
 constexpr int K2_MIN_CTAS = FEM2D_K2_CTAS;     // CTAs per SM the integrator is compiled for
