@@ -623,30 +623,49 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
             }
             const PackDesc pk = packs[idx];
             if (warp == 0) {
-            // ---- one lane per segment: work item, class, the nine FP64 quotients, tile enumeration -> context
-            if (lane < pk.n) {
-                WsSeg& sg = c.seg[lane];
-                const WorkItem it = g.items[pk.first + lane];
-                const ClassDesc cd = g.classes[it.cls];
-                const uint32_t nP = cd.lp.n, nUP = cd.lp.nU, nQ = cd.lq.n, nUQ = cd.lq.nU;
-                // per-class constants (HierCurlBasisFn::defined_over, basis.rs:395-413; M2D::det / inverse, space.rs:138-147)
-                const double detP = cd.dxP * cd.dyP - 0.0 * 0.0, detQ = cd.dxQ * cd.dyQ - 0.0 * 0.0;
-                const double ge = (double)(detP >= detQ), lt = (double)(detP < detQ);
-                sg.it = it;
-                sg.sb = make_subblocks(nP, nUP, nQ, nUQ, cd.local, TP);
-                sg.jiuP = cd.dyP / detP; sg.jivP = cd.dxP / detP;      // jac_inv.u[0] = dy_dv / det, jac_inv.v[1] = dx_du / det
-                sg.jiuQ = cd.dyQ / detQ; sg.jivQ = cd.dxQ / detQ;
-                sg.ratio_uv = ge * (cd.dxP / cd.dyP) + lt * (cd.dxQ / cd.dyQ);   // max_uv_ratios integrals.rs:250-259, basis.rs:341-343
-                sg.ratio_vu = ge * (cd.dyP / cd.dxP) + lt * (cd.dyQ / cd.dxQ);   // max_vu_ratios integrals.rs:262-271, basis.rs:346-348
-                sg.maxdet = detP > detQ ? detP : detQ;                           // partial_max integrals.rs:421-423
-                sg.coefA = 1.0 / cd.mu;                                          // integrals.rs:37
-                sg.coefB = cd.eps * (cd.su * cd.sv) * (1.0 * 1.0);               // eps * p.glq_scale() * q.glq_scale() integrals.rs:303-305
-                sg.su = cd.su; sg.sv = cd.sv;
-                sg.v_off = cd.v_off;
-                sg.nP = nP; sg.nUP = nUP; sg.nQ = nQ; sg.nUQ = nUQ; sg.local = cd.local;
-                sg.strideP = pad4(nUP) + pad4(nP - nUP);
-                sg.strideQ = cd.local ? sg.strideP : pad4(nUQ) + pad4(nQ - nUQ);
-                sg.listP_off = cd.lp.off; sg.listQ_off = cd.lq.off; sg.tabPu = cd.tabPu; sg.tabPv = cd.tabPv;
+            // ---- nine lanes per segment: work item, class, the nine FP64 quotients (an FP64 division is a ~30-instruction dependent chain,
+            // so each lane takes one), tile enumeration -> context.  Per-class constants: HierCurlBasisFn::defined_over, basis.rs:395-413;
+            // M2D::det / inverse, space.rs:138-147.
+            for (uint32_t s0 = 0; s0 < pk.n; s0 += 3) {
+                const uint32_t sgi = s0 + lane / 9, k = lane % 9;
+                const bool mine = lane < 27 && sgi < pk.n;
+                double quot = 0.0, detP = 0.0, detQ = 0.0;
+                uint32_t cls = 0;
+                if (mine) {
+                    cls = g.items[pk.first + sgi].cls;
+                    const ClassDesc& cd = g.classes[cls];
+                    const double dxP = cd.dxP, dyP = cd.dyP, dxQ = cd.dxQ, dyQ = cd.dyQ;
+                    detP = dxP * dyP - 0.0 * 0.0; detQ = dxQ * dyQ - 0.0 * 0.0;
+                    const double num = k == 0 ? dyP : k == 1 ? dxP : k == 2 ? dyQ : k == 3 ? dxQ : k == 4 ? dxP : k == 5 ? dxQ : k == 6 ? dyP : k == 7 ? dyQ : 1.0;
+                    const double den = k < 2 ? detP : k < 4 ? detQ : k == 4 ? dyP : k == 5 ? dyQ : k == 6 ? dxP : k == 7 ? dxQ : cd.mu;
+                    quot = num / den;
+                }
+                const uint32_t base = lane - k;   // first lane of my segment's group
+                const double q0 = __shfl_sync(0xffffffffu, quot, base), q1 = __shfl_sync(0xffffffffu, quot, base + 1), q2 = __shfl_sync(0xffffffffu, quot, base + 2);
+                const double q3 = __shfl_sync(0xffffffffu, quot, base + 3), q4 = __shfl_sync(0xffffffffu, quot, base + 4), q5 = __shfl_sync(0xffffffffu, quot, base + 5);
+                const double q6 = __shfl_sync(0xffffffffu, quot, base + 6), q7 = __shfl_sync(0xffffffffu, quot, (base + 7) & 31), q8 = __shfl_sync(0xffffffffu, quot, (base + 8) & 31);
+                if (mine && k == 0) {
+                    WsSeg& sg = c.seg[sgi];
+                    const WorkItem it = g.items[pk.first + sgi];
+                    const ClassDesc cd = g.classes[cls];
+                    const uint32_t nP = cd.lp.n, nUP = cd.lp.nU, nQ = cd.lq.n, nUQ = cd.lq.nU;
+                    const double ge = (double)(detP >= detQ), lt = (double)(detP < detQ);
+                    sg.it = it;
+                    sg.sb = make_subblocks(nP, nUP, nQ, nUQ, cd.local, TP);
+                    sg.jiuP = q0; sg.jivP = q1;      // jac_inv.u[0] = dy_dv / det, jac_inv.v[1] = dx_du / det
+                    sg.jiuQ = q2; sg.jivQ = q3;
+                    sg.ratio_uv = ge * q4 + lt * q5;   // max_uv_ratios integrals.rs:250-259, basis.rs:341-343: ge * (dxP / dyP) + lt * (dxQ / dyQ)
+                    sg.ratio_vu = ge * q6 + lt * q7;   // max_vu_ratios integrals.rs:262-271, basis.rs:346-348: ge * (dyP / dxP) + lt * (dyQ / dxQ)
+                    sg.maxdet = detP > detQ ? detP : detQ;                           // partial_max integrals.rs:421-423
+                    sg.coefA = q8;                                                   // 1.0 / mu, integrals.rs:37
+                    sg.coefB = cd.eps * (cd.su * cd.sv) * (1.0 * 1.0);               // eps * p.glq_scale() * q.glq_scale() integrals.rs:303-305
+                    sg.su = cd.su; sg.sv = cd.sv;
+                    sg.v_off = cd.v_off;
+                    sg.nP = nP; sg.nUP = nUP; sg.nQ = nQ; sg.nUQ = nUQ; sg.local = cd.local;
+                    sg.strideP = pad4(nUP) + pad4(nP - nUP);
+                    sg.strideQ = cd.local ? sg.strideP : pad4(nUQ) + pad4(nQ - nUQ);
+                    sg.listP_off = cd.lp.off; sg.listQ_off = cd.lq.off; sg.tabPu = cd.tabPu; sg.tabPv = cd.tabPv;
+                }
             }
             __syncwarp();
             // ---- slot / slab offsets of the segments, chunk size

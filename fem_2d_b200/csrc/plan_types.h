@@ -150,6 +150,9 @@ FEM2D_HD inline uint32_t mt_sub_at(uint32_t k) { return k == 0 ? 0u : k == 1 ? 3
 FEM2D_HD inline uint32_t mt_width(uint32_t sub) { return (sub == 1 || sub == 2) ? (uint32_t)MT_QX : (uint32_t)MT_Q; }
 FEM2D_HD inline uint32_t mt_tri_count(uint32_t n, uint32_t tp) {
     const uint32_t nrt = mt_div_up(n, tp), nct = mt_div_up(n, MT_Q);
+    // tp a multiple of MT_Q: row tile rt starts at column tile rt * (tp / MT_Q) and every row tile keeps at least one column tile, so the
+    // sum below is an arithmetic series (the persistent integrator evaluates this per work item on the device)
+    if (tp % MT_Q == 0 && nrt > 0) { const uint32_t q = tp / MT_Q; if (nct > (nrt - 1) * q) return nrt * nct - q * (nrt * (nrt - 1) / 2); }
     uint32_t c = 0;
     for (uint32_t rt = 0; rt < nrt; rt++) { const uint32_t lo = rt * tp / MT_Q; if (nct > lo) c += nct - lo; }
     return c;
