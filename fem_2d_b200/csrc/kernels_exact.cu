@@ -585,7 +585,7 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
 
     if (!g.follows_sampler) cudaTriggerProgrammaticLaunchCompletion();
     if (threadIdx.x == 0) {
-        for (int b = 0; b < K2_WS_NBUF; b++) { mbar_init(&s_full[b], K2_WS_PROD_WARPS); mbar_init(&s_empty[b], K2_WS_CONS_WARPS); }
+        for (int b = 0; b < K2_WS_NBUF; b++) { mbar_init(&s_full[b], K2_WS_PROD_WARPS * 32); mbar_init(&s_empty[b], K2_WS_CONS_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) s_uw[k] = g.glq[128 + k];
@@ -618,7 +618,7 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
                 if (plane == 0) c.end = 1u;
                 mbar_wait(&s_empty[stage], phase ^ 1u);
                 prod_sync();
-                if (lane == 0) mbar_arrive(&s_full[stage]);
+                mbar_arrive(&s_full[stage]);
                 break;
             }
             const PackDesc pk = packs[idx];
@@ -721,7 +721,7 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
                     ws_stage_chunk<PROD>(g, c, s_cols, n_cols, s_tab, s_spec, buf, chunk, m0, nrow, plane);
                     __syncwarp();
                     WS_T(t_w2); if (warp == 0) { WS_ADD(1, t_w1 - t_w0); WS_ADD(2, t_w2 - t_w1); WS_ADD(6, 1); }
-                    if (lane == 0) mbar_arrive(&s_full[stage]);
+                    mbar_arrive(&s_full[stage]);   // every staging lane releases its own slab stores (the staging warps have slack for the 32 arrivals)
                     stage = stage + 1 == K2_WS_NBUF ? 0u : stage + 1; phase ^= (stage == 0u);
                 }
             }

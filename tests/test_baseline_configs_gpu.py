@@ -173,3 +173,27 @@ def test_hp1m_full_size_properties_and_spot_checks():
     assert n > 500000
     # the sample must contain local-desc pairs: keys produced by a non-leaf Elem
     assert np.count_nonzero(single & ~is_leaf[el]) > 10000
+
+
+def test_persistent_integrator_is_repeatable():
+    """The persistent integrator hands slabs from staging warps to contraction warps through mbarriers and takes its packs from a
+    global counter, so pack-to-CTA assignment and timing differ from run to run; the values must not: 40 assemblies of BASELINE configs[3]
+    (two staging warps) and 10 of configs[2] without dedupe (one staging warp, 16 384 packs), every one bit-identical to the first --
+    which the whole-matrix tests above / the full-size tests compare with the oracle."""
+    import torch
+    for mesh_fn, g, dedupe, reps, want_stagers in ((recipes.mesh_cfg4, 12, True, 40, 2), (recipes.mesh_cfg3, 8, False, 10, 1)):
+        df = F.Domain.from_mesh(mesh_fn(recipes.api("product")))
+        glq = (F.gauss_quadrature_points(g), F.gauss_quadrature_points(g))
+        plan = F.Plan(df.view(), device=0, dedupe=dedupe)
+        assert plan.info["tile_p"] == 4 and plan.work_info()["staging_warps"] == want_stagers
+        a0 = torch.empty(plan.nnz, dtype=torch.float64, device="cuda:0"); b0 = torch.empty_like(a0)
+        plan.assemble_device(glq, a0.data_ptr(), b0.data_ptr())
+        a = torch.empty_like(a0); b = torch.empty_like(b0)
+        side = torch.cuda.Stream()
+        for k in range(reps):
+            a.fill_(float("nan")); b.fill_(float("nan"))
+            torch.cuda.synchronize()
+            st = side if k % 2 else torch.cuda.current_stream()
+            plan.assemble_device(glq, a.data_ptr(), b.data_ptr(), stream=st.cuda_stream)
+            torch.cuda.synchronize()
+            assert torch.equal(a.view(torch.int64), a0.view(torch.int64)) and torch.equal(b.view(torch.int64), b0.view(torch.int64)), k
