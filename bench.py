@@ -235,32 +235,45 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available() or F.device_count() == 0:
         raise SystemExit("bench.py: no CUDA device -- the fem_2d_b200 numeric path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    workload = args.workload
+    w = WORKLOADS[workload]
+    mode = {"exact": F.MODE_EXACT, "sumfact": F.MODE_SUMFACT, "dmma": F.MODE_DMMA}[args.mode]
+    domain = build_product_domain(workload)
+    view = domain.view()
+    glq = (F.gauss_quadrature_points(w["glq"]), F.gauss_quadrature_points(w["glq"]))
     dist = None
-    cpu_group = None
+    nccl = None
+    e2e = None
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        dist.init_process_group(backend="nccl", device_id=dev)
-        # CPU-side group: ranks > 0 wait on it while rank 0 drives all N GPUs from one process in the end-to-end leg (an NCCL barrier
-        # would keep a kernel spinning on their GPUs and time-slice against rank 0's work there)
-        cpu_group = dist.new_group(backend="gloo")
+        # The end-to-end leg comes first at N > 1: rank 0 drives all N GPUs from ONE process (fem2d_galerkin_sample_gep_hcurl_multi) while
+        # the other ranks wait on a CPU-side (gloo) barrier and have not created their CUDA contexts yet -- a second process's context on a
+        # GPU, even an idle one behind an NCCL barrier, makes the GPU switch contexts under rank 0's bursts (measured: 21 -> 36-54 ms).
+        dist.init_process_group(backend="gloo")
+        if not args.no_e2e:
+            e2e = run_e2e(F, view, glq, mode, args, 0, rank, world, dist)
+            if rank == 0:
+                F.trim_cache()
+            dist.barrier()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        nccl = dist.new_group(backend="nccl")
 
     def barrier():
         if dist is not None:
-            dist.barrier()
+            dist.barrier(group=nccl)
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
         if dist is None:
             return float(x)
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=nccl)
         return float(t.item())
 
     stream = torch.cuda.current_stream()
-    mode = {"exact": F.MODE_EXACT, "sumfact": F.MODE_SUMFACT, "dmma": F.MODE_DMMA}[args.mode]
     peaks, peak_kind = _peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     fp64 = {}
@@ -343,11 +356,6 @@ def run_ours(args):
                 "kernel_ms": float(k2_ms), "share_of_step": float(k2_ms / tot_ms)}
 
     # ---------------------------------------------------------------------------------------------- headline: BASELINE configs[2]
-    workload = args.workload
-    w = WORKLOADS[workload]
-    domain = build_product_domain(workload)
-    view = domain.view()
-    glq = (F.gauss_quadrature_points(w["glq"]), F.gauss_quadrature_points(w["glq"]))
     plan = F.Plan(view, device=local_rank, dedupe=bool(args.dedupe))
     nnz = plan.nnz
     ranges = rank_ranges(plan, world, rank)
@@ -419,9 +427,8 @@ def run_ours(args):
         extra = run_extras(F, torch, args, domain, view, plan, glq, d_a, d_b, mode, stream, dev, local_rank, workload, nnz, hbm_peak)
 
     # ---- end to end through the reference-facing call: host Domain view -> host CSR arrays ------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        e2e = run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz, cpu_group)
+    if not args.no_e2e and world == 1:
+        e2e = run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -577,7 +584,7 @@ def rank_ranges(plan, world, rank):
     return [(int(b1[rank]), int(b1[rank + 1])), (int(b2[rank]), int(b2[rank + 1]))]
 
 
-def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz, cpu_group=None):
+def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist):
     """The reference-facing call with HOST buffers, every step: fem2d_galerkin_sample_gep_hcurl_multi = host planner + symbolic phase on
     every device + K1/K2/K3 + D2H of A, B and the compressed pattern + host expansion of rows[] / cols[], ONE process driving all N GPUs
     (what a single Rust caller of the drop-in gets).  Under torchrun rank 0 makes the call on devices 0..N-1 while the other ranks wait at
@@ -591,10 +598,11 @@ def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz, c
              "bs_dir", "bs_dof"]
     steps = max(1, min(args.steps, args.e2e_steps))
     out = None
-    if dist is not None:
-        torch.cuda.synchronize()
-        dist.barrier(group=cpu_group)      # every rank's GPU is idle from here on
     if rank == 0:
+        # size of the result: a first call with capacity 0 reports nnz and fails with BAD_ARGUMENT
+        probe0 = F.Plan(view, device=0, dedupe=True)
+        nnz = probe0.nnz
+        del probe0
         # inputs: the flattened Domain arrays in pinned host memory
         pinned = {}
         h2d = 0
@@ -619,7 +627,7 @@ def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz, c
             got = F.galerkin_sample_gep_hcurl_multi(v, glq, devices, mode=mode, out=p)
             assert got == nnz
 
-        for _ in range(2):
+        for _ in range(4):
             one()
         for d in devices:
             torch.cuda.synchronize(d)
@@ -663,8 +671,6 @@ def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist, dev, nnz, c
                                        "note": "same call, pageable view arrays and pageable outputs (plain vectors, INTEGRATION.md first listing); pinned outputs from fem2d_host_alloc are the documented path"}
             out["caller_side_rebuild"] = {"seconds_per_matrix": reb, "what": "std::map<[u32;2], f64> filled from the sorted arrays with end hints + its destruction: stand-in for SparseMatrix::from_sorted_upper_tri (BTreeMap bulk build) in the Rust shim; NOT inside e2e.value",
                                           "e2e_ms_including_two_rebuilds_pinned": 1e3 * sec / steps + 2e3 * reb}
-    if dist is not None:
-        dist.barrier(group=cpu_group)
     return out
 
 

@@ -333,7 +333,7 @@ int fem2d_plan_pattern_transfer_info(fem2d_plan* plan, uint64_t info[4]) {
     fem2d::Plan& p = plan->p;
     if (p.device < 0) return fail(FEM2D_ERR_NO_DEVICE, "host-only plan");
     std::string err;
-    const int st = fem2d::device_col_runs_host(p, nullptr, err);
+    const int st = fem2d::device_col_runs_host(p, nullptr, 0, nullptr, nullptr, nullptr, err);
     if (st != FEM2D_OK) return fail(st, err);
     info[0] = ((uint64_t)p.host.n_dofs + 1) * 4; info[1] = p.n_col_runs; info[2] = (2 * p.n_col_runs + 1) * 4; info[3] = p.nnz * 8;
     return FEM2D_OK;
@@ -369,9 +369,7 @@ int fem2d_plan_row_blocks_split(const fem2d_plan* plan, uint32_t world, uint64_t
     if (!plan || !bounds_single || !bounds_shared || world == 0) return fail(FEM2D_ERR_BAD_ARGUMENT, "bad argument");
     const fem2d::Plan& p = plan->p;
     // first DoF carried by more than one Elem: the reference numbers all single-Elem (Elem-type) DoFs first (domain.rs:83-96)
-    std::vector<unsigned char> seen(p.host.n_dofs, 0);
-    uint32_t first_shared = p.host.n_dofs;
-    for (uint32_t d : p.host.canon_dof) { if (seen[d]) first_shared = std::min(first_shared, d); seen[d] = 1; }
+    const uint32_t first_shared = fem2d::first_shared(p.host);
     uint64_t split = p.nnz;
     if (p.device < 0) {
         const auto& rows = p.host_pattern.rows;
@@ -387,11 +385,27 @@ int fem2d_plan_row_blocks_split(const fem2d_plan* plan, uint32_t world, uint64_t
         part(0, split, bounds_single); part(split, p.nnz, bounds_shared);
         return FEM2D_OK;
     }
+    // device plan: everything follows from the CSR row offsets (one 4 B x n_dofs copy, cached in the plan; the host-output calls need it anyway)
     std::string err;
-    int st = fem2d::device_first_slot_of_row(p, first_shared, &split, err);
-    if (st == FEM2D_OK) st = fem2d::device_row_block_bounds_range(p, 0, split, world, bounds_single, err);
-    if (st == FEM2D_OK) st = fem2d::device_row_block_bounds_range(p, split, p.nnz, world, bounds_shared, err);
-    return st == FEM2D_OK ? st : fail(st, err);
+    fem2d::Plan& pm = const_cast<fem2d::Plan&>(p);   // caching the pinned copy of the row offsets does not change the plan
+    const int st = fem2d::device_row_ptr_host(pm, nullptr, err);
+    if (st != FEM2D_OK) return fail(st, err);
+    const uint32_t* rp = p.h_row_ptr;
+    const uint32_t n = p.host.n_dofs;
+    split = first_shared < n ? rp[first_shared] : p.nnz;
+    auto part = [&](uint64_t lo, uint64_t hi, uint64_t* b) {
+        b[0] = lo; b[world] = hi;
+        for (uint32_t r = 1; r < world; r++) {
+            uint64_t s = lo + (hi - lo) * r / world;
+            if (s > lo && s < hi) {   // advance to the next row start unless s is one
+                const uint32_t row = (uint32_t)(std::upper_bound(rp, rp + n + 1, (uint32_t)s) - rp) - 1;   // last row with rp[row] <= s
+                if (rp[row] != s) s = std::min<uint64_t>(rp[row + 1], hi);
+            }
+            b[r] = s;
+        }
+    };
+    part(0, split, bounds_single); part(split, p.nnz, bounds_shared);
+    return FEM2D_OK;
 }
 
 int fem2d_assemble_device(fem2d_plan* plan, int basis_kind, int a_kind, int b_kind, int mode, const double* u_pts, const double* u_w, uint32_t nu,
@@ -510,10 +524,11 @@ static int assemble_ranges_impl(fem2d_plan* plan, int basis_kind, int a_kind, in
     // The pattern crosses PCIe in compressed form and is expanded on host threads while the value arrays are in flight: rows[] from
     // the CSR row offsets (4 B per row), cols[] from the runs of consecutive column ids (8 B per run, ~5 runs per row on hp-meshes).
     // They are fetched first: a small copy queued next to the value copies would wait behind them, and so would the expansion.
+    uint32_t windows[2 * fem2d::MAX_SLOT_RANGES] = {};
     {
         std::string perr;
         if (rows) { st = fem2d::device_row_ptr_host(p, nullptr, perr); if (st != FEM2D_OK) return fail(st, perr); }
-        if (cols) { st = fem2d::device_col_runs_host(p, nullptr, perr); if (st != FEM2D_OK) return fail(st, perr); }
+        if (cols) { st = fem2d::device_col_runs_host(p, nullptr, n_ranges, b, e, windows, perr); if (st != FEM2D_OK) return fail(st, perr); }
     }
     st = fem2d_assemble_device_ranges(plan, basis_kind, a_kind, b_kind, mode, u_pts, u_w, nu, v_pts, v_w, nv, n_ranges, b, e, p.d_out_a, p.d_out_b, nullptr);
     if (st != FEM2D_OK) return st;
@@ -532,7 +547,11 @@ static int assemble_ranges_impl(fem2d_plan* plan, int basis_kind, int a_kind, in
         off = 0;
         for (uint32_t k = 0; k < n_ranges; k++) {
             if (rows) expand_runs(p.h_row_ptr, p.host.n_dofs, [](uint64_t r) { return (uint32_t)r; }, 0u, b[k], e[k], rows + (at_slot ? b[k] : off), hw);
-            if (cols) expand_runs(p.h_col_run_slot, p.n_col_runs, [run_col](uint64_t r) { return run_col[r]; }, 1u, b[k], e[k], cols + (at_slot ? b[k] : off), hw);
+            if (cols && e[k] > b[k]) {   // the window of runs that covers this range (the only part of the run arrays that was fetched)
+                const uint32_t lo = windows[2 * k], hi = windows[2 * k + 1];
+                const uint32_t* rc = run_col + lo;
+                expand_runs(p.h_col_run_slot + lo, (uint64_t)hi - lo, [rc](uint64_t r) { return rc[r]; }, 1u, b[k], e[k], cols + (at_slot ? b[k] : off), hw);
+            }
             off += e[k] - b[k];
         }
     }
@@ -605,6 +624,7 @@ int fem2d_galerkin_sample_gep_hcurl_multi(const fem2d_domain_view* view, uint32_
         if (hst != FEM2D_OK) return fail(hst, err);
         g_multi_ms[0] = ms_since(tm0);
         if (host.n_pairs >= (1ull << 31)) return fail(FEM2D_ERR_UNSUPPORTED, "more than 2^31 pairs");
+        if (n_devices > 1) (void)fem2d::first_shared(host);   // once, before every device plan takes its copy
         std::vector<int> status(n_devices, FEM2D_OK);
         std::vector<std::string> message(n_devices);
         std::vector<uint64_t> nnz(n_devices, 0);

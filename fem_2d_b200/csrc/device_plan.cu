@@ -734,42 +734,97 @@ __global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32
 }
 }  // namespace
 
-int device_col_runs_host(Plan& P, cudaStream_t st, std::string& err) {
-    if (P.h_col_run_slot) return FEM2D_OK;
+namespace {
+// for every slot range [b, e): index of the last run that starts at or before b, and of the first run start >= e (the sentinel at the latest)
+__global__ void run_window_kernel(const uint32_t* __restrict__ run_slot, uint32_t n_runs, const unsigned long long* __restrict__ be, uint32_t n_ranges,
+                                  uint32_t* __restrict__ out) {
+    const uint32_t k = threadIdx.x;
+    if (k >= n_ranges) return;
+    const unsigned long long b = be[2 * k], e = be[2 * k + 1];
+    uint32_t lo = 0, hi = n_runs;                 // last index with run_slot[idx] <= b  (run_slot[0] == 0)
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (run_slot[mid] <= b) lo = mid; else hi = mid; }
+    out[2 * k] = lo;
+    uint32_t l2 = 0, h2 = n_runs;                 // first index with run_slot[idx] >= e  (run_slot[n_runs] == nnz)
+    while (l2 < h2) { const uint32_t mid = (l2 + h2) >> 1; if (run_slot[mid] < e) l2 = mid + 1; else h2 = mid; }
+    out[2 * k + 1] = l2;
+}
+}  // namespace
+
+// Column runs of the pattern: compacted on the device once per plan (run starts + first columns stay on the device); the pinned host
+// copies hold either everything (n_ranges == 0) or only the windows of runs that cover the given slot ranges -- a rank of a
+// multi-device call expands 1/N of the pattern and fetches 1/N of the runs.  windows[2k], windows[2k+1]: first run and end run (its
+// start is >= the range's end) of range k.
+int device_col_runs_host(Plan& P, cudaStream_t st, uint32_t n_ranges, const uint64_t* begins, const uint64_t* ends, uint32_t* windows, std::string& err) {
     CK(cudaSetDevice(P.device));
     const uint32_t nnz = (uint32_t)P.nnz;
-    // Scratch from the (size-matched, cached) device allocator.
-    uint32_t *d_slot = nullptr, *d_col = nullptr;
-    CK(dev_malloc((void**)&d_slot, ((size_t)nnz + 1) * 4 + 256, st));
-    uint32_t* d_n = d_slot + (((size_t)nnz + 1 + 63) & ~(size_t)63);   // the count lives in the slack behind the slots
-    cub::CountingInputIterator<uint32_t> it(0);
-    ColRunHead pred{P.d_rows, P.d_cols};
-    size_t temp = 0;
-    CK(cub::DeviceSelect::If(nullptr, temp, it, d_slot, d_n, (int)nnz, pred, st));
-    void* d_temp = nullptr;
-    { const cudaError_t e0 = dev_malloc(&d_temp, temp, st); if (e0 != cudaSuccess) { dev_free(d_slot, st); err = cudaGetErrorString(e0); return FEM2D_ERR_CUDA; } }
-    cudaError_t e = cub::DeviceSelect::If(d_temp, temp, it, d_slot, d_n, (int)nnz, pred, st);
-    uint32_t n_runs = 0;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&n_runs, d_n, 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e == cudaSuccess) e = dev_malloc((void**)&d_col, ((size_t)n_runs + 1) * 4, st);
-    if (e == cudaSuccess && n_runs) { gather_u32_kernel<<<(n_runs + 255) / 256, 256, 0, st>>>(P.d_cols, d_slot, n_runs, d_col); e = cudaGetLastError(); }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_slot + n_runs, &P.nnz32_sentinel, 4, cudaMemcpyHostToDevice, st);   // sentinel: end of the last run
-    if (e == cudaSuccess) {
-        P.h_col_run_slot = (uint32_t*)pinned_acquire(((size_t)n_runs + 1) * 4, &P.h_col_run_cap[0]);
-        P.h_col_run_col = (uint32_t*)pinned_acquire(((size_t)n_runs + 1) * 4, &P.h_col_run_cap[1]);
-        if (!P.h_col_run_slot || !P.h_col_run_col) e = cudaErrorMemoryAllocation;
+    if (!P.d_col_run_slot) {
+        uint32_t *d_slot = nullptr, *d_col = nullptr;
+        CK(dev_malloc((void**)&d_slot, ((size_t)nnz + 1) * 4 + 256, st));
+        uint32_t* d_n = d_slot + (((size_t)nnz + 1 + 63) & ~(size_t)63);   // the count lives in the slack behind the slots
+        cub::CountingInputIterator<uint32_t> it(0);
+        ColRunHead pred{P.d_rows, P.d_cols};
+        size_t temp = 0;
+        CK(cub::DeviceSelect::If(nullptr, temp, it, d_slot, d_n, (int)nnz, pred, st));
+        void* d_temp = nullptr;
+        { const cudaError_t e0 = dev_malloc(&d_temp, temp, st); if (e0 != cudaSuccess) { dev_free(d_slot, st); err = cudaGetErrorString(e0); return FEM2D_ERR_CUDA; } }
+        cudaError_t e = cub::DeviceSelect::If(d_temp, temp, it, d_slot, d_n, (int)nnz, pred, st);
+        uint32_t n_runs = 0;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&n_runs, d_n, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = dev_malloc((void**)&d_col, ((size_t)n_runs + 1) * 4, st);
+        if (e == cudaSuccess && n_runs) { gather_u32_kernel<<<(n_runs + 255) / 256, 256, 0, st>>>(P.d_cols, d_slot, n_runs, d_col); e = cudaGetLastError(); }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_slot + n_runs, &P.nnz32_sentinel, 4, cudaMemcpyHostToDevice, st);   // sentinel: end of the last run
+        if (e == cudaSuccess) {
+            P.h_col_run_slot = (uint32_t*)pinned_acquire(((size_t)n_runs + 1) * 4, &P.h_col_run_cap[0]);
+            P.h_col_run_col = (uint32_t*)pinned_acquire(((size_t)n_runs + 1) * 4, &P.h_col_run_cap[1]);
+            if (!P.h_col_run_slot || !P.h_col_run_col) e = cudaErrorMemoryAllocation;
+        }
+        dev_free(d_temp, st);
+        if (e != cudaSuccess) {
+            dev_free(d_slot, st); dev_free(d_col, st);
+            pinned_release(P.h_col_run_slot, P.h_col_run_cap[0]); pinned_release(P.h_col_run_col, P.h_col_run_cap[1]);
+            P.h_col_run_slot = P.h_col_run_col = nullptr;
+            err = cudaGetErrorString(e); return FEM2D_ERR_CUDA;
+        }
+        P.d_col_run_slot = d_slot; P.d_col_run_col = d_col; P.n_col_runs = n_runs; P.col_runs_all = false;
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(P.h_col_run_slot, d_slot, ((size_t)n_runs + 1) * 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(P.h_col_run_col, d_col, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    dev_free(d_slot, st); dev_free(d_col, st); dev_free(d_temp, st);
-    if (e != cudaSuccess) {
-        pinned_release(P.h_col_run_slot, P.h_col_run_cap[0]); pinned_release(P.h_col_run_col, P.h_col_run_cap[1]);
-        P.h_col_run_slot = P.h_col_run_col = nullptr;
-        err = cudaGetErrorString(e); return FEM2D_ERR_CUDA;
+    const uint32_t n_runs = (uint32_t)P.n_col_runs;
+    if (n_ranges == 0) {
+        if (!P.col_runs_all) {
+            CK(cudaMemcpyAsync(P.h_col_run_slot, P.d_col_run_slot, ((size_t)n_runs + 1) * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(P.h_col_run_col, P.d_col_run_col, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            P.col_runs_all = true;
+        }
+        return FEM2D_OK;
     }
-    P.n_col_runs = n_runs;
+    if (n_ranges > MAX_SLOT_RANGES) { err = "too many slot ranges"; return FEM2D_ERR_BAD_ARGUMENT; }
+    if (P.col_runs_all) {   // everything is on the host already: the windows follow from the host copy
+        for (uint32_t k = 0; k < n_ranges; k++) {
+            const uint32_t* s0 = P.h_col_run_slot;
+            windows[2 * k] = (uint32_t)(std::upper_bound(s0, s0 + n_runs + 1, (uint32_t)std::min<uint64_t>(begins[k], nnz)) - s0) - 1;
+            windows[2 * k + 1] = (uint32_t)(std::lower_bound(s0, s0 + n_runs + 1, (uint32_t)std::min<uint64_t>(ends[k], nnz)) - s0);
+        }
+        return FEM2D_OK;
+    }
+    unsigned long long h_be[2 * MAX_SLOT_RANGES];
+    for (uint32_t k = 0; k < n_ranges; k++) { h_be[2 * k] = begins[k]; h_be[2 * k + 1] = std::min<uint64_t>(ends[k], nnz); }
+    unsigned long long* d_be = nullptr;
+    CK(dev_malloc((void**)&d_be, sizeof(h_be) + 2 * MAX_SLOT_RANGES * 4, st));
+    uint32_t* d_w = reinterpret_cast<uint32_t*>(d_be + 2 * MAX_SLOT_RANGES);
+    cudaError_t e = cudaMemcpyAsync(d_be, h_be, sizeof(unsigned long long) * 2 * n_ranges, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) { run_window_kernel<<<1, 32, 0, st>>>(P.d_col_run_slot, n_runs, d_be, n_ranges, d_w); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(windows, d_w, 2 * n_ranges * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    dev_free(d_be, st);
+    for (uint32_t k = 0; k < n_ranges && e == cudaSuccess; k++) {
+        const uint32_t lo = windows[2 * k], hi = windows[2 * k + 1];
+        if (hi < lo) continue;
+        e = cudaMemcpyAsync(P.h_col_run_slot + lo, P.d_col_run_slot + lo, ((size_t)hi - lo + 1) * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && hi > lo) e = cudaMemcpyAsync(P.h_col_run_col + lo, P.d_col_run_col + lo, ((size_t)hi - lo) * 4, cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { err = cudaGetErrorString(e); return FEM2D_ERR_CUDA; }
     return FEM2D_OK;
 }
 
@@ -782,6 +837,7 @@ void device_plan_release(Plan& P) {
     pinned_release(P.h_row_ptr, P.h_row_ptr_cap); P.h_row_ptr = nullptr;
     pinned_release(P.h_col_run_slot, P.h_col_run_cap[0]); pinned_release(P.h_col_run_col, P.h_col_run_cap[1]);
     P.h_col_run_slot = P.h_col_run_col = nullptr;
+    dev_free(P.d_col_run_slot); dev_free(P.d_col_run_col);
     dev_free(P.d_range_items); dev_free(P.d_aij_arena);
     dev_free(P.d_V); dev_free(P.d_tabs); dev_free(P.d_gram); dev_free(P.d_dmma_items); dev_free(P.d_out_a); dev_free(P.d_out_b);
     for (int r = 0; r < Plan::RING; r++) for (int k = 0; k < 4; k++) if (P.ev[r][k]) cudaEventDestroy(P.ev[r][k]);

@@ -42,6 +42,8 @@ struct Plan {
     uint32_t* h_col_run_slot = nullptr; uint32_t* h_col_run_col = nullptr;
     size_t h_col_run_cap[2] = {0, 0};
     uint64_t n_col_runs = 0;
+    uint32_t* d_col_run_slot = nullptr; uint32_t* d_col_run_col = nullptr;   // device copies (kept: later calls may need other windows)
+    bool col_runs_all = false;           // the pinned host copies hold every run (otherwise only the windows fetched so far)
     uint32_t nnz32_sentinel = 0;         // == nnz, kept in the plan so an async H2D of it has a stable source
     uint32_t* d_extra_slot = nullptr;
     uint32_t* d_extra_src = nullptr;
@@ -126,7 +128,7 @@ int device_row_block_bounds_range(const Plan& plan, uint64_t lo, uint64_t hi, ui
 // Pinned host copy of the CSR row offsets (fetched once per plan).
 int device_row_ptr_host(Plan& plan, cudaStream_t st, std::string& err);
 // Column runs of the pattern, compacted on the device and copied to pinned host memory (once per plan).
-int device_col_runs_host(Plan& plan, cudaStream_t st, std::string& err);
+int device_col_runs_host(Plan& plan, cudaStream_t st, uint32_t n_ranges, const uint64_t* begins, const uint64_t* ends, uint32_t* windows, std::string& err);
 void device_plan_release(Plan& plan);
 
 // kernels_exact.cu  (compiled with -fmad=false)

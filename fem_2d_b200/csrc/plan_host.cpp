@@ -134,6 +134,16 @@ void order_items(const HostPlan& H, std::vector<WorkItem>& items) {
     std::stable_partition(items.begin(), items.end(), [&](const WorkItem& it) { return item_is_big(H, it); });
 }
 
+uint32_t first_shared(const HostPlan& H) {
+    if (H.first_shared_dof < 0) {
+        std::vector<unsigned char> seen(H.n_dofs, 0);
+        uint32_t fs = H.n_dofs;
+        for (uint32_t d : H.canon_dof) { if (seen[d]) fs = std::min(fs, d); seen[d] = 1; }
+        H.first_shared_dof = fs;
+    }
+    return (uint32_t)H.first_shared_dof;
+}
+
 void pack_items(const HostPlan& H, std::vector<WorkItem>& items, std::vector<PackDesc>& packs) {
     packs.clear();
     if (!(H.use_ws && H.tile_p == (uint32_t)K2_TILE_P)) { order_items(H, items); return; }

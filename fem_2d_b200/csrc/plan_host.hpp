@@ -28,12 +28,16 @@ struct HostPlan {
     uint64_t n_pairs = 0;    // == number of (p,q) integrations the reference performs (x2 for A and B)
     uint64_t n_values = 0;   // entries of V
     uint32_t max_list_n = 0;
+    mutable int64_t first_shared_dof = -1;   // smallest DoF carried by more than one Elem (computed on first use by first_shared())
     uint32_t tile_p = 4;            // micro-tile height chosen for the exact integrator (4: throughput, 1: latency)
     uint32_t ws_prod = 1;           // staging warps of the persistent integrator (1 or 2), see K2_WS_TWO_STAGERS_ABOVE
     uint32_t ws_round_slots() const { return (uint32_t)((K2_WS_WARPS - (int)ws_prod) * 32 * K2_WS_TPT); }   // micro-tiles one round of contraction threads holds
     bool use_ws = true;             // throughput shape: big items run in the warp-specialised persistent integrator (FEM2D_K2_WS=0: tuning)
     uint32_t max_slab_stride = 0;   // max over classes of pad4(nU)+pad4(nV) of P (+ the same of Q for non-local classes)
 };
+
+// First DoF carried by more than one Elem: the reference numbers all single-Elem (Elem-type) DoFs first (domain.rs:83-96).  Cached in the plan.
+uint32_t first_shared(const HostPlan& plan);
 
 // dx_du, dy_dv of every Elem (element.rs:33-50), in the reference's operation order.
 int elem_geometry(const fem2d_domain_view* view, std::vector<double>& dx, std::vector<double>& dy, std::string& err);
