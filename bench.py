@@ -5,15 +5,20 @@ Contract (see the task statement): `python bench.py --gpus N --steps K --warmup 
   * workload      BASELINE.json configs[2]: test_mesh_a.json, Orders(6,6), 6x global T (1,178,112 DoFs, 57,557,904 upper-
                   triangular entries per matrix), HierPoly / CurlCurl / L2Inner, GLQ [8,8], EXACT (bit-faithful) mode.
   * value         device-resident: plan + domain already in HBM, one step = sampler (K1) + integrator (K2) + scatter (K3)
-                  into device CSR value arrays; CUDA events on the launch stream, max over ranks.
-  * e2e           the reference-facing call: flattened Domain in (pinned) host memory -> symbolic + numeric + D2H of
-                  rows/cols/A/B into pinned host buffers, every step, wall clock around the synchronous C-ABI calls.
-  * roofline      dominant kernel = K3 gather/scatter (HBM bound): algorithmic bytes = 16 B x nnz_upper + 4 B x nnz_upper
-                  source-map read (SURVEY.md 8d counts 4 B x n_pairs; the gather form reads one index per slot).
-  * cpu_baseline  the C++ oracle (restatement of the Rayon path; kind "port") on a bounded sample of the same workload.
-  * --impl reference   times that CPU restatement on all host cores (the Rust reference cannot be built here: no rustc/cargo).
-N > 1: strong scaling of the same mesh -- every rank owns a row block of the pattern (fem2d_plan_row_blocks), integrates the
-classes its slots need and scatters its block; no data-path collective (the value buffer is recomputed per rank).
+                  into device CSR value arrays; CUDA events on the launch stream, max over ranks; the step is replayed from a CUDA graph.
+  * roofline      dominant kernel of the headline step = K3 gather/scatter (HBM bound): algorithmic bytes = 16 B x nnz_upper + the
+                  packed source map (SURVEY.md 8d budgets a 4 B index; the smaller figure the kernel really reads is used).
+  * workloads     first-class second results where the integrator IS the step: `hp1m` (north_star target, >= 1M-DoF anisotropic
+                  hp-mesh, every N) and `cfg3_dedupe0` (headline mesh without block dedupe, N = 1), each with an FP64-issue roofline
+                  block (algorithmic lane-ops of the reference's per-pair quadrature / integrator time / measured DMUL+DADD peak);
+                  `roofline_fp64` repeats hp1m's.
+  * e2e           the reference-facing one-shot call with HOST buffers, every step: fem2d_galerkin_sample_gep_hcurl_multi on all N GPUs
+                  from one process (host planner + symbolic + numeric + D2H + host expansion of rows/cols), wall clock.
+  * cpu_baseline  the C++ oracle (restatement of the Rayon path; kind "port") on the SAME full workload, all host threads, once.
+  * --impl reference   the same CPU restatement, full workload per step, as many steps as fit a 600 s budget (the Rust reference
+                  cannot be built here: no rustc/cargo).
+N > 1: strong scaling of the same meshes -- every rank owns a row block of the pattern (fem2d_plan_row_blocks_split), integrates what
+its slots read and scatters its block; no data-path collective (halo tiles are recomputed).
 """
 from __future__ import annotations
 
@@ -651,9 +656,7 @@ def run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist):
             assert got == nnz
 
         for _ in range(4):
-            one()
-        for d in devices:
-            torch.cuda.synchronize(d)
+            one()             # (the call is synchronous: every device is idle when it returns)
         per_step = []
         t0 = time.perf_counter()
         for _ in range(steps):
