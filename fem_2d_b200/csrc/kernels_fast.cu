@@ -99,6 +99,9 @@ __global__ void __launch_bounds__(256) k2_sumfact_kernel(const SFArgs g) {
 cudaError_t ensure_gram(Plan& P, uint32_t NO, cudaStream_t st) {
     const size_t need = std::max<size_t>(P.host.grams.size(), 1) * G_KINDS * NO * NO;
     if (need > P.gram_capacity) {
+        // an earlier call on this stream may still read the old buffer, and the block cache can hand it straight to another allocation
+        const cudaError_t es = cudaStreamSynchronize(st);
+        if (es != cudaSuccess) return es;
         fem2d::dev_free(P.d_gram, st); P.d_gram = nullptr; P.gram_capacity = 0;
         cudaError_t e = fem2d::dev_malloc((void**)&P.d_gram, need * sizeof(double), st);
         if (e != cudaSuccess) return e;
