@@ -457,6 +457,13 @@ def run_ours(args):
     if not args.no_e2e and world == 1:
         e2e = run_e2e(F, view, glq, mode, args, local_rank, rank, world, dist)
 
+    if rank == 0 and world == 1 and not args.no_cpu and "hp1m" in workloads and "error" not in workloads["hp1m"]:
+        # CPU side by side for the north_star workload too: the same full assembly by the C++ restatement, all host threads, once
+        threads = os.cpu_count() or 1
+        r = cpu_port_run("hp1m", threads)
+        workloads["hp1m"]["cpu_baseline"] = {"value": 2.0 * r["nnz"] / r["seconds"], "unit": "nnz/s", "cores": threads, "kind": "port",
+                                             "sample": f"the full workload, once ({r['dofs']} DoFs, {r['nnz']} upper entries/matrix): {r['seconds']:.2f}s = integrate "
+                                                       f"{r['integrate_s']:.2f}s ({threads} threads) + serial merge {r['merge_s']:.2f}s"}
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         # the SAME workload, whole: ~30 s on 16 host cores (the serial ordered-map merge dominates, as in the reference's design)
