@@ -142,12 +142,11 @@ int device_petsc_image(Plan& P, const double* d_vals, void** d_image, uint64_t* 
     CKP(dev_malloc(&img, total + 16));
     uint32_t* head = (uint32_t*)img;
     uint32_t* j_out = head + 4 + n;
-    // the value block starts at 16 + 4n + 4nf bytes: 8-byte aligned iff n + nf is even; written as two u32 halves, so 4-byte alignment suffices
-    uint2* a_out = nullptr; (void)a_out;
     aij_head_kernel<<<(n + 256) / 256, 256>>>(P.d_aij_counts, n, (uint32_t)nf, head);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && nf) {
-        // a_out as uint2 needs 8-byte alignment; fall back to a shifted scratch when the block is only 4-byte aligned
+        // the value block starts at 16 + 4 n + 4 nf bytes, 8-byte aligned iff n + nf is even: the fill kernel stores uint2, so an odd
+        // n + nf goes through an aligned scratch block and one device-to-device copy
         char* a_base = (char*)img + 16 + 4ull * n + 4ull * nf;
         const bool aligned = ((uintptr_t)a_base & 7u) == 0;
         uint2* a_dst = (uint2*)a_base;
