@@ -60,3 +60,27 @@ def test_throughput_shape_with_inter_layer_blocks_bit_identical(basis):
         assert np.array_equal(rows, ref.rows) and np.array_equal(cols, ref.cols)
         assert np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(ref.a).view(np.uint64)), f"A differs (dedupe={dedupe})"
         assert np.array_equal(np.ascontiguousarray(b).view(np.uint64), np.ascontiguousarray(ref.b).view(np.uint64)), f"B differs (dedupe={dedupe})"
+
+
+@pytest.mark.parametrize("nu,nv", [(5, 4), (9, 40)])
+def test_throughput_shape_extreme_glq_shapes(nu, nv):
+    """The same 14 611-DoF hp-mesh with GLQ shapes at both ends: 5 x 4 (a whole pack's rows fit one staged chunk; fewer points than the staging
+    step holds) and 9 x 40 (one quadrature row of the widest pack no longer fits a ring buffer of the persistent integrator, so the launch
+    falls back to k2_exact_kernel with 256-thread CTAs for every work item), bit for bit against the oracle."""
+    def build(api):
+        return recipes.mesh_cfg4(api, t_levels=3, rounds=3, pmin=2, pmax=10)
+    do, df = O.Domain.from_mesh(build(recipes.api("oracle"))), F.Domain.from_mesh(build(recipes.api("product")))
+    glq = (F.gauss_quadrature_points(nu), F.gauss_quadrature_points(nv))
+    ref = O.galerkin_sample_gep_hcurl(do, glq=glq, n_threads=16)
+    plan = F.Plan(df.view(), device=0)
+    assert plan.info["tile_p"] == 4
+    rows, cols, a, b = plan.assemble(glq)
+    assert np.array_equal(rows, ref.rows) and np.array_equal(cols, ref.cols)
+    assert np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(ref.a).view(np.uint64))
+    assert np.array_equal(np.ascontiguousarray(b).view(np.uint64), np.ascontiguousarray(ref.b).view(np.uint64))
+    # the second call re-uses the plan's scratch with the other tile-to-kernel routing
+    glq2 = (F.gauss_quadrature_points(6), F.gauss_quadrature_points(6))
+    ref2 = O.galerkin_sample_gep_hcurl(do, glq=glq2, n_threads=16)
+    _, _, a2, b2 = plan.assemble(glq2)
+    assert np.array_equal(np.ascontiguousarray(a2).view(np.uint64), np.ascontiguousarray(ref2.a).view(np.uint64))
+    assert np.array_equal(np.ascontiguousarray(b2).view(np.uint64), np.ascontiguousarray(ref2.b).view(np.uint64))
