@@ -608,7 +608,7 @@ class Plan:
         """fem2d_plan_work_info: pairs / micro-tiles one numeric call integrates (every class once)."""
         out = (C.c_uint64 * 8)()
         _ck(_L.fem2d_plan_work_info(self._h, out))
-        keys = ["same_pairs", "cross_pairs", "same_tiles", "cross_tiles", "pairs_per_same_tile", "pairs_per_cross_tile", "staged_columns", "staging_warps"]
+        keys = ["same_pairs", "cross_pairs", "same_tiles", "cross_tiles", "pairs_per_same_tile", "pairs_per_cross_tile", "warp_slots", "staging_warps"]
         return {k: int(out[i]) for i, k in enumerate(keys)}
 
     def fp64_lane_ops(self, nu: int, nv: int) -> int:

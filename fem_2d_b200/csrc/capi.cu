@@ -279,9 +279,18 @@ int fem2d_plan_work_info(const fem2d_plan* plan, uint64_t out[8]) {
         else { out[0] += uP * uQ + vP * vQ; out[1] += uP * vQ + vP * uQ; }                      // galerkin.rs:138-178
         const SubBlocks sb = make_subblocks(LP.n, LP.nU, LQ.n, LQ.nU, c.local, H.tile_p);
         out[2] += sb.cnt[0] + sb.cnt[3]; out[3] += sb.cnt[1] + sb.cnt[2];
-        out[6] += (uint64_t)LP.n + (c.local ? 0u : LQ.n);
     }
     out[4] = (uint64_t)H.tile_p * MT_Q; out[5] = (uint64_t)H.tile_p * MT_QX;
+    // thread slots the integrator's warps span (whole warps: a pack's same-direction tiles and its cross-direction tiles each round up to 32)
+    out[6] = 0;
+    if (!H.packs.empty())
+        for (const PackDesc& pk : H.packs) {
+            uint64_t same = 0, cross = 0;
+            for (uint32_t k = 0; k < pk.n; k++) { same += H.items[pk.first + k].n_same; cross += H.items[pk.first + k].mt_count - H.items[pk.first + k].n_same; }
+            out[6] += ((same + 31) & ~31ull) + ((cross + 31) & ~31ull);
+        }
+    else
+        for (const WorkItem& it : H.items) out[6] += (((uint64_t)it.n_same + 31) & ~31ull) + (((uint64_t)(it.mt_count - it.n_same) + 31) & ~31ull);
     out[7] = (H.use_ws && H.tile_p == (uint32_t)K2_TILE_P) ? H.ws_prod : 0u;
     return FEM2D_OK;
 }

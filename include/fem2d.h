@@ -101,7 +101,7 @@ int fem2d_plan_check_work_items(const fem2d_plan* plan, uint64_t out[4]);
 /* Work of one numeric call of the integrator, counted on the plan's classes (every class is integrated once per call): out[0] same-direction
  * pairs (U-U, V-V: A and B, 8 FP64 operations per pair and quadrature point + 4 per pair and quadrature row in the reference's order,
  * integrals.rs:36-91,302-353, glq.rs:19-32), out[1] cross-direction pairs (U-V, V-U: A only, 3 per point + 2 per row), out[2] / out[3] micro-tiles of
- * the two kinds, out[4] / out[5] pairs per micro-tile of the two kinds, out[6] function columns staged (P side + Q side of every class),
+ * the two kinds, out[4] / out[5] pairs per micro-tile of the two kinds, out[6] thread slots of the warps that hold those micro-tiles (whole warps per pack / work item and kind),
  * out[7] staging warps per CTA of the persistent integrator chosen for this plan (1 or 2; 0: the plan runs the latency shape).
  * Host logic; works on host-only plans. */
 int fem2d_plan_work_info(const fem2d_plan* plan, uint64_t out[8]);
