@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <functional>
 #include <cstring>
 #include <numeric>
 #include <thread>
@@ -362,27 +363,51 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
     // ---- blocks and classes.  Block order: for every Elem d (ascending) its local block, then its blocks with each
     // ancestor that carries functions (nearest ancestor first).
     std::unordered_map<ClassKey, uint32_t, ClassKeyHash> class_pool;
-    std::vector<uint8_t> locs;
-    for (uint32_t d = 0; d < ne; d++) {
-        const uint32_t nd = v->bs_off[d + 1] - v->bs_off[d];
-        if (nd == 0) continue;
-        locs.clear();
-        uint32_t child_on_path = d;
-        for (int32_t e = (int32_t)d; e >= 0; e = v->elem_parent[e]) {
-            const bool local = (uint32_t)e == d;
-            if (!local) locs.push_back(v->elem_loc[child_on_path]);   // locs: from d upwards to the child of e
-            child_on_path = (uint32_t)e;
-            const uint32_t nE = v->bs_off[e + 1] - v->bs_off[e];
-            if (nE == 0) continue;
-            ClassKey key; std::memset(&key, 0, sizeof(key));
-            double su = 1.0, ou = 0.0, sv = 1.0, ov = 0.0;
-            if (!local) {
-                // relative_parametric_range(e) of d: fold from the child of e down to d (elem.rs:170-188)
-                double r[4] = {-1.0, 1.0, -1.0, 1.0}, t[4];
-                for (auto it = locs.rbegin(); it != locs.rend(); ++it) { sub_range(*it, r, t); std::memcpy(r, t, sizeof(r)); }
-                su = (r[1] - r[0]) / 2.0; ou = (r[1] + r[0]) / 2.0;   // scale_gauss_quad_points glq.rs:238-249
-                sv = (r[3] - r[2]) / 2.0; ov = (r[3] + r[2]) / 2.0;
+    // Pass 1 (host threads over contiguous Elem ranges): the (ancestor, descendant) pairs that carry functions on both sides and the
+    // descendant's sub-range inside the ancestor; pass 2 (serial, in Elem order): class pooling, tables, block numbering.
+    struct BlockRec { uint32_t e, d; double su, ou, sv, ov; };
+    auto records_of = [&](uint32_t d0, uint32_t d1, std::vector<BlockRec>& out) {
+        std::vector<uint8_t> locs;
+        for (uint32_t d = d0; d < d1; d++) {
+            if (v->bs_off[d + 1] == v->bs_off[d]) continue;
+            locs.clear();
+            uint32_t child_on_path = d;
+            for (int32_t e = (int32_t)d; e >= 0; e = v->elem_parent[e]) {
+                const bool local = (uint32_t)e == d;
+                if (!local) locs.push_back(v->elem_loc[child_on_path]);   // locs: from d upwards to the child of e
+                child_on_path = (uint32_t)e;
+                if (v->bs_off[e + 1] == v->bs_off[e]) continue;
+                BlockRec r{(uint32_t)e, d, 1.0, 0.0, 1.0, 0.0};
+                if (!local) {
+                    // relative_parametric_range(e) of d: fold from the child of e down to d (elem.rs:170-188)
+                    double rg[4] = {-1.0, 1.0, -1.0, 1.0}, t[4];
+                    for (auto it = locs.rbegin(); it != locs.rend(); ++it) { sub_range(*it, rg, t); std::memcpy(rg, t, sizeof(rg)); }
+                    r.su = (rg[1] - rg[0]) / 2.0; r.ou = (rg[1] + rg[0]) / 2.0;   // scale_gauss_quad_points glq.rs:238-249
+                    r.sv = (rg[3] - rg[2]) / 2.0; r.ov = (rg[3] + rg[2]) / 2.0;
+                }
+                out.push_back(r);
             }
+        }
+    };
+    std::vector<std::vector<BlockRec>> rec_parts(n_threads);
+    if (n_threads == 1) records_of(0, ne, rec_parts[0]);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < n_threads; t++) th.emplace_back(records_of, (uint32_t)((uint64_t)ne * t / n_threads), (uint32_t)((uint64_t)ne * (t + 1) / n_threads), std::ref(rec_parts[t]));
+        for (auto& t : th) t.join();
+    }
+    {
+        size_t n_rec = 0;
+        for (auto& part : rec_parts) n_rec += part.size();
+        P.blocks.reserve(n_rec); class_pool.reserve(n_rec);
+    }
+    for (auto& part : rec_parts)
+        for (const BlockRec& r : part) {
+            const uint32_t e = r.e, d = r.d;
+            const bool local = e == d;
+            const uint32_t nd = v->bs_off[d + 1] - v->bs_off[d], nE = v->bs_off[e + 1] - v->bs_off[e];
+            const double su = r.su, ou = r.ou, sv = r.sv, ov = r.ov;
+            ClassKey key; std::memset(&key, 0, sizeof(key));
             const uint32_t elP = v->elem_element[e];
             key.g[0] = P.elem_dx[e]; key.g[1] = P.elem_dy[e]; key.g[2] = P.elem_dx[d]; key.g[3] = P.elem_dy[d];
             key.g[4] = su; key.g[5] = ou; key.g[6] = sv; key.g[7] = ov;
@@ -410,11 +435,10 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
                 P.classes.push_back(c);
                 class_pool.emplace(key, cls);
             }
-            BlockDesc b; b.pair_off = P.n_pairs; b.cls = cls; b.elemP = (uint32_t)e; b.elemQ = d; b.pad = 0;
+            BlockDesc b; b.pair_off = P.n_pairs; b.cls = cls; b.elemP = e; b.elemQ = d; b.pad = 0;
             P.blocks.push_back(b);
             P.n_pairs += local ? (uint64_t)nd * (nd + 1) / 2 : (uint64_t)nE * nd;
         }
-    }
     if (P.blocks.empty()) { err = "the view carries DoFs but no basis specs: nothing to integrate"; return FEM2D_ERR_BAD_ARGUMENT; }
     if (P.n_values >= (1ull << 31) || P.n_pairs >= (1ull << 32)) { err = "domain too large for 32-bit source indices"; return FEM2D_ERR_UNSUPPORTED; }
 
@@ -464,26 +488,41 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
         for (const ClassDesc& c : P.classes) n += (c.n_mt + cap - 1) / cap;
         if (n >= 2 * 148) break;
     }
-    for (uint32_t c : cls_order) {
-        const uint32_t n_mt = P.classes[c].n_mt;
-        const ClassDesc& cd = P.classes[c];
-        const ListDesc& LP = P.lists[cd.listP]; const ListDesc& LQ = P.lists[cd.listQ];
-        const uint32_t same_end = mt_same_count(make_subblocks(LP.n, LP.nU, LQ.n, LQ.nU, cd.local, P.tile_p));
-        // equal shares; one more item if the warp alignment of the cross-direction tiles would push a share past the cap
-        uint32_t n_items = (n_mt + cap - 1) / cap;
-        for (;; n_items++) {
-            bool fits = true;
-            for (uint32_t k = 0; k < n_items && fits; k++) {
-                const uint32_t b = (uint32_t)((uint64_t)n_mt * k / n_items), e = (uint32_t)((uint64_t)n_mt * (k + 1) / n_items);
-                const uint32_t ns = b < same_end ? std::min(e, same_end) - b : 0u;
-                fits = item_slots(ns, e - b) <= cap;
+    // (classes are independent: on plans with many classes the list is cut into contiguous pieces of cls_order, one per host thread,
+    // and the pieces are concatenated in order, so the item list does not depend on the thread count)
+    auto items_of = [&](size_t k0, size_t k1, std::vector<WorkItem>& out) {
+        for (size_t kc = k0; kc < k1; kc++) {
+            const uint32_t c = cls_order[kc];
+            const uint32_t n_mt = P.classes[c].n_mt;
+            const ClassDesc& cd = P.classes[c];
+            const ListDesc& LP = P.lists[cd.listP]; const ListDesc& LQ = P.lists[cd.listQ];
+            const uint32_t same_end = mt_same_count(make_subblocks(LP.n, LP.nU, LQ.n, LQ.nU, cd.local, P.tile_p));
+            // equal shares; one more item if the warp alignment of the cross-direction tiles would push a share past the cap
+            uint32_t n_items = (n_mt + cap - 1) / cap;
+            for (;; n_items++) {
+                bool fits = true;
+                for (uint32_t k = 0; k < n_items && fits; k++) {
+                    const uint32_t b = (uint32_t)((uint64_t)n_mt * k / n_items), e = (uint32_t)((uint64_t)n_mt * (k + 1) / n_items);
+                    const uint32_t ns = b < same_end ? std::min(e, same_end) - b : 0u;
+                    fits = item_slots(ns, e - b) <= cap;
+                }
+                if (fits || n_items >= n_mt) break;
             }
-            if (fits || n_items >= n_mt) break;
+            for (uint32_t k = 0; k < n_items; k++) {
+                const uint32_t b = (uint32_t)((uint64_t)n_mt * k / n_items), e = (uint32_t)((uint64_t)n_mt * (k + 1) / n_items);
+                if (e > b) out.push_back(make_item(P, c, {{b, e - b}}, nullptr));
+            }
         }
-        for (uint32_t k = 0; k < n_items; k++) {
-            const uint32_t b = (uint32_t)((uint64_t)n_mt * k / n_items), e = (uint32_t)((uint64_t)n_mt * (k + 1) / n_items);
-            if (e > b) P.items.push_back(make_item(P, c, {{b, e - b}}, nullptr));
-        }
+    };
+    const unsigned item_threads = cls_order.size() < 8192 ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (item_threads == 1) items_of(0, cls_order.size(), P.items);
+    else {
+        std::vector<std::vector<WorkItem>> parts(item_threads);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < item_threads; t++)
+            th.emplace_back(items_of, cls_order.size() * t / item_threads, cls_order.size() * (t + 1) / item_threads, std::ref(parts[t]));
+        for (auto& t : th) t.join();
+        for (auto& part : parts) P.items.insert(P.items.end(), part.begin(), part.end());
     }
     pack_items(P, P.items, P.packs);
     return FEM2D_OK;
