@@ -392,6 +392,7 @@ int device_symbolic(Plan& P, std::string& err) {
         if (mt >= (1ull << 32)) { err = "too many micro-tiles"; return FEM2D_ERR_UNSUPPORTED; }
     }
     const size_t o_voff = desc.reserve(h_voff.size() * 4), o_mtoff = desc.reserve(h_mtoff.size() * 4);
+    const size_t o_geom = desc.reserve(H.classes.size() * sizeof(ClassGeom));   // written on the device
     const size_t desc_plan_bytes = desc.size;                     // everything above lives as long as the plan
     const size_t o_blocks = desc.reserve(hb.size() * sizeof(DevBlock)), o_canon = desc.reserve(H.canon_dof.size() * 4);
     // staged in a cached pinned buffer: one asynchronous H2D at PCIe speed instead of a pageable copy
@@ -429,7 +430,7 @@ int device_symbolic(Plan& P, std::string& err) {
 #define CKC(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { err = std::string(#x) + ": " + cudaGetErrorString(e_); dev_free(scratch); dev_free(scratch2); return FEM2D_ERR_CUDA; } } while (0)
     // descriptors: the plan-owned part goes to a first small plan allocation, the rest into the scratch arena
     CKC(dev_malloc(&P.d_desc_arena, desc_plan_bytes));
-    CKC(cudaMemcpyAsync(P.d_desc_arena, blob, desc_plan_bytes, cudaMemcpyHostToDevice, nullptr));
+    CKC(cudaMemcpyAsync(P.d_desc_arena, blob, o_geom, cudaMemcpyHostToDevice, nullptr));   // the class constants behind o_geom are computed on the device
     CKC(cudaMemcpyAsync(at<char>(scratch, s_desc), blob + desc_plan_bytes, desc.size - desc_plan_bytes, cudaMemcpyHostToDevice, nullptr));
     P.d_classes = at<ClassDesc>(P.d_desc_arena, o_classes); P.d_lists = at<ListDesc>(P.d_desc_arena, o_lists);
     P.d_spec_i = at<uint8_t>(P.d_desc_arena, o_si); P.d_spec_j = at<uint8_t>(P.d_desc_arena, o_sj);
@@ -438,6 +439,8 @@ int device_symbolic(Plan& P, std::string& err) {
     P.d_work_counter = at<uint32_t>(P.d_desc_arena, o_ctr);
     P.d_packs = at<PackDesc>(P.d_desc_arena, o_packs);
     P.d_class_voff = at<uint32_t>(P.d_desc_arena, o_voff); P.d_class_mtoff = at<uint32_t>(P.d_desc_arena, o_mtoff);
+    P.d_class_geom = at<ClassGeom>(P.d_desc_arena, o_geom);
+    CKC(launch_class_geom(P, (uint32_t)H.classes.size(), nullptr));
     DevBlock* d_blocks = at<DevBlock>(scratch, s_desc + (o_blocks - desc_plan_bytes));
     uint32_t* d_canon = at<uint32_t>(scratch, s_desc + (o_canon - desc_plan_bytes));
     uint32_t *d_cnt = at<uint32_t>(scratch, s_cnt), *d_len = at<uint32_t>(scratch, s_len), *d_ldir = at<uint32_t>(scratch, s_ldir);

@@ -31,6 +31,7 @@ struct Plan {
     TableDesc* d_tables = nullptr;
     GramDesc* d_grams = nullptr;
     WorkItem* d_items = nullptr;
+    ClassGeom* d_class_geom = nullptr;   // desc arena; filled by launch_class_geom during the symbolic phase
     uint32_t* d_rows = nullptr;
     uint32_t* d_cols = nullptr;
     uint32_t* d_src1 = nullptr;
@@ -132,6 +133,7 @@ int device_col_runs_host(Plan& plan, cudaStream_t st, uint32_t n_ranges, const u
 void device_plan_release(Plan& plan);
 
 // kernels_exact.cu  (compiled with -fmad=false)
+cudaError_t launch_class_geom(const Plan& plan, uint32_t n_classes, cudaStream_t st);   // fills plan.d_class_geom from plan.d_classes
 cudaError_t launch_k1_tables(const Plan& plan, int basis_kind, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st);
 cudaError_t launch_k2_exact(const Plan& plan, const WorkItem* d_items, uint32_t n_items, const PackDesc* d_packs, const ItemSplit& split,
                             uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches);

@@ -57,11 +57,20 @@ struct K2Args {
     // launch); 0: it follows the first integrator grid, which it does not depend on -- it runs alongside it and waits for it only
     // before exiting, so that a grid waiting on this one has transitively waited on both.
     int follows_sampler;
-    uint32_t list_cap;   // warp-specialised integrator: bytes reserved per cached BasisSpec order list (>= the longest list, multiple of 16)
-    uint32_t col_cap;    // ... and entries of its column table (>= the widest pack's slab row, multiple of 4)
+    uint32_t col_cap;    // warp-specialised integrator: entries of its column table (>= the widest pack's slab row, multiple of 4)
+    const ClassGeom* geom;   // warp-specialised integrator: per-class constants (class_geom_kernel)
+    int roles_by_subpartition;   // warp-specialised integrator: 1 = staging warps chosen by SM sub-partition (default), 0 = by warp index (tuning)
 };
 
 __device__ __forceinline__ uint32_t pad4(uint32_t x) { return (x + 3u) & ~3u; }
+
+// Row stride (doubles) of a sampled table inside the staging warps' shared-memory cache.  The lanes of a staging warp read the rows of
+// 32 different (i, j) orders at once; with the natural stride (8 or 12 points = 64 or 96 bytes) those rows start in 2 or 4 bank
+// groups only.  An odd stride puts up to 16 different orders into 16 different 8-byte bank pairs.
+#ifndef FEM2D_K2_WS_TABPAD
+#define FEM2D_K2_WS_TABPAD 1
+#endif
+__host__ __device__ __forceinline__ uint32_t ws_tab_stride(uint32_t npt) { return FEM2D_K2_WS_TABPAD ? (npt | 1u) : npt; }
 
 // Accumulators of one thread: acc[2][TP][MT_Q].  Same-direction tile (TP x MT_Q pairs): [0] = A, [1] = B.  Cross-direction tile
 // (TP x MT_QX pairs, A only): column c lives in [c >> 1][r][c & 1].
@@ -448,62 +457,77 @@ __device__ __forceinline__ void ws_stage_column(const double* __restrict__ colA,
     }
 }
 
-// Stages the slab columns a pack needs for the quadrature rows [m0, m0 + nrow) with the 32 lanes of one warp (same values, same
+struct WsTask {
+    const double* colA; const double* colB; const double* rowA; const double* rowB;   // n-axis / m-axis factors of curl and value
+    double jj, ps;
+    double* sC; double* sF;     // the column's first entry in the curl / value slab of this chunk
+    uint32_t stride;
+    int flip;
+    bool scaled;
+};
+
+__device__ __forceinline__ WsTask ws_task(const K2Args& g, const WsCtx& c, uint32_t e, const double* s_tab, double* buf, uint32_t chunk, uint32_t m0) {
+    const uint32_t TS = ws_tab_stride(g.NPT), AS = g.NO * TS;
+    const uint32_t col = e & 0xffffu, side = (e >> 16) & 1u;
+    const WsSeg& sg = c.seg[(e >> 17) & 3u];
+    const uint32_t strideP = sg.strideP, strideQ = sg.strideQ;
+    const uint32_t nUF = side ? sg.nUQ : sg.nUP;
+    WsTask k;
+    k.stride = side ? strideQ : strideP;
+    double* seg_buf = buf + (size_t)chunk * sg.slab_off;
+    // slabs of a segment: C_P [chunk][strideP], F_P, then (non-local) C_Q [chunk][strideQ], F_Q
+    k.sC = seg_buf + (side ? (size_t)chunk * 2 * strideP : 0) + col;
+    k.sF = k.sC + (size_t)chunk * k.stride;
+    // table cache slots: 0 / 1 = the scaled u / v tables of a non-local P side, 2 / 3 = the unscaled tables (every Q side, local P sides)
+    const uint32_t slot_u = (side || sg.local) ? 2u : 0u;
+    const double* tu = s_tab + (size_t)slot_u * 3 * AS;          // cached tables hold N, T, T' (N' is never sampled on this path)
+    const double* tv = s_tab + (size_t)(slot_u + 1) * 3 * AS;
+    const bool isU = col < pad4(nUF);
+    const uint32_t i = (e >> 20) & 31u, j = (e >> 25) & 31u;   // the column's (i, j) orders travel in its table entry (pack set-up)
+    // U-directed: curl = -((jiu * (N_i(m) * T'_j(n))) * ps0), val = (jiu * N_i(m)) * T_j(n)        (basis.rs:225-242)
+    // V-directed: curl =   (jiv * (T'_i(m) * N_j(n))) * ps1,  val = (jiv * T_i(m)) * N_j(n)        (basis.rs:230-252)
+    // cache layout: [N | T | T'] x order x point
+    k.rowA = tu + (isU ? 0 : 2) * AS + i * TS + m0;   // factor of the curl taken at m: N_i | T'_i
+    k.rowB = tu + (isU ? 0 : 1) * AS + i * TS + m0;   // factor of the value taken at m: N_i | T_i
+    k.colA = tv + (isU ? 2 : 0) * AS + j * TS;        // factor of the curl taken at n: T'_j | N_j
+    k.colB = tv + (isU ? 1 : 0) * AS + j * TS;        // factor of the value taken at n: T_j | N_j
+    k.jj = isU ? (side ? sg.jiuQ : sg.jiuP) : (side ? sg.jivQ : sg.jivP);
+    // derivative scale = the OTHER function's para_scale (integrals.rs:44,47); Q's is (1,1), P's is (su,sv)
+    k.ps = side ? (isU ? sg.su : sg.sv) : 1.0;
+    k.scaled = k.ps != 1.0;                    // x * 1.0 == x bit for bit: the product is skipped
+    k.flip = isU ? (int)0x80000000 : 0;        // IEEE negation = sign-bit flip, done in the integer pipe
+    return k;
+}
+
+// Stages the slab columns a pack needs for the quadrature rows [m0, m0 + nrow) with the lanes of the staging warps (same values, same
 // operation order as the staging pass of k2_exact_kernel).  One task = one function column of one segment for the whole chunk, taken
-// from the pack's column table (segment | side | column), so the lanes stay busy whatever the widths of the segments: the column's
-// (i, j) orders are looked up once, the v-axis table values of four points are held in registers while the rows m run inside, and the
-// inner body is four FP64 operations and two shared-memory stores per (function, point) with no loads in the dependent chain.
+// from the pack's column table (column | side | segment | i | j), so the lanes stay busy whatever the widths of the segments: the
+// v-axis table values of four points are held in registers while the rows m run inside, and the inner body is four FP64 operations and
+// two shared-memory stores per (function, point) with no loads in the dependent chain.
 template <int PROD>
-__device__ __forceinline__ void ws_stage_chunk(const K2Args& g, const WsCtx& c, const uint32_t* s_cols, uint32_t n_cols, const double* s_tab, const uint8_t* s_spec,
+__device__ __forceinline__ void ws_stage_chunk(const K2Args& g, const WsCtx& c, const uint32_t* s_cols, uint32_t n_cols, const double* s_tab,
                                                double* buf, uint32_t chunk, uint32_t m0, uint32_t nrow, uint32_t lane) {
-    const uint32_t nv = g.nv, AS = g.NO * g.NPT;
+    const uint32_t nv = g.nv;
+    const uint32_t npair = nrow & ~1u;
+    // eight independent chains per step, written stage by stage so that the in-order issue of a staging warp never waits on the
+    // 8-cycle FP64 latency: 4 points x 2 quadrature rows, then 4 points x the odd last row
     for (uint32_t t = lane; t < n_cols; t += PROD * 32) {   // `lane`: index across the staging warps
-        const uint32_t e = s_cols[t], col = e & 0xffffu, side = (e >> 16) & 1u;
-        const WsSeg& sg = c.seg[e >> 17];
-        const uint32_t strideP = sg.strideP, strideQ = sg.strideQ;
-        const uint32_t stride = side ? strideQ : strideP, nF = side ? sg.nQ : sg.nP, nUF = side ? sg.nUQ : sg.nUP;
-        double* seg_buf = buf + (size_t)chunk * sg.slab_off;
-        // slabs of a segment: C_P [chunk][strideP], F_P, then (non-local) C_Q [chunk][strideQ], F_Q
-        double* sC = seg_buf + (side ? (size_t)chunk * 2 * strideP : 0);
-        double* sF = sC + (size_t)chunk * stride;
-        // table cache slots: 0 / 1 = the scaled u / v tables of a non-local P side, 2 / 3 = the unscaled tables (every Q side, local P sides)
-        const uint32_t slot_u = (side || sg.local) ? 2u : 0u;
-        const double* tu = s_tab + (size_t)slot_u * 3 * AS;          // cached tables hold N, T, T' (N' is never sampled on this path)
-        const double* tv = s_tab + (size_t)(slot_u + 1) * 3 * AS;
-        const uint8_t* sp_i = s_spec + ((size_t)(e >> 17) * 4 + 2 * side) * g.list_cap; const uint8_t* sp_j = sp_i + g.list_cap;
-        const uint32_t padU = pad4(nUF);
-        // a padding column of a 4-wide tile row takes the values of the group's last function: only pairs beyond the block's last
-        // row / column read it, and their results are never stored
-        const bool isU = col < padU;
-        const uint32_t a = isU ? min(col, nUF - 1) : nUF + min(col - padU, nF - nUF - 1);
-        const uint32_t i = sp_i[a], j = sp_j[a];
-        // U-directed: curl = -((jiu * (N_i(m) * T'_j(n))) * ps0), val = (jiu * N_i(m)) * T_j(n)        (basis.rs:225-242)
-        // V-directed: curl =   (jiv * (T'_i(m) * N_j(n))) * ps1,  val = (jiv * T_i(m)) * N_j(n)        (basis.rs:230-252)
-        // cache layout: [N | T | T'] x order x point
-        const double* rowA = tu + (isU ? 0 : 2) * AS + i * g.NPT;   // factor of the curl taken at m: N_i | T'_i
-        const double* rowB = tu + (isU ? 0 : 1) * AS + i * g.NPT;   // factor of the value taken at m: N_i | T_i
-        const double* colA = tv + (isU ? 2 : 0) * AS + j * g.NPT;   // factor of the curl taken at n: T'_j | N_j
-        const double* colB = tv + (isU ? 1 : 0) * AS + j * g.NPT;   // factor of the value taken at n: T_j | N_j
-        const double jj = isU ? (side ? sg.jiuQ : sg.jiuP) : (side ? sg.jivQ : sg.jivP);
-        // derivative scale = the OTHER function's para_scale (integrals.rs:44,47); Q's is (1,1), P's is (su,sv)
-        const double ps = side ? (isU ? sg.su : sg.sv) : 1.0;
-        const bool scaled = ps != 1.0;                 // x * 1.0 == x bit for bit: the product is skipped
-        const int flip = isU ? (int)0x80000000 : 0;    // IEEE negation = sign-bit flip, done in the integer pipe
-        // eight independent chains per step, written stage by stage so that the in-order issue of the single staging warp never
-        // waits on the 8-cycle FP64 latency: 4 points x 2 quadrature rows, then 4 points x the odd last row
-        const uint32_t npair = nrow & ~1u;
-        if (npair) ws_stage_column<4, 2>(colA, colB, rowA + m0, rowB + m0, jj, ps, scaled, flip, sC + col, sF + col, stride, nv, npair);
-        if (nrow & 1u) ws_stage_column<4, 1>(colA, colB, rowA + m0 + npair, rowB + m0 + npair, jj, ps, scaled, flip,
-                                             sC + col + (size_t)npair * nv * stride, sF + col + (size_t)npair * nv * stride, stride, nv, 1u);
+        const WsTask a = ws_task(g, c, s_cols[t], s_tab, buf, chunk, m0);
+        if (npair) ws_stage_column<4, 2>(a.colA, a.colB, a.rowA, a.rowB, a.jj, a.ps, a.scaled, a.flip, a.sC, a.sF, a.stride, nv, npair);
+        if (nrow & 1u) ws_stage_column<4, 1>(a.colA, a.colB, a.rowA + npair, a.rowB + npair, a.jj, a.ps, a.scaled, a.flip, a.sC + (size_t)npair * nv * a.stride,
+                                             a.sF + (size_t)npair * nv * a.stride, a.stride, nv, 1u);
     }
 }
 
 // Copies the N, T, T' arrays of sampled table `id` (K1 layout [N | N' | T | T'] x order x point) into a cache slot.
 __device__ __forceinline__ void ws_cache_table(const K2Args& g, uint32_t id, double* dst, uint32_t lane) {
-    const uint32_t AS = g.NO * g.NPT;
+    const uint32_t AS = g.NO * g.NPT, TS = ws_tab_stride(g.NPT), AC = g.NO * TS;
     const double* src = g.tabs + (size_t)id * 4 * AS;
 #pragma unroll 4
-    for (uint32_t k = lane; k < AS; k += 32) { dst[k] = src[k]; dst[AS + k] = src[2 * AS + k]; dst[2 * AS + k] = src[3 * AS + k]; }
+    for (uint32_t a = lane; a < AS; a += 32) {
+        const uint32_t c = a + (a / g.NPT) * (TS - g.NPT);   // row o = a / NPT starts at o * TS
+        dst[c] = src[a]; dst[AC + c] = src[2 * AS + a]; dst[2 * AC + c] = src[3 * AS + a];
+    }
 }
 
 // One pass of a TP x 2 sub-tile over one quadrature row: inner += ((p * q) [* scale]) * v_w[n] for n = 0 .. nv-1 (glq.rs:24-28), then
@@ -561,6 +585,29 @@ __device__ unsigned long long g_ws_prof[8];
 #define WS_ADD(k, v)
 #endif
 
+// Per-class constants, once per plan.  HierCurlBasisFn::defined_over, basis.rs:395-413; M2D::det / inverse, space.rs:138-147; the same
+// expressions (and the same separately rounded operations) as the prologue of k2_exact_kernel.
+__global__ void class_geom_kernel(const ClassDesc* __restrict__ classes, uint32_t n, ClassGeom* __restrict__ out) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const ClassDesc& cd = classes[c];
+    const double dxP = cd.dxP, dyP = cd.dyP, dxQ = cd.dxQ, dyQ = cd.dyQ;
+    const double detP = dxP * dyP - 0.0 * 0.0, detQ = dxQ * dyQ - 0.0 * 0.0;
+    const double ge = (double)(detP >= detQ), lt = (double)(detP < detQ);
+    ClassGeom o;
+    o.jiuP = dyP / detP; o.jivP = dxP / detP;      // jac_inv.u[0] = dy_dv / det, jac_inv.v[1] = dx_du / det
+    o.jiuQ = dyQ / detQ; o.jivQ = dxQ / detQ;
+    o.ratio_uv = ge * (dxP / dyP) + lt * (dxQ / dyQ);   // max_uv_ratios integrals.rs:250-259, basis.rs:341-343
+    o.ratio_vu = ge * (dyP / dxP) + lt * (dyQ / dxQ);   // max_vu_ratios integrals.rs:262-271, basis.rs:346-348
+    o.maxdet = detP > detQ ? detP : detQ;               // partial_max integrals.rs:421-423
+    o.coefA = 1.0 / cd.mu;                              // integrals.rs:37
+    o.coefB = cd.eps * (cd.su * cd.sv) * (1.0 * 1.0);   // eps * p.glq_scale() * q.glq_scale() integrals.rs:303-305
+    out[c] = o;
+}
+
+constexpr uint32_t K2_WS_SM_SLOTS = 1024;
+__device__ uint32_t g_ws_sm_arrivals[K2_WS_SM_SLOTS];   // CTAs of the persistent integrator that have started on each SM, ever (only the parity is used)
+
 template <int TP, int PROD>
 __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const PackDesc* __restrict__ packs, const uint32_t n_packs, uint32_t* __restrict__ work_counter) {
     extern __shared__ __align__(16) double smem[];
@@ -573,20 +620,34 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
     WsCtx* s_ctx = reinterpret_cast<WsCtx*>(smem + 256 + 2 * K2_WS_NBUF);
     static_assert(sizeof(WsCtx) % 16 == 0, "context ring keeps the slabs 16-byte aligned");
     // staging-warp caches: four sampled tables (slots 0 / 1: scaled u / v tables of the non-local P sides of the current pack; 2 / 3: the
-    // unscaled u / v tables) and the (i, j) order lists of the P and Q sides of every segment of the current pack
-    const uint32_t AS3 = 3 * g.NO * g.NPT;
+    // unscaled u / v tables) and the column table of the current pack
+    const uint32_t AS3 = 3 * g.NO * ws_tab_stride(g.NPT);
     double* s_tab = smem + 256 + 2 * K2_WS_NBUF + K2_WS_NCTX * sizeof(WsCtx) / sizeof(double);
-    uint8_t* s_spec = reinterpret_cast<uint8_t*>(s_tab + 4 * (size_t)AS3);
-    uint32_t* s_cols = reinterpret_cast<uint32_t*>(s_spec + (size_t)K2_PACK_MAX * 4 * g.list_cap);   // column table of the current pack
+    uint32_t* s_cols = reinterpret_cast<uint32_t*>(s_tab + 4 * (size_t)AS3);   // column table of the current pack
     double* s_slab = reinterpret_cast<double*>(s_cols + g.col_cap);
     const uint32_t buf_doubles = g.slab_doubles;   // per ring buffer
-    const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const uint32_t lane = threadIdx.x % 32;
     const uint32_t nu = g.nu, nv = g.nv;
+    // Roles by SM sub-partition.  A warp's scheduler and FP64 pipe are those of its hardware warp slot (%warpid % 4, measured:
+    // scripts/micro/smsp_map.cu), a CTA of eight warps has two warps on each of the four sub-partitions, and which warp index sits
+    // where differs between the two CTAs of an SM.  With the staging warps taken by index the contraction warps of an SM spread
+    // 2 / 3 / 4 / 3 over the sub-partitions (two staging warps per CTA) and the fullest one paces every chunk.  So the first CTA on
+    // an SM stages on sub-partitions 0 (and 1), the second on 2 (and 3): 3 contraction warps + 1 staging warp everywhere with two
+    // staging warps per CTA.  Only the warp -> role map changes; tiles, threads slots and arithmetic do not.
+    __shared__ uint32_t s_smsp[K2_WS_WARPS], s_second;
+    {
+        uint32_t hw;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(hw));
+        if (lane == 0) s_smsp[threadIdx.x / 32] = hw & 3u;
+    }
 
     if (!g.follows_sampler) cudaTriggerProgrammaticLaunchCompletion();
     if (threadIdx.x == 0) {
         for (int b = 0; b < K2_WS_NBUF; b++) { mbar_init(&s_full[b], K2_WS_PROD_WARPS * 32); mbar_init(&s_empty[b], K2_WS_CONS_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_second = atomicAdd(&g_ws_sm_arrivals[smid % K2_WS_SM_SLOTS], 1u) & 1u;   // two consecutive arrivals on an SM always differ
     }
     for (uint32_t k = threadIdx.x; k < nu; k += blockDim.x) s_uw[k] = g.glq[128 + k];
     for (uint32_t k = threadIdx.x; k < nv; k += blockDim.x) s_vw[k] = g.glq[384 + k];
@@ -595,6 +656,26 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
         cudaTriggerProgrammaticLaunchCompletion();
     }
     __syncthreads();
+
+    // logical warp index: staging warps first (0 .. PROD-1), then the contraction warps in index order
+    uint32_t warp;
+    {
+        const uint32_t me = threadIdx.x / 32;
+        uint32_t taken = 0;   // bit w: warp w stages
+        int mine = -1;
+#pragma unroll
+        for (int k = 0; k < K2_WS_PROD_WARPS; k++) {
+            const uint32_t want = (2u * s_second + (uint32_t)k) & 3u;
+            uint32_t pick = 0xffffffffu;
+            for (uint32_t w = 0; w < (uint32_t)K2_WS_WARPS; w++)
+                if (g.roles_by_subpartition && pick == 0xffffffffu && !(taken >> w & 1u) && s_smsp[w] == want) pick = w;
+            for (uint32_t w = 0; w < (uint32_t)K2_WS_WARPS; w++)   // no warp there (never seen): lowest free index
+                if (pick == 0xffffffffu && !(taken >> w & 1u)) pick = w;
+            taken |= 1u << pick;
+            if (pick == me) mine = k;
+        }
+        warp = mine >= 0 ? (uint32_t)mine : (uint32_t)K2_WS_PROD_WARPS + me - (uint32_t)__popc(taken & ((1u << me) - 1u));
+    }
 
     uint32_t stage = 0, phase = 0, ci = 0;
     if (warp < K2_WS_PROD_WARPS) {
@@ -607,10 +688,13 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
         __shared__ uint32_t s_pack_idx, s_n_cols;
         if (warp == 0) { ws_cache_table(g, 0u, s_tab + 2 * (size_t)AS3, lane); ws_cache_table(g, 1u, s_tab + 3 * (size_t)AS3, lane); }   // tables 0 / 1: unscaled u / v points
         uint32_t cached_u = 0xffffffffu, cached_v = 0xffffffffu;                                 // table ids held by slots 0 / 1
+        // packs are claimed one ahead: the atomic's round trip runs behind the staging of the current pack
+        uint32_t next_idx = 0;
+        if (plane == 0) next_idx = atomicAdd(work_counter, 1u);
         for (;;) {
             WS_T(t_item0);
             prod_sync();   // every staging warp is done with the previous pack's caches and context
-            if (plane == 0) s_pack_idx = atomicAdd(work_counter, 1u);
+            if (plane == 0) { s_pack_idx = next_idx; if (next_idx < n_packs) next_idx = atomicAdd(work_counter, 1u); }
             prod_sync();
             const uint32_t idx = s_pack_idx;
             WsCtx& c = s_ctx[ci];
@@ -623,49 +707,23 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
             }
             const PackDesc pk = packs[idx];
             if (warp == 0) {
-            // ---- nine lanes per segment: work item, class, the nine FP64 quotients (an FP64 division is a ~30-instruction dependent chain,
-            // so each lane takes one), tile enumeration -> context.  Per-class constants: HierCurlBasisFn::defined_over, basis.rs:395-413;
-            // M2D::det / inverse, space.rs:138-147.
-            for (uint32_t s0 = 0; s0 < pk.n; s0 += 3) {
-                const uint32_t sgi = s0 + lane / 9, k = lane % 9;
-                const bool mine = lane < 27 && sgi < pk.n;
-                double quot = 0.0, detP = 0.0, detQ = 0.0;
-                uint32_t cls = 0;
-                if (mine) {
-                    cls = g.items[pk.first + sgi].cls;
-                    const ClassDesc& cd = g.classes[cls];
-                    const double dxP = cd.dxP, dyP = cd.dyP, dxQ = cd.dxQ, dyQ = cd.dyQ;
-                    detP = dxP * dyP - 0.0 * 0.0; detQ = dxQ * dyQ - 0.0 * 0.0;
-                    const double num = k == 0 ? dyP : k == 1 ? dxP : k == 2 ? dyQ : k == 3 ? dxQ : k == 4 ? dxP : k == 5 ? dxQ : k == 6 ? dyP : k == 7 ? dyQ : 1.0;
-                    const double den = k < 2 ? detP : k < 4 ? detQ : k == 4 ? dyP : k == 5 ? dyQ : k == 6 ? dxP : k == 7 ? dxQ : cd.mu;
-                    quot = num / den;
-                }
-                const uint32_t base = lane - k;   // first lane of my segment's group
-                const double q0 = __shfl_sync(0xffffffffu, quot, base), q1 = __shfl_sync(0xffffffffu, quot, base + 1), q2 = __shfl_sync(0xffffffffu, quot, base + 2);
-                const double q3 = __shfl_sync(0xffffffffu, quot, base + 3), q4 = __shfl_sync(0xffffffffu, quot, base + 4), q5 = __shfl_sync(0xffffffffu, quot, base + 5);
-                const double q6 = __shfl_sync(0xffffffffu, quot, base + 6), q7 = __shfl_sync(0xffffffffu, quot, (base + 7) & 31), q8 = __shfl_sync(0xffffffffu, quot, (base + 8) & 31);
-                if (mine && k == 0) {
-                    WsSeg& sg = c.seg[sgi];
-                    const WorkItem it = g.items[pk.first + sgi];
-                    const ClassDesc cd = g.classes[cls];
-                    const uint32_t nP = cd.lp.n, nUP = cd.lp.nU, nQ = cd.lq.n, nUQ = cd.lq.nU;
-                    const double ge = (double)(detP >= detQ), lt = (double)(detP < detQ);
-                    sg.it = it;
-                    sg.sb = make_subblocks(nP, nUP, nQ, nUQ, cd.local, TP);
-                    sg.jiuP = q0; sg.jivP = q1;      // jac_inv.u[0] = dy_dv / det, jac_inv.v[1] = dx_du / det
-                    sg.jiuQ = q2; sg.jivQ = q3;
-                    sg.ratio_uv = ge * q4 + lt * q5;   // max_uv_ratios integrals.rs:250-259, basis.rs:341-343: ge * (dxP / dyP) + lt * (dxQ / dyQ)
-                    sg.ratio_vu = ge * q6 + lt * q7;   // max_vu_ratios integrals.rs:262-271, basis.rs:346-348: ge * (dyP / dxP) + lt * (dyQ / dxQ)
-                    sg.maxdet = detP > detQ ? detP : detQ;                           // partial_max integrals.rs:421-423
-                    sg.coefA = q8;                                                   // 1.0 / mu, integrals.rs:37
-                    sg.coefB = cd.eps * (cd.su * cd.sv) * (1.0 * 1.0);               // eps * p.glq_scale() * q.glq_scale() integrals.rs:303-305
-                    sg.su = cd.su; sg.sv = cd.sv;
-                    sg.v_off = cd.v_off;
-                    sg.nP = nP; sg.nUP = nUP; sg.nQ = nQ; sg.nUQ = nUQ; sg.local = cd.local;
-                    sg.strideP = pad4(nUP) + pad4(nP - nUP);
-                    sg.strideQ = cd.local ? sg.strideP : pad4(nUQ) + pad4(nQ - nUQ);
-                    sg.listP_off = cd.lp.off; sg.listQ_off = cd.lq.off; sg.tabPu = cd.tabPu; sg.tabPv = cd.tabPv;
-                }
+            // ---- one lane per segment: work item, class, per-class constants (ClassGeom) -> context
+            if (lane < pk.n) {
+                WsSeg& sg = c.seg[lane];
+                const WorkItem it = g.items[pk.first + lane];
+                const ClassDesc cd = g.classes[it.cls];
+                const ClassGeom cg = g.geom[it.cls];
+                const uint32_t nP = cd.lp.n, nUP = cd.lp.nU, nQ = cd.lq.n, nUQ = cd.lq.nU;
+                sg.it = it;
+                sg.sb = make_subblocks(nP, nUP, nQ, nUQ, cd.local, TP);
+                sg.jiuP = cg.jiuP; sg.jivP = cg.jivP; sg.jiuQ = cg.jiuQ; sg.jivQ = cg.jivQ;
+                sg.ratio_uv = cg.ratio_uv; sg.ratio_vu = cg.ratio_vu; sg.maxdet = cg.maxdet; sg.coefA = cg.coefA; sg.coefB = cg.coefB;
+                sg.su = cd.su; sg.sv = cd.sv;
+                sg.v_off = cd.v_off;
+                sg.nP = nP; sg.nUP = nUP; sg.nQ = nQ; sg.nUQ = nUQ; sg.local = cd.local;
+                sg.strideP = pad4(nUP) + pad4(nP - nUP);
+                sg.strideQ = cd.local ? sg.strideP : pad4(nUQ) + pad4(nQ - nUQ);
+                sg.listP_off = cd.lp.off; sg.listQ_off = cd.lq.off; sg.tabPu = cd.tabPu; sg.tabPv = cd.tabPv;
             }
             __syncwarp();
             // ---- slot / slab offsets of the segments, chunk size
@@ -681,20 +739,10 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
             const uint32_t chunk_rows = min(nu, buf_doubles / (2 * nv * tot_stride));
             const uint32_t gap = item_gap(n_same, n_same + n_cross), n_slots = n_same + n_cross + gap;
             if (lane == 0) { c.n_seg = pk.n; c.chunk_rows = chunk_rows; c.n_slots = n_slots; c.gap = gap; c.n_same = n_same; c.end = 0u; }
-            // ---- caches: the scaled P-side tables (the ancestor sampled over the descendant, basis.rs:372-393) and the order lists
+            // ---- caches: the scaled P-side tables (the ancestor sampled over the descendant, basis.rs:372-393)
             if (tab_u != 0xffffffffu && cached_u != tab_u) { ws_cache_table(g, tab_u, s_tab, lane); cached_u = tab_u; }
             if (tab_v != 0xffffffffu && cached_v != tab_v) { ws_cache_table(g, tab_v, s_tab + AS3, lane); cached_v = tab_v; }
-            for (uint32_t s2 = 0; s2 < pk.n; s2++) {
-                const WsSeg& sg = c.seg[s2];
-                uint8_t* sp = s_spec + (size_t)s2 * 4 * g.list_cap;
-#pragma unroll 4
-                for (uint32_t k = lane; k < sg.nP; k += 32) { sp[k] = g.spec_i[sg.listP_off + k]; sp[g.list_cap + k] = g.spec_j[sg.listP_off + k]; }
-                if (!sg.local) {
-#pragma unroll 4
-                    for (uint32_t k = lane; k < sg.nQ; k += 32) { sp[2 * g.list_cap + k] = g.spec_i[sg.listQ_off + k]; sp[3 * g.list_cap + k] = g.spec_j[sg.listQ_off + k]; }
-                }
-            }
-            // ---- column table: every slab column the pack's tiles touch, as segment | side | column
+            // ---- column table: every slab column the pack's tiles touch, as column | side << 16 | segment << 17 | i << 20 | j << 25
             uint32_t n_cols = 0;
             for (uint32_t s2 = 0; s2 < pk.n; s2++) {
                 const WsSeg& sg = c.seg[s2];
@@ -704,6 +752,33 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
                         for (uint32_t k = lane; k < c_w; k += 32) s_cols[n_cols + k] = s2 << 17 | side << 16 | (c_lo + k);
                         n_cols += c_w;
                     }
+            }
+            __syncwarp();
+            // (i, j) orders of the columns' functions, straight from the plan's pooled BasisSpec lists: 8 columns per lane and batch, so
+            // that all global loads of a batch are in flight together (one L2 round trip per 256 columns)
+            for (uint32_t t0 = 0; t0 < n_cols; t0 += 8 * 32) {
+                uint32_t e[8], vi[8], vj[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const uint32_t t = t0 + u * 32 + lane;
+                    e[u] = 0; vi[u] = 0; vj[u] = 0;
+                    if (t < n_cols) {
+                        e[u] = s_cols[t];
+                        const WsSeg& sg = c.seg[(e[u] >> 17) & 3u];
+                        const uint32_t side = (e[u] >> 16) & 1u, col = e[u] & 0xffffu;
+                        const uint32_t nF = side ? sg.nQ : sg.nP, nUF = side ? sg.nUQ : sg.nUP, padU = pad4(nUF);
+                        // a padding column of a 4-wide tile row takes the values of the group's last function: only pairs beyond the block's
+                        // last row / column read it, and their results are never stored
+                        const uint32_t a = col < padU ? min(col, nUF - 1) : nUF + min(col - padU, nF - nUF - 1);
+                        const uint32_t off = (side ? sg.listQ_off : sg.listP_off) + a;
+                        vi[u] = g.spec_i[off]; vj[u] = g.spec_j[off];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const uint32_t t = t0 + u * 32 + lane;
+                    if (t < n_cols) s_cols[t] = e[u] | vi[u] << 20 | vj[u] << 25;
+                }
             }
             if (lane == 0) s_n_cols = n_cols;
             }   // warp == 0
@@ -718,7 +793,7 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
                     mbar_wait(&s_empty[stage], phase ^ 1u);     // the contraction warps are done with what this buffer held
                     WS_T(t_w1);
                     double* buf = s_slab + (size_t)stage * buf_doubles;
-                    ws_stage_chunk<PROD>(g, c, s_cols, n_cols, s_tab, s_spec, buf, chunk, m0, nrow, plane);
+                    ws_stage_chunk<PROD>(g, c, s_cols, n_cols, s_tab, buf, chunk, m0, nrow, plane);
                     __syncwarp();
                     WS_T(t_w2); if (warp == 0) { WS_ADD(1, t_w1 - t_w0); WS_ADD(2, t_w2 - t_w1); WS_ADD(6, 1); }
                     mbar_arrive(&s_full[stage]);   // every staging lane releases its own slab stores (the staging warps have slack for the 32 arrivals)
@@ -729,7 +804,7 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
         }
     } else {
         // ============================================================================================ contraction warps
-        const uint32_t tid = threadIdx.x - K2_WS_PROD_WARPS * 32;   // 0 .. CONS-1
+        const uint32_t tid = (warp - K2_WS_PROD_WARPS) * 32 + lane;   // 0 .. CONS-1
         for (;;) {
             WS_T(t_f0);
             mbar_wait(&s_full[stage], phase);   // first chunk of the next pack (or the end marker); its context is complete
@@ -740,14 +815,24 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
             const uint32_t n_slots = c.n_slots, gap = c.gap, n_same = c.n_same, n_seg = c.n_seg, chunk_rows = c.chunk_rows;
             const uint32_t chunk = chunk_rows * nv;
             bool first = true;
-            // K2_WS_TPT micro-tiles per thread and round: every staged chunk feeds TPT x CONS tiles
-            for (uint32_t round0 = 0; round0 < n_slots; round0 += K2_WS_TPT * CONS) {
-                // ---- my micro-tiles of this round: code = sub | segment << 2 | row tile << 4 | column tile << 18, 0xffffffff = none
-                uint32_t code[K2_WS_TPT], prow[K2_WS_TPT], pcol[K2_WS_TPT];
-#pragma unroll
-                for (int t = 0; t < K2_WS_TPT; t++) {
-                    const uint32_t slot = round0 + t * CONS + tid;
-                    code[t] = 0xffffffffu; prow[t] = 0; pcol[t] = 0;
+            // One round = CONS thread slots.  A thread holds two ASSIGNMENTS, one per pass over a quadrature row:
+            //   same-direction slot: both are its own 4 x 2 tile (pass 0 accumulates A from the curl slabs, pass 1 B from the value slabs);
+            //   cross-direction slot (A only, 4 x 4 tile = two 4 x 2 halves): the 64 halves of a warp's 32 tiles are dealt so that in each
+            //   pass the lanes read CONSECUTIVE column pairs -- lane l takes half l % 2 of tile 16 * pass + l / 2 of its warp.  (A lane that
+            //   takes both halves of its own tile reads 16 bytes at a 32-byte lane stride: a two-way bank conflict on every Q-side load,
+            //   8 instead of 4 LSU cycles, scripts/micro/lds_bw.cu.)  Which lane computes a pair does not enter its value.
+            // asg = sub | segment << 2 | half << 4 | row tile << 5 | column tile << 19, 0xffffffff = none; rc = slab column of the first row | of the first column << 16
+            static_assert(K2_WS_TPT == 1, "one micro-tile slot per contraction thread and round");
+            for (uint32_t round0 = 0; round0 < n_slots; round0 += CONS) {
+                uint32_t asg[2], rc[2];
+                const uint32_t my_slot = round0 + tid;
+                const bool cross_warp = (my_slot & ~31u) >= n_same + gap;   // cross-direction tiles start on a warp boundary (item_gap)
+    #pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t slot = cross_warp ? (my_slot & ~31u) + 16u * h + (lane >> 1) : my_slot;
+                    const uint32_t half = cross_warp ? (lane & 1u) : 0u;
+                    asg[h] = 0xffffffffu; rc[h] = 0;
+                    if (h == 1 && !cross_warp) { asg[1] = asg[0]; rc[1] = rc[0]; continue; }
                     if (slot < n_slots && !(slot >= n_same && slot < n_same + gap)) {
                         // segment: the same-direction tiles of all segments come first (segment by segment), then the cross-direction ones
                         const bool is_same = slot < n_same;
@@ -758,21 +843,20 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
                         uint32_t li = is_same ? k - sg.same_off : sg.it.n_same + (k - sg.cross_off), r = 0, sub, rt, ct;
                         while (li >= sg.it.rcount[r]) { li -= sg.it.rcount[r]; r++; }        // which of the item's tile ranges
                         decode_tile(sg.sb, sg.it.rbegin[r] + li, TP, sub, rt, ct);
-                        code[t] = sub | sgi << 2 | rt << 4 | ct << 18;
-                        prow[t] = (sub >= 2 ? pad4(sg.nUP) - sg.nUP : 0) + sg.sb.row0[sub] + rt * TP;               // slab column of the canonical row index
-                        pcol[t] = ((sub & 1) ? pad4(sg.nUQ) - sg.nUQ : 0) + sg.sb.col0[sub] + ct * mt_width(sub);
+                        asg[h] = sub | sgi << 2 | half << 4 | rt << 5 | ct << 19;
+                        const uint32_t prow = (sub >= 2 ? pad4(sg.nUP) - sg.nUP : 0) + sg.sb.row0[sub] + rt * TP;               // slab column of the canonical row index
+                        const uint32_t pcol = ((sub & 1) ? pad4(sg.nUQ) - sg.nUQ : 0) + sg.sb.col0[sub] + ct * mt_width(sub) + half * MT_Q;
+                        rc[h] = prow | pcol << 16;
                     }
                 }
-                // sol[t][0] / sol[t][1]: A / B of a same-direction tile; columns 0-1 / 2-3 (A only) of a cross-direction tile
-                double sol[K2_WS_TPT][2][TP][MT_Q];
-#pragma unroll
-                for (int t = 0; t < K2_WS_TPT; t++)
-#pragma unroll
-                    for (int h = 0; h < 2; h++)
-#pragma unroll
-                        for (int r = 0; r < TP; r++)
-#pragma unroll
-                            for (int q = 0; q < MT_Q; q++) sol[t][h][r][q] = 0.0;
+                // sol[0] / sol[1]: A / B of a same-direction tile; the A values of the two cross-direction halves
+                double sol[2][TP][MT_Q];
+    #pragma unroll
+                for (int h = 0; h < 2; h++)
+    #pragma unroll
+                    for (int r = 0; r < TP; r++)
+    #pragma unroll
+                        for (int q = 0; q < MT_Q; q++) sol[h][r][q] = 0.0;
                 for (uint32_t m0 = 0; m0 < nu; m0 += chunk_rows) {
                     const uint32_t nrow = min(chunk_rows, nu - m0);
                     WS_T(t_c0);
@@ -781,32 +865,40 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
                     WS_T(t_c1);
                     if (warp == K2_WS_PROD_WARPS) WS_ADD(3, t_c1 - t_c0);
                     const double* buf = s_slab + (size_t)stage * buf_doubles;
-#pragma unroll
-                    for (int t = 0; t < K2_WS_TPT; t++) {
-                        if (code[t] == 0xffffffffu) continue;
-                        const uint32_t sub = code[t] & 3u;
-                        const WsSeg& sg = c.seg[(code[t] >> 2) & 3u];
-                        const uint32_t strideP = sg.strideP, strideQ = sg.strideQ;
-                        const double* s_CP = buf + (size_t)chunk * sg.slab_off; const double* s_FP = s_CP + (size_t)chunk * strideP;
-                        const double* s_CQ = sg.local ? s_CP : s_FP + (size_t)chunk * strideP;
-                        const double* cp = s_CP + prow[t]; const double* cq = s_CQ + pcol[t];
-                        if (sub == 0 || sub == 3) {
+                    if (!cross_warp) {
+                        if (asg[0] != 0xffffffffu) {
+                            const uint32_t sub = asg[0] & 3u;
+                            const WsSeg& sg = c.seg[(asg[0] >> 2) & 3u];
+                            const uint32_t strideP = sg.strideP, strideQ = sg.strideQ;
+                            const double* s_CP = buf + (size_t)chunk * sg.slab_off; const double* s_FP = s_CP + (size_t)chunk * strideP;
+                            const double* s_CQ = sg.local ? s_CP : s_FP + (size_t)chunk * strideP;
                             const double* s_FQ = sg.local ? s_FP : s_CQ + (size_t)chunk * strideQ;
+                            const double* cp = s_CP + (rc[0] & 0xffffu); const double* cq = s_CQ + (rc[0] >> 16);
+                            const double* fp = s_FP + (rc[0] & 0xffffu); const double* fq = s_FQ + (rc[0] >> 16);
                             const double ratio = sub == 0 ? sg.ratio_uv : sg.ratio_vu, maxdet = sg.maxdet;
-                            const double* fp = s_FP + prow[t]; const double* fq = s_FQ + pcol[t];
                             for (uint32_t r = 0; r < nrow; r++) {
                                 const double uw = s_uw[m0 + r];
-                                ws_row_pass<true, TP>(cp, cq, strideP, strideQ, s_vw, nv, ratio, uw, sol[t][0]);      // A: (curl_p * curl_q) * ratio
-                                ws_row_pass<true, TP>(fp, fq, strideP, strideQ, s_vw, nv, maxdet, uw, sol[t][1]);     // B: (val_p * val_q) * max(det)
+                                ws_row_pass<true, TP>(cp, cq, strideP, strideQ, s_vw, nv, ratio, uw, sol[0]);      // A: (curl_p * curl_q) * ratio
+                                ws_row_pass<true, TP>(fp, fq, strideP, strideQ, s_vw, nv, maxdet, uw, sol[1]);     // B: (val_p * val_q) * max(det)
                                 cp += (size_t)nv * strideP; cq += (size_t)nv * strideQ; fp += (size_t)nv * strideP; fq += (size_t)nv * strideQ;
                             }
-                        } else {
-                            for (uint32_t r = 0; r < nrow; r++) {
-                                const double uw = s_uw[m0 + r];
-                                ws_row_pass<false, TP>(cp, cq, strideP, strideQ, s_vw, nv, 1.0, uw, sol[t][0]);       // A, columns 0-1
-                                ws_row_pass<false, TP>(cp, cq + MT_Q, strideP, strideQ, s_vw, nv, 1.0, uw, sol[t][1]);   // A, columns 2-3
-                                cp += (size_t)nv * strideP; cq += (size_t)nv * strideQ;
-                            }
+                        }
+                    } else {
+                        // the two halves may belong to different segments of a pack: each carries its own slabs and strides
+                        const double* cp[2]; const double* cq[2]; uint32_t sP[2], sQ[2];
+    #pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const WsSeg& sg = c.seg[asg[h] == 0xffffffffu ? 0u : (asg[h] >> 2) & 3u];
+                            sP[h] = sg.strideP; sQ[h] = sg.strideQ;
+                            const double* s_CP = buf + (size_t)chunk * sg.slab_off;
+                            const double* s_CQ = sg.local ? s_CP : s_CP + (size_t)chunk * 2 * sP[h];
+                            cp[h] = s_CP + (rc[h] & 0xffffu); cq[h] = s_CQ + (rc[h] >> 16);
+                        }
+                        for (uint32_t r = 0; r < nrow; r++) {
+                            const double uw = s_uw[m0 + r];
+                            if (asg[0] != 0xffffffffu) ws_row_pass<false, TP>(cp[0], cq[0], sP[0], sQ[0], s_vw, nv, 1.0, uw, sol[0]);
+                            if (asg[1] != 0xffffffffu) ws_row_pass<false, TP>(cp[1], cq[1], sP[1], sQ[1], s_vw, nv, 1.0, uw, sol[1]);
+                            cp[0] += (size_t)nv * sP[0]; cq[0] += (size_t)nv * sQ[0]; cp[1] += (size_t)nv * sP[1]; cq[1] += (size_t)nv * sQ[1];
                         }
                     }
                     __syncwarp();
@@ -815,39 +907,48 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
                     if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp is done reading the buffer
                     stage = stage + 1 == K2_WS_NBUF ? 0u : stage + 1; phase ^= (stage == 0u);
                 }
-#pragma unroll
-                for (int t = 0; t < K2_WS_TPT; t++) {
-                    if (code[t] == 0xffffffffu) continue;
-                    const uint32_t sub = code[t] & 3u, rt = (code[t] >> 4) & 0x3fffu, ct = code[t] >> 18;
-                    const WsSeg& sg = c.seg[(code[t] >> 2) & 3u];
-                    const uint32_t row0 = sg.sb.row0[sub] + rt * TP, col0 = sg.sb.col0[sub] + ct * mt_width(sub);
-                    const uint32_t row_end = sg.sb.row0[sub] + sg.sb.rows[sub], col_end = sg.sb.col0[sub] + sg.sb.cols[sub];
-                    const uint32_t nQ = sg.nQ;
-                    const double coefA = sg.coefA, coefB = sg.coefB;
-                    double2* out = g.V + sg.v_off;
-                    if (sub == 0 || sub == 3) {
-#pragma unroll
+                if (!cross_warp) {
+                    if (asg[0] != 0xffffffffu) {
+                        const uint32_t sub = asg[0] & 3u, rt = (asg[0] >> 5) & 0x3fffu, ct = asg[0] >> 19;
+                        const WsSeg& sg = c.seg[(asg[0] >> 2) & 3u];
+                        const uint32_t row0 = sg.sb.row0[sub] + rt * TP, col0 = sg.sb.col0[sub] + ct * MT_Q;
+                        const uint32_t row_end = sg.sb.row0[sub] + sg.sb.rows[sub], col_end = sg.sb.col0[sub] + sg.sb.cols[sub];
+                        const uint32_t nQ = sg.nQ;
+                        const double coefA = sg.coefA, coefB = sg.coefB;
+                        double2* out = g.V + sg.v_off;
+    #pragma unroll
                         for (int r = 0; r < TP; r++) {
                             const uint32_t a = row0 + r;
                             if (a >= row_end) continue;
-#pragma unroll
+    #pragma unroll
                             for (int q = 0; q < MT_Q; q++) {
                                 const uint32_t b = col0 + q;
                                 if (b >= col_end) continue;
-                                out[(size_t)a * nQ + b] = make_double2(coefA * sol[t][0][r][q], coefB * sol[t][1][r][q]);
+                                out[(size_t)a * nQ + b] = make_double2(coefA * sol[0][r][q], coefB * sol[1][r][q]);
                             }
                         }
-                    } else {
-#pragma unroll
+                    }
+                } else {
+    #pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        if (asg[h] == 0xffffffffu) continue;
+                        const uint32_t sub = asg[h] & 3u, half = (asg[h] >> 4) & 1u, rt = (asg[h] >> 5) & 0x3fffu, ct = asg[h] >> 19;
+                        const WsSeg& sg = c.seg[(asg[h] >> 2) & 3u];
+                        const uint32_t row0 = sg.sb.row0[sub] + rt * TP, col0 = sg.sb.col0[sub] + ct * MT_QX + half * MT_Q;
+                        const uint32_t row_end = sg.sb.row0[sub] + sg.sb.rows[sub], col_end = sg.sb.col0[sub] + sg.sb.cols[sub];
+                        const uint32_t nQ = sg.nQ;
+                        const double coefA = sg.coefA, coefB = sg.coefB;
+                        double2* out = g.V + sg.v_off;
+    #pragma unroll
                         for (int r = 0; r < TP; r++) {
                             const uint32_t a = row0 + r;
                             if (a >= row_end) continue;
-#pragma unroll
-                            for (int q = 0; q < MT_QX; q++) {
+    #pragma unroll
+                            for (int q = 0; q < MT_Q; q++) {
                                 const uint32_t b = col0 + q;
                                 if (b >= col_end) continue;
                                 // cross-direction mass entries: every integrand term is a signed zero, the quadrature returns +0.0 (integrals.rs:318-339)
-                                out[(size_t)a * nQ + b] = make_double2(coefA * sol[t][q >> 1][r][q & 1], coefB * 0.0);
+                                out[(size_t)a * nQ + b] = make_double2(coefA * sol[h][r][q], coefB * 0.0);
                             }
                         }
                     }
@@ -884,6 +985,12 @@ cudaError_t launch_k1_tables(const Plan& P, int basis_kind, uint32_t nu, uint32_
     return cudaGetLastError();
 }
 
+cudaError_t launch_class_geom(const Plan& P, uint32_t n_classes, cudaStream_t st) {
+    if (n_classes == 0) return cudaSuccess;
+    class_geom_kernel<<<(n_classes + 127) / 128, 128, 0, st>>>(P.d_classes, n_classes, P.d_class_geom);
+    return cudaGetLastError();
+}
+
 // One launch of the exact integrator over items [first, first + count) with CTAs of NT threads; max_stride = widest slab row
 // among those items' classes, soft = shared-memory budget per CTA that keeps the intended number of CTAs on an SM.
 template <int NT>
@@ -914,7 +1021,7 @@ static cudaError_t launch_k2_part(const Plan& P, const WorkItem* d_items, uint32
             done[P.device] = true;
         }
     }
-    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, slab_doubles, follows_sampler, 0u, 0u};
+    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, slab_doubles, follows_sampler, 0u, nullptr, 0};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(count); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -925,10 +1032,10 @@ static cudaError_t launch_k2_part(const Plan& P, const WorkItem* d_items, uint32
 }
 
 // Shared memory of the warp-specialised integrator in front of its slab ring: weights, mbarriers, item contexts, the staging warp's
-// table cache (4 tables) and order-list cache (4 lists).
+// table cache (4 tables) and the column table of the current pack.
 static size_t ws_fixed_smem(const Plan& P, uint32_t NO, uint32_t NPT, uint32_t max_stride) {
-    const size_t list_cap = (P.host.max_list_n + 15u) & ~(size_t)15;
-    return (256 + 2 * K2_WS_NBUF) * sizeof(double) + K2_WS_NCTX * sizeof(WsCtx) + 4 * (size_t)(3 * NO * NPT) * sizeof(double) + (size_t)K2_PACK_MAX * 4 * list_cap +
+    (void)P;
+    return (256 + 2 * K2_WS_NBUF) * sizeof(double) + K2_WS_NCTX * sizeof(WsCtx) + 4 * (size_t)(3 * NO * ws_tab_stride(NPT)) * sizeof(double) +
            (size_t)((max_stride + 3u) & ~3u) * sizeof(uint32_t);
 }
 
@@ -936,7 +1043,6 @@ static size_t ws_fixed_smem(const Plan& P, uint32_t NO, uint32_t NPT, uint32_t m
 static cudaError_t launch_k2_ws(const Plan& P, const WorkItem* d_items, const PackDesc* d_packs, uint32_t count, uint32_t max_stride, uint32_t nu, uint32_t nv,
                                 uint32_t NO, uint32_t NPT, int follows_sampler, cudaStream_t st) {
     if (count == 0) return cudaSuccess;
-    const uint32_t list_cap = (P.host.max_list_n + 15u) & ~15u;
     const size_t fixed = ws_fixed_smem(P, NO, NPT, max_stride);
     const size_t per_row = (size_t)max_stride * 2 * sizeof(double) * nv;     // chunks are whole quadrature rows
     const size_t hard = (size_t)P.max_smem_optin - 1024;
@@ -954,7 +1060,9 @@ static cudaError_t launch_k2_ws(const Plan& P, const WorkItem* d_items, const Pa
             done[P.device] = true;
         }
     }
-    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, buf_doubles, follows_sampler, list_cap, (max_stride + 3u) & ~3u};
+    static const int by_subpartition = [] { const char* ev = std::getenv("FEM2D_K2_WS_ROLES"); return ev ? std::atoi(ev) : 1; }();   // tuning: 0 = staging warps by warp index
+    K2Args g{P.d_classes, P.d_lists, P.d_spec_i, P.d_spec_j, d_items, P.d_tabs, P.d_glq, P.d_V, NO, NPT, nu, nv, buf_doubles, follows_sampler, (max_stride + 3u) & ~3u,
+             P.d_class_geom, by_subpartition};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(std::min<uint32_t>(count, (uint32_t)(K2_MIN_CTAS * std::max(P.sm_count, 1)))); cfg.blockDim = dim3(K2_WS_THREADS);
     cfg.dynamicSmemBytes = smem; cfg.stream = st;

@@ -52,10 +52,11 @@ constexpr int K2_WS_THREADS = K2_WS_WARPS * 32;
 constexpr int K2_WS_MAXREG = (65536 / (FEM2D_K2_CTAS * K2_WS_THREADS)) / 8 * 8 > 128 ? 128 : (65536 / (FEM2D_K2_CTAS * K2_WS_THREADS)) / 8 * 8;   // registers per thread that keep K2_MIN_CTAS CTAs on an SM
 constexpr int K2_WS_NBUF = FEM2D_K2_WS_NBUF;       // slab ring depth
 constexpr int K2_WS_SMEM_KB = FEM2D_K2_WS_SMEM_KB;
-// One staging warp keeps up while a pack's micro-tiles outnumber the slab columns staged for them (uniform-order meshes: 0.49 columns
-// per tile at BASELINE configs[2]); hp-meshes stage about 0.9 columns per tile and get two (measured: 9.1 -> 8.5 ms at 1.38 M DoFs,
-// while configs[2] without dedupe goes 2.08 -> 2.20 ms with two).
-constexpr double K2_WS_TWO_STAGERS_ABOVE = 0.7;    // staged columns per micro-tile
+// Staging warps per CTA.  With the roles dealt by SM sub-partition (k2_ws_kernel) two staging warps leave 3 contraction warps + 1 staging
+// warp on every sub-partition of an SM, one leaves 4 / 4 / 3 / 3 contraction warps with the fullest sub-partitions pacing every chunk:
+// two measured faster on every workload (configs[2] without dedupe 2.14 -> 2.01 ms, cfg4 0.40 -> 0.37 ms, hp1m 8.49 -> 8.23 ms), so the
+// threshold (slab columns staged per micro-tile above which a plan gets two) is 0; FEM2D_K2_WS_PROD=1 selects one for tuning.
+constexpr double K2_WS_TWO_STAGERS_ABOVE = 0.0;    // staged columns per micro-tile
 constexpr int K2_TILE_P = FEM2D_TILE_P;
 constexpr int K2_THREADS = FEM2D_K2_THREADS;
 constexpr int K2_MIN_CTAS = FEM2D_K2_CTAS;     // CTAs per SM the integrator is compiled for
@@ -86,6 +87,13 @@ struct ClassDesc {
     uint32_t n_mt;               // micro-tiles in this class
     uint32_t gramU, gramV;       // ids of the (tabPu,tabQu) / (tabPv,tabQv) 1-D Gram sets (re-ordered modes only)
     ListDesc lp, lq;             // copies of lists[listP], lists[listQ]: one dependent load less in the integrator's prologue
+};
+
+// Per-class constants of the exact integrator (Jacobian inverse entries, uv / vu ratios, max(det), 1/mu, eps * glq scales): plan-constant,
+// computed once per plan on the device (class_geom_kernel, same expressions as the integrator's prologue) and read by the persistent
+// integrator's pack set-up instead of nine FP64 divisions per work item.
+struct ClassGeom {
+    double jiuP, jivP, jiuQ, jivQ, ratio_uv, ratio_vu, maxdet, coefA, coefB;
 };
 
 struct TableDesc {

@@ -1,0 +1,12 @@
+# Tuning: per-phase timings with one / two staging warps (scripts/gpu.sh 900 'bash scripts/roles_probe.sh [workloads]')
+W=${1:-cfg3,cfg4,hp1m}
+for prod in 1 2; do
+echo "== prod=$prod"
+FEM2D_K2_WS_PROD=$prod python scripts/perf_probe.py $W exact 2>&1 | grep -E "workload|ERR|Error" | python -c "
+import sys,json
+for l in sys.stdin:
+    try:
+        d=json.loads(l); print(d['workload'], d['dedupe'], d['items'], d['integrator_ms'], d['scatter_ms'], d['total_ms'])
+    except Exception: print(l.strip())"
+done
+python -m pytest tests/test_fuzz_gpu.py tests/test_golden.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
