@@ -759,10 +759,10 @@ int fem2d_debug_multi_timing(double* out, uint32_t n) {
 }
 
 /* tuning builds only (-DFEM2D_WS_PROFILE; zeros otherwise): cycle counters of the warp-specialised integrator; not part of include/fem2d.h */
-int fem2d_debug_ws_profile(uint64_t out[8], int reset) {
-    unsigned long long t[8];
+int fem2d_debug_ws_profile(uint64_t out[16], int reset) {
+    unsigned long long t[16];
     CKS(fem2d::ws_profile(t, reset));
-    for (int k = 0; k < 8; k++) out[k] = t[k];
+    for (int k = 0; k < 16; k++) out[k] = t[k];
     return FEM2D_OK;
 }
 

@@ -141,7 +141,7 @@ cudaError_t launch_k2_exact(const Plan& plan, const WorkItem* d_items, uint32_t 
 // slab row (pad4(U) + pad4(V) functions of P, + of Q unless local) among the classes of each part.
 ItemSplit split_items(const HostPlan& host, const std::vector<WorkItem>& items, const std::vector<PackDesc>& packs);
 cudaError_t fp64_peak(int kind, double* gflops);
-cudaError_t ws_profile(unsigned long long out[8], int reset);   // tuning builds (-DFEM2D_WS_PROFILE): cycle counters of k2_ws_kernel
+cudaError_t ws_profile(unsigned long long out[16], int reset);   // tuning builds (-DFEM2D_WS_PROFILE): cycle counters of k2_ws_kernel
 
 // kernels_fast.cu
 cudaError_t launch_k2_sumfact(Plan& plan, uint32_t nu, uint32_t nv, uint32_t NO, uint32_t NPT, cudaStream_t st, uint32_t* launches);

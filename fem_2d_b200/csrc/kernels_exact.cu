@@ -381,9 +381,12 @@ struct alignas(16) WsSeg {
 };
 struct alignas(16) WsCtx {
     WsSeg seg[K2_PACK_MAX];
-    uint32_t n_seg, chunk_rows, n_slots, gap, n_same, end, pad0, pad1;   // n_same: same-direction tiles of all segments (they come first)
+    uint32_t n_seg, chunk_rows, n_slots, gap, n_same, end;   // n_same: same-direction tiles of all segments (they come first)
+    uint32_t n_cols, tab_u, tab_v, pad0, pad1, pad2;         // staging: entries of the pack's column table, scaled P-side tables (0xffffffff: none)
 };
-constexpr int K2_WS_NCTX = K2_WS_NBUF + 2;   // pack contexts in flight: the staging warp runs at most NBUF chunks (>= packs) ahead
+// pack contexts in flight: the staging warps run at most NBUF chunks (>= packs) ahead of a contraction warp that may still be in the
+// epilogue of the pack before those, and prepare one more pack in their slack time
+constexpr int K2_WS_NCTX = K2_WS_NBUF + 3;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -457,6 +460,21 @@ __device__ __forceinline__ void ws_stage_column(const double* __restrict__ colA,
     }
 }
 
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking probe of a phase
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// One staging task: a slab column (one function of one segment and side) with its table rows and constants.
 struct WsTask {
     const double* colA; const double* colB; const double* rowA; const double* rowB;   // n-axis / m-axis factors of curl and value
     double jj, ps;
@@ -576,8 +594,9 @@ __device__ __forceinline__ void ws_row_pass(const double* __restrict__ p, const 
 
 #ifdef FEM2D_WS_PROFILE
 // tuning build only: cycle counts summed over CTAs. 0 staging warp: item setup, 1 waiting for an empty buffer, 2 staging;
-// 3 contraction warp 0: waiting for a full buffer, 4 contracting (+ epilogue, decode); 5 items; 6 chunks
-__device__ unsigned long long g_ws_prof[8];
+// 3 contraction warp 0: waiting for a full buffer, 4 contracting (+ epilogue, decode); 5 items; 6 chunks; 7 first chunk of a pack;
+// 8-12 pack set-up: claim + syncs, descriptors -> context, offsets + table cache, column table, (i, j) orders
+__device__ unsigned long long g_ws_prof[16];
 #define WS_T(var) const long long var = clock64()
 #define WS_ADD(k, v) do { if (lane == 0) atomicAdd(&g_ws_prof[k], (unsigned long long)(v)); } while (0)
 #else
@@ -605,6 +624,108 @@ __global__ void class_geom_kernel(const ClassDesc* __restrict__ classes, uint32_
     out[c] = o;
 }
 
+// Pack set-up by the first staging warp, in two steps of about one staged chunk's time each: (1) work items, classes and per-class
+// constants -> context `c` (one lane per segment), thread-slot and slab offsets; (2) the column table with the (i, j) orders of every
+// staged function.  Functions of their own: each runs once per pack from two places -- ahead of time, when the staging warps would
+// otherwise wait for a free ring buffer, or at the start of the pack.
+template <int TP>
+__device__ __noinline__ void ws_setup_context(const PackDesc* __restrict__ packs, uint32_t n_packs, uint32_t idx, const WorkItem* __restrict__ items,
+                                           const ClassDesc* __restrict__ classes, const ClassGeom* __restrict__ geom,
+                                           WsCtx* cp, uint32_t nu, uint32_t nv, uint32_t buf_doubles, uint32_t lane) {
+    WsCtx& c = *cp;
+    if (idx >= n_packs) {   // end marker: travels through the ring like a chunk
+        if (lane == 0) c.end = 1u;
+        __syncwarp();
+        return;
+    }
+    WS_T(t_s0);
+    const PackDesc pk = packs[idx];
+    // ---- one lane per segment: work item, class, per-class constants (ClassGeom) -> context
+    if (lane < pk.n) {
+        WsSeg& sg = c.seg[lane];
+        const WorkItem it = items[pk.first + lane];
+        const ClassDesc cd = classes[it.cls];
+        const ClassGeom cg = geom[it.cls];
+        const uint32_t nP = cd.lp.n, nUP = cd.lp.nU, nQ = cd.lq.n, nUQ = cd.lq.nU;
+        sg.it = it;
+        sg.sb = make_subblocks(nP, nUP, nQ, nUQ, cd.local, TP);
+        sg.jiuP = cg.jiuP; sg.jivP = cg.jivP; sg.jiuQ = cg.jiuQ; sg.jivQ = cg.jivQ;
+        sg.ratio_uv = cg.ratio_uv; sg.ratio_vu = cg.ratio_vu; sg.maxdet = cg.maxdet; sg.coefA = cg.coefA; sg.coefB = cg.coefB;
+        sg.su = cd.su; sg.sv = cd.sv;
+        sg.v_off = cd.v_off;
+        sg.nP = nP; sg.nUP = nUP; sg.nQ = nQ; sg.nUQ = nUQ; sg.local = cd.local;
+        sg.strideP = pad4(nUP) + pad4(nP - nUP);
+        sg.strideQ = cd.local ? sg.strideP : pad4(nUQ) + pad4(nQ - nUQ);
+        sg.listP_off = cd.lp.off; sg.listQ_off = cd.lq.off; sg.tabPu = cd.tabPu; sg.tabPv = cd.tabPv;
+    }
+    __syncwarp();
+    WS_T(t_s1); WS_ADD(9, t_s1 - t_s0);
+    // ---- slot / slab offsets of the segments, chunk size
+    uint32_t tot_stride = 0, n_same = 0, n_cross = 0, tab_u = 0xffffffffu, tab_v = 0xffffffffu;
+    for (uint32_t s2 = 0; s2 < pk.n; s2++) {
+        WsSeg& sg = c.seg[s2];
+        if (lane == 0) { sg.slab_off = 2 * tot_stride; sg.same_off = n_same; sg.cross_off = n_cross; }
+        tot_stride += sg.strideP + (sg.local ? 0u : sg.strideQ);
+        n_same += sg.it.n_same; n_cross += sg.it.mt_count - sg.it.n_same;
+        if (!sg.local) { tab_u = sg.tabPu; tab_v = sg.tabPv; }   // the planner packs non-local segments of one table pair only
+    }
+    // whole quadrature rows per chunk (the launch makes sure one row of the widest pack fits a ring buffer)
+    const uint32_t chunk_rows = min(nu, buf_doubles / (2 * nv * tot_stride));
+    const uint32_t gap = item_gap(n_same, n_same + n_cross), n_slots = n_same + n_cross + gap;
+    if (lane == 0) { c.n_seg = pk.n; c.chunk_rows = chunk_rows; c.n_slots = n_slots; c.gap = gap; c.n_same = n_same; c.end = 0u; c.tab_u = tab_u; c.tab_v = tab_v; }
+    WS_T(t_s2); WS_ADD(10, t_s2 - t_s1);
+    __syncwarp();
+}
+
+__device__ __noinline__ void ws_setup_columns(const uint8_t* __restrict__ spec_i, const uint8_t* __restrict__ spec_j, WsCtx* cp, uint32_t* s_cols, uint32_t lane) {
+    WsCtx& c = *cp;
+    if (c.end) return;
+    const uint32_t n_seg = c.n_seg;
+    WS_T(t_s2);
+    // ---- column table: every slab column the pack's tiles touch, as column | side << 16 | segment << 17 | i << 20 | j << 25
+    uint32_t n_cols = 0;
+    for (uint32_t s2 = 0; s2 < n_seg; s2++) {
+        const WsSeg& sg = c.seg[s2];
+        for (uint32_t side = 0; side < (sg.local ? 1u : 2u); side++)
+            for (uint32_t grp = 0; grp < 2; grp++) {
+                const uint32_t c_lo = sg.it.stage[side][grp][0], c_w = sg.it.stage[side][grp][1] - c_lo;   // only the functions this item's tiles touch
+                for (uint32_t k = lane; k < c_w; k += 32) s_cols[n_cols + k] = s2 << 17 | side << 16 | (c_lo + k);
+                n_cols += c_w;
+            }
+    }
+    __syncwarp();
+    WS_T(t_s3); WS_ADD(11, t_s3 - t_s2);
+    // (i, j) orders of the columns' functions, straight from the plan's pooled BasisSpec lists: 8 columns per lane and batch, so
+    // that all global loads of a batch are in flight together (one L2 round trip per 256 columns)
+    for (uint32_t t0 = 0; t0 < n_cols; t0 += 8 * 32) {
+        uint32_t e[8], vi[8], vj[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t t = t0 + u * 32 + lane;
+            e[u] = 0; vi[u] = 0; vj[u] = 0;
+            if (t < n_cols) {
+                e[u] = s_cols[t];
+                const WsSeg& sg = c.seg[(e[u] >> 17) & 3u];
+                const uint32_t side = (e[u] >> 16) & 1u, col = e[u] & 0xffffu;
+                const uint32_t nF = side ? sg.nQ : sg.nP, nUF = side ? sg.nUQ : sg.nUP, padU = pad4(nUF);
+                // a padding column of a 4-wide tile row takes the values of the group's last function: only pairs beyond the block's
+                // last row / column read it, and their results are never stored
+                const uint32_t a = col < padU ? min(col, nUF - 1) : nUF + min(col - padU, nF - nUF - 1);
+                const uint32_t off = (side ? sg.listQ_off : sg.listP_off) + a;
+                vi[u] = spec_i[off]; vj[u] = spec_j[off];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const uint32_t t = t0 + u * 32 + lane;
+            if (t < n_cols) s_cols[t] = e[u] | vi[u] << 20 | vj[u] << 25;
+        }
+    }
+    WS_T(t_s4); WS_ADD(12, t_s4 - t_s3);
+    if (lane == 0) c.n_cols = n_cols;
+    __syncwarp();
+}
+
 constexpr uint32_t K2_WS_SM_SLOTS = 1024;
 __device__ uint32_t g_ws_sm_arrivals[K2_WS_SM_SLOTS];   // CTAs of the persistent integrator that have started on each SM, ever (only the parity is used)
 
@@ -624,7 +745,7 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
     const uint32_t AS3 = 3 * g.NO * ws_tab_stride(g.NPT);
     double* s_tab = smem + 256 + 2 * K2_WS_NBUF + K2_WS_NCTX * sizeof(WsCtx) / sizeof(double);
     uint32_t* s_cols = reinterpret_cast<uint32_t*>(s_tab + 4 * (size_t)AS3);   // column table of the current pack
-    double* s_slab = reinterpret_cast<double*>(s_cols + g.col_cap);
+    double* s_slab = reinterpret_cast<double*>(s_cols + 2 * g.col_cap);   // two column tables: the current pack's and the next one's
     const uint32_t buf_doubles = g.slab_doubles;   // per ring buffer
     const uint32_t lane = threadIdx.x % 32;
     const uint32_t nu = g.nu, nv = g.nv;
@@ -685,122 +806,64 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
         // the staging warps meet at a named barrier after the set-up and before the next set-up overwrites the caches.
         const uint32_t plane = warp * 32 + lane;   // lane index across the staging warps
         auto prod_sync = [] { if (K2_WS_PROD_WARPS > 1) asm volatile("bar.sync 1, %0;" ::"r"(K2_WS_PROD_WARPS * 32) : "memory"); else __syncwarp(); };
-        __shared__ uint32_t s_pack_idx, s_n_cols;
         if (warp == 0) { ws_cache_table(g, 0u, s_tab + 2 * (size_t)AS3, lane); ws_cache_table(g, 1u, s_tab + 3 * (size_t)AS3, lane); }   // tables 0 / 1: unscaled u / v points
         uint32_t cached_u = 0xffffffffu, cached_v = 0xffffffffu;                                 // table ids held by slots 0 / 1
-        // packs are claimed one ahead: the atomic's round trip runs behind the staging of the current pack
-        uint32_t next_idx = 0;
-        if (plane == 0) next_idx = atomicAdd(work_counter, 1u);
+        // Packs are claimed one ahead (the atomic's round trip runs behind the staging of the current pack), and the claimed pack is set
+        // up ahead of time when the staging warps find their next ring buffer still in use: its context and column table go to the next
+        // slots of their rings, so the contraction warps rarely wait for the first chunk of a pack.
+        uint32_t cur_idx = 0, next_idx = 0, cb = 0;   // cb: column-table buffer of the current pack
+        uint32_t cur_ready = 0, next_ready = 0;   // set-up steps done: 0 none, 1 context, 2 context + column table
+        if (warp == 0) { if (lane == 0) cur_idx = atomicAdd(work_counter, 1u); cur_idx = __shfl_sync(0xffffffffu, cur_idx, 0); }
         for (;;) {
             WS_T(t_item0);
-            prod_sync();   // every staging warp is done with the previous pack's caches and context
-            if (plane == 0) { s_pack_idx = next_idx; if (next_idx < n_packs) next_idx = atomicAdd(work_counter, 1u); }
-            prod_sync();
-            const uint32_t idx = s_pack_idx;
+            prod_sync();   // every staging warp is done with the previous pack's column table and table cache
             WsCtx& c = s_ctx[ci];
-            if (idx >= n_packs) {   // end marker: travels through the ring like a chunk
-                if (plane == 0) c.end = 1u;
+            const uint32_t* cols = s_cols + cb * g.col_cap;
+            if (warp == 0) {
+                if (cur_ready < 1u) ws_setup_context<TP>(packs, n_packs, cur_idx, g.items, g.classes, g.geom, &c, nu, nv, buf_doubles, lane);
+                if (cur_ready < 2u) ws_setup_columns(g.spec_i, g.spec_j, &c, s_cols + cb * g.col_cap, lane);
+                if (!c.end) {
+                    if (lane == 0) next_idx = atomicAdd(work_counter, 1u);   // consumed when the next pack is set up
+                    // the scaled P-side tables (the ancestor sampled over the descendant, basis.rs:372-393)
+                    const uint32_t tab_u = c.tab_u, tab_v = c.tab_v;
+                    if (tab_u != 0xffffffffu && cached_u != tab_u) { ws_cache_table(g, tab_u, s_tab, lane); cached_u = tab_u; }
+                    if (tab_v != 0xffffffffu && cached_v != tab_v) { ws_cache_table(g, tab_v, s_tab + AS3, lane); cached_v = tab_v; }
+                }
+                next_ready = 0;
+            }
+            prod_sync();
+            if (c.end) {
                 mbar_wait(&s_empty[stage], phase ^ 1u);
-                prod_sync();
                 mbar_arrive(&s_full[stage]);
                 break;
             }
-            const PackDesc pk = packs[idx];
-            if (warp == 0) {
-            // ---- one lane per segment: work item, class, per-class constants (ClassGeom) -> context
-            if (lane < pk.n) {
-                WsSeg& sg = c.seg[lane];
-                const WorkItem it = g.items[pk.first + lane];
-                const ClassDesc cd = g.classes[it.cls];
-                const ClassGeom cg = g.geom[it.cls];
-                const uint32_t nP = cd.lp.n, nUP = cd.lp.nU, nQ = cd.lq.n, nUQ = cd.lq.nU;
-                sg.it = it;
-                sg.sb = make_subblocks(nP, nUP, nQ, nUQ, cd.local, TP);
-                sg.jiuP = cg.jiuP; sg.jivP = cg.jivP; sg.jiuQ = cg.jiuQ; sg.jivQ = cg.jivQ;
-                sg.ratio_uv = cg.ratio_uv; sg.ratio_vu = cg.ratio_vu; sg.maxdet = cg.maxdet; sg.coefA = cg.coefA; sg.coefB = cg.coefB;
-                sg.su = cd.su; sg.sv = cd.sv;
-                sg.v_off = cd.v_off;
-                sg.nP = nP; sg.nUP = nUP; sg.nQ = nQ; sg.nUQ = nUQ; sg.local = cd.local;
-                sg.strideP = pad4(nUP) + pad4(nP - nUP);
-                sg.strideQ = cd.local ? sg.strideP : pad4(nUQ) + pad4(nQ - nUQ);
-                sg.listP_off = cd.lp.off; sg.listQ_off = cd.lq.off; sg.tabPu = cd.tabPu; sg.tabPv = cd.tabPv;
-            }
-            __syncwarp();
-            // ---- slot / slab offsets of the segments, chunk size
-            uint32_t tot_stride = 0, n_same = 0, n_cross = 0, tab_u = 0xffffffffu, tab_v = 0xffffffffu;
-            for (uint32_t s2 = 0; s2 < pk.n; s2++) {
-                WsSeg& sg = c.seg[s2];
-                if (lane == 0) { sg.slab_off = 2 * tot_stride; sg.same_off = n_same; sg.cross_off = n_cross; }
-                tot_stride += sg.strideP + (sg.local ? 0u : sg.strideQ);
-                n_same += sg.it.n_same; n_cross += sg.it.mt_count - sg.it.n_same;
-                if (!sg.local) { tab_u = sg.tabPu; tab_v = sg.tabPv; }   // the planner packs non-local segments of one table pair only
-            }
-            // whole quadrature rows per chunk (the launch makes sure one row of the widest pack fits a ring buffer)
-            const uint32_t chunk_rows = min(nu, buf_doubles / (2 * nv * tot_stride));
-            const uint32_t gap = item_gap(n_same, n_same + n_cross), n_slots = n_same + n_cross + gap;
-            if (lane == 0) { c.n_seg = pk.n; c.chunk_rows = chunk_rows; c.n_slots = n_slots; c.gap = gap; c.n_same = n_same; c.end = 0u; }
-            // ---- caches: the scaled P-side tables (the ancestor sampled over the descendant, basis.rs:372-393)
-            if (tab_u != 0xffffffffu && cached_u != tab_u) { ws_cache_table(g, tab_u, s_tab, lane); cached_u = tab_u; }
-            if (tab_v != 0xffffffffu && cached_v != tab_v) { ws_cache_table(g, tab_v, s_tab + AS3, lane); cached_v = tab_v; }
-            // ---- column table: every slab column the pack's tiles touch, as column | side << 16 | segment << 17 | i << 20 | j << 25
-            uint32_t n_cols = 0;
-            for (uint32_t s2 = 0; s2 < pk.n; s2++) {
-                const WsSeg& sg = c.seg[s2];
-                for (uint32_t side = 0; side < (sg.local ? 1u : 2u); side++)
-                    for (uint32_t grp = 0; grp < 2; grp++) {
-                        const uint32_t c_lo = sg.it.stage[side][grp][0], c_w = sg.it.stage[side][grp][1] - c_lo;   // only the functions this item's tiles touch
-                        for (uint32_t k = lane; k < c_w; k += 32) s_cols[n_cols + k] = s2 << 17 | side << 16 | (c_lo + k);
-                        n_cols += c_w;
-                    }
-            }
-            __syncwarp();
-            // (i, j) orders of the columns' functions, straight from the plan's pooled BasisSpec lists: 8 columns per lane and batch, so
-            // that all global loads of a batch are in flight together (one L2 round trip per 256 columns)
-            for (uint32_t t0 = 0; t0 < n_cols; t0 += 8 * 32) {
-                uint32_t e[8], vi[8], vj[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const uint32_t t = t0 + u * 32 + lane;
-                    e[u] = 0; vi[u] = 0; vj[u] = 0;
-                    if (t < n_cols) {
-                        e[u] = s_cols[t];
-                        const WsSeg& sg = c.seg[(e[u] >> 17) & 3u];
-                        const uint32_t side = (e[u] >> 16) & 1u, col = e[u] & 0xffffu;
-                        const uint32_t nF = side ? sg.nQ : sg.nP, nUF = side ? sg.nUQ : sg.nUP, padU = pad4(nUF);
-                        // a padding column of a 4-wide tile row takes the values of the group's last function: only pairs beyond the block's
-                        // last row / column read it, and their results are never stored
-                        const uint32_t a = col < padU ? min(col, nUF - 1) : nUF + min(col - padU, nF - nUF - 1);
-                        const uint32_t off = (side ? sg.listQ_off : sg.listP_off) + a;
-                        vi[u] = g.spec_i[off]; vj[u] = g.spec_j[off];
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const uint32_t t = t0 + u * 32 + lane;
-                    if (t < n_cols) s_cols[t] = e[u] | vi[u] << 20 | vj[u] << 25;
-                }
-            }
-            if (lane == 0) s_n_cols = n_cols;
-            }   // warp == 0
-            prod_sync();
-            const uint32_t n_cols = s_n_cols, chunk_rows = c.chunk_rows, n_slots = c.n_slots;
+            const uint32_t n_cols = c.n_cols, chunk_rows = c.chunk_rows, n_slots = c.n_slots;
             WS_T(t_item1); if (warp == 0) { WS_ADD(0, t_item1 - t_item0); WS_ADD(5, 1); }
             const uint32_t chunk = chunk_rows * nv;
             for (uint32_t round0 = 0; round0 < n_slots; round0 += K2_WS_TPT * CONS) {
                 for (uint32_t m0 = 0; m0 < nu; m0 += chunk_rows) {
                     const uint32_t nrow = min(chunk_rows, nu - m0);
                     WS_T(t_w0);
+                    if (warp == 0 && next_ready < 2u && !__any_sync(0xffffffffu, mbar_test(&s_empty[stage], phase ^ 1u))) {
+                        // slack: the ring buffer is still being read -> one step of the set-up of the pack claimed at the start of this one
+                        WsCtx* cn = &s_ctx[ci + 1 == K2_WS_NCTX ? 0 : ci + 1];
+                        if (next_ready == 0) ws_setup_context<TP>(packs, n_packs, __shfl_sync(0xffffffffu, next_idx, 0), g.items, g.classes, g.geom, cn, nu, nv, buf_doubles, lane);
+                        else ws_setup_columns(g.spec_i, g.spec_j, cn, s_cols + (cb ^ 1u) * g.col_cap, lane);
+                        next_ready++;
+                        WS_ADD(13, 1);
+                    }
                     mbar_wait(&s_empty[stage], phase ^ 1u);     // the contraction warps are done with what this buffer held
                     WS_T(t_w1);
                     double* buf = s_slab + (size_t)stage * buf_doubles;
-                    ws_stage_chunk<PROD>(g, c, s_cols, n_cols, s_tab, buf, chunk, m0, nrow, plane);
+                    ws_stage_chunk<PROD>(g, c, cols, n_cols, s_tab, buf, chunk, m0, nrow, plane);
                     __syncwarp();
                     WS_T(t_w2); if (warp == 0) { WS_ADD(1, t_w1 - t_w0); WS_ADD(2, t_w2 - t_w1); WS_ADD(6, 1); }
                     mbar_arrive(&s_full[stage]);   // every staging lane releases its own slab stores (the staging warps have slack for the 32 arrivals)
                     stage = stage + 1 == K2_WS_NBUF ? 0u : stage + 1; phase ^= (stage == 0u);
                 }
             }
-            ci = ci + 1 == K2_WS_NCTX ? 0u : ci + 1;
+            if (warp == 0) { cur_idx = __shfl_sync(0xffffffffu, next_idx, 0); cur_ready = next_ready; }
+            ci = ci + 1 == K2_WS_NCTX ? 0u : ci + 1; cb ^= 1u;
         }
     } else {
         // ============================================================================================ contraction warps
@@ -1036,7 +1099,7 @@ static cudaError_t launch_k2_part(const Plan& P, const WorkItem* d_items, uint32
 static size_t ws_fixed_smem(const Plan& P, uint32_t NO, uint32_t NPT, uint32_t max_stride) {
     (void)P;
     return (256 + 2 * K2_WS_NBUF) * sizeof(double) + K2_WS_NCTX * sizeof(WsCtx) + 4 * (size_t)(3 * NO * ws_tab_stride(NPT)) * sizeof(double) +
-           (size_t)((max_stride + 3u) & ~3u) * sizeof(uint32_t);
+           2 * (size_t)((max_stride + 3u) & ~3u) * sizeof(uint32_t);
 }
 
 // Persistent, warp-specialised launch over the packs [0, count) of an item list: two CTAs per SM, each with a ring of K2_WS_NBUF slab buffers.
@@ -1112,13 +1175,13 @@ cudaError_t launch_k2_exact(const Plan& P, const WorkItem* d_items, uint32_t n_i
     return e;
 }
 
-cudaError_t ws_profile(unsigned long long out[8], int reset) {
+cudaError_t ws_profile(unsigned long long out[16], int reset) {
 #ifdef FEM2D_WS_PROFILE
-    cudaError_t e = cudaMemcpyFromSymbol(out, g_ws_prof, 8 * sizeof(unsigned long long));
-    if (e == cudaSuccess && reset) { unsigned long long z[8] = {}; e = cudaMemcpyToSymbol(g_ws_prof, z, sizeof(z)); }
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_ws_prof, 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess && reset) { unsigned long long z[16] = {}; e = cudaMemcpyToSymbol(g_ws_prof, z, sizeof(z)); }
     return e;
 #else
-    for (int k = 0; k < 8; k++) out[k] = 0;
+    for (int k = 0; k < 16; k++) out[k] = 0;
     (void)reset;
     return cudaSuccess;
 #endif

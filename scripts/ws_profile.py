@@ -14,13 +14,14 @@ a = torch.empty(plan.nnz, dtype=torch.float64, device="cuda"); b = torch.empty_l
 for _ in range(2):
     plan.assemble_device(glq, a.data_ptr(), b.data_ptr())
 torch.cuda.synchronize()
-out = (C.c_uint64 * 8)()
+out = (C.c_uint64 * 16)()
 F._L.fem2d_debug_ws_profile(out, 1)
 plan.assemble_device(glq, a.data_ptr(), b.data_ptr())
 torch.cuda.synchronize()
 F._L.fem2d_debug_ws_profile(out, 1)
 t = plan.last_timing()
-names = ["prod_setup", "prod_wait_empty", "prod_stage", "cons_wait_full", "cons_contract", "items", "chunks", "cons_wait_first"]
+names = ["prod_setup", "prod_wait_empty", "prod_stage", "cons_wait_full", "cons_contract", "items", "chunks", "cons_wait_first",
+         "setup_claim", "setup_desc", "setup_offsets_tables", "setup_cols", "setup_orders", "-", "-", "-"]
 vals = [int(x) for x in out]
 ctas = 296
 print(wl, dedupe, "integrator_ms", round(t["integrator_ms"], 4), "kernel cycles", int(t["integrator_ms"] * 1.965e6), "cycles per CTA:", {n: vals[k] // ctas for k, n in enumerate(names)})
