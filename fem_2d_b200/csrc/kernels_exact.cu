@@ -553,7 +553,11 @@ __device__ __forceinline__ void ws_cache_table(const K2Args& g, uint32_t id, dou
 // slabs with max(det) for B), a cross-direction tile twice on the curl slabs (columns 0-1, columns 2-3; no ratio factor,
 // integrals.rs:53-84).  Running the passes one after the other keeps a single set of inner accumulators live, which leaves the
 // scheduler the registers to interleave all eight chains of a pass and to fetch the next points' operands early.
-template <bool SCALE, int TP>
+// MODE 2 multiplies the WEIGHT by `scale` instead of every product: bit-identical when `scale` is a power of two, because then
+// both x * scale and scale * w are exact and ((x * scale) * w) = fl(x * scale * w) = (x * (scale * w)) (no overflow / underflow: the
+// exponent of scale is within +-64, plan_types.h is_pow2_scale) -- one DMUL per point instead of eight.  Ratios of dyadically refined Elems are powers
+// of two on every mesh, max(det) is one when the base Elements' sides are (the reference's test meshes a and b; not c: 4.2 x 4.2).
+template <int MODE, int TP>   // 0: no scale (cross-direction), 1: scale every product, 2: scale the weight (power-of-two scale)
 __device__ __forceinline__ void ws_row_pass(const double* __restrict__ p, const double* __restrict__ q, uint32_t strideP, uint32_t strideQ,
                                             const double* __restrict__ vw, uint32_t nv, double scale, double uw, double (&sol)[TP][MT_Q]) {
     double in[TP][MT_Q];
@@ -565,12 +569,12 @@ __device__ __forceinline__ void ws_row_pass(const double* __restrict__ p, const 
     for (uint32_t n = 0; n < nv; n++) {
         double pv[TP], qv[MT_Q], t[TP][MT_Q];
         load_rows<TP>(p, pv); load_rows<MT_Q>(q, qv);
-        const double w = vw[n];
+        const double w = MODE == 2 ? vw[n] * scale : vw[n];
 #pragma unroll
         for (int r = 0; r < TP; r++)
 #pragma unroll
             for (int c = 0; c < MT_Q; c++) t[r][c] = pv[r] * qv[c];
-        if (SCALE) {
+        if (MODE == 1) {
 #pragma unroll
             for (int r = 0; r < TP; r++)
 #pragma unroll
@@ -729,7 +733,9 @@ __device__ __noinline__ void ws_setup_columns(const uint8_t* __restrict__ spec_i
 constexpr uint32_t K2_WS_SM_SLOTS = 1024;
 __device__ uint32_t g_ws_sm_arrivals[K2_WS_SM_SLOTS];   // CTAs of the persistent integrator that have started on each SM, ever (only the parity is used)
 
-template <int TP, int PROD>
+// FOLD bit 0: the uv / vu ratios of every class of the plan are powers of two, bit 1: so is every max(det) -- decided per plan on the
+// host (HostPlan::ws_fold); such a scale multiplies the quadrature weight instead of every product (ws_row_pass), bit for bit the same.
+template <int TP, int PROD, int FOLD>
 __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const PackDesc* __restrict__ packs, const uint32_t n_packs, uint32_t* __restrict__ work_counter) {
     extern __shared__ __align__(16) double smem[];
     constexpr int K2_WS_PROD_WARPS = PROD, K2_WS_CONS_WARPS = K2_WS_WARPS - PROD;   // staging / contraction warps of this instantiation
@@ -939,17 +945,18 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
                             const double* cp = s_CP + (rc[0] & 0xffffu); const double* cq = s_CQ + (rc[0] >> 16);
                             const double* fp = s_FP + (rc[0] & 0xffffu); const double* fq = s_FQ + (rc[0] >> 16);
                             const double ratio = sub == 0 ? sg.ratio_uv : sg.ratio_vu, maxdet = sg.maxdet;
+                            // scales that are powers of two in every class of the plan go into the weights (FOLD, ws_row_pass MODE 2)
                             for (uint32_t r = 0; r < nrow; r++) {
                                 const double uw = s_uw[m0 + r];
-                                ws_row_pass<true, TP>(cp, cq, strideP, strideQ, s_vw, nv, ratio, uw, sol[0]);      // A: (curl_p * curl_q) * ratio
-                                ws_row_pass<true, TP>(fp, fq, strideP, strideQ, s_vw, nv, maxdet, uw, sol[1]);     // B: (val_p * val_q) * max(det)
+                                ws_row_pass<(FOLD & 1) ? 2 : 1, TP>(cp, cq, strideP, strideQ, s_vw, nv, ratio, uw, sol[0]);      // A: (curl_p * curl_q) * ratio
+                                ws_row_pass<(FOLD & 2) ? 2 : 1, TP>(fp, fq, strideP, strideQ, s_vw, nv, maxdet, uw, sol[1]);     // B: (val_p * val_q) * max(det)
                                 cp += (size_t)nv * strideP; cq += (size_t)nv * strideQ; fp += (size_t)nv * strideP; fq += (size_t)nv * strideQ;
                             }
                         }
                     } else {
                         // the two halves may belong to different segments of a pack: each carries its own slabs and strides
                         const double* cp[2]; const double* cq[2]; uint32_t sP[2], sQ[2];
-    #pragma unroll
+#pragma unroll
                         for (int h = 0; h < 2; h++) {
                             const WsSeg& sg = c.seg[asg[h] == 0xffffffffu ? 0u : (asg[h] >> 2) & 3u];
                             sP[h] = sg.strideP; sQ[h] = sg.strideQ;
@@ -959,8 +966,8 @@ __global__ void __maxnreg__(K2_WS_MAXREG) k2_ws_kernel(const K2Args g, const Pac
                         }
                         for (uint32_t r = 0; r < nrow; r++) {
                             const double uw = s_uw[m0 + r];
-                            if (asg[0] != 0xffffffffu) ws_row_pass<false, TP>(cp[0], cq[0], sP[0], sQ[0], s_vw, nv, 1.0, uw, sol[0]);
-                            if (asg[1] != 0xffffffffu) ws_row_pass<false, TP>(cp[1], cq[1], sP[1], sQ[1], s_vw, nv, 1.0, uw, sol[1]);
+                            if (asg[0] != 0xffffffffu) ws_row_pass<0, TP>(cp[0], cq[0], sP[0], sQ[0], s_vw, nv, 1.0, uw, sol[0]);
+                            if (asg[1] != 0xffffffffu) ws_row_pass<0, TP>(cp[1], cq[1], sP[1], sQ[1], s_vw, nv, 1.0, uw, sol[1]);
                             cp[0] += (size_t)nv * sP[0]; cq[0] += (size_t)nv * sQ[0]; cp[1] += (size_t)nv * sP[1]; cq[1] += (size_t)nv * sQ[1];
                         }
                     }
@@ -1117,8 +1124,10 @@ static cudaError_t launch_k2_ws(const Plan& P, const WorkItem* d_items, const Pa
         static bool done[64] = {};
         std::lock_guard<std::mutex> lk(mu);
         if (P.device >= 0 && P.device < 64 && !done[P.device]) {
-            cudaError_t e = cudaFuncSetAttribute(k2_ws_kernel<K2_TILE_P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hard);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_ws_kernel<K2_TILE_P, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hard);
+            cudaError_t e = cudaSuccess;
+            auto optin = [&](auto kernel) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hard); };
+            optin(k2_ws_kernel<K2_TILE_P, 1, 0>); optin(k2_ws_kernel<K2_TILE_P, 1, 1>); optin(k2_ws_kernel<K2_TILE_P, 1, 3>);
+            optin(k2_ws_kernel<K2_TILE_P, 2, 0>); optin(k2_ws_kernel<K2_TILE_P, 2, 1>); optin(k2_ws_kernel<K2_TILE_P, 2, 3>);
             if (e != cudaSuccess) return e;
             done[P.device] = true;
         }
@@ -1132,8 +1141,13 @@ static cudaError_t launch_k2_ws(const Plan& P, const WorkItem* d_items, const Pa
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    const cudaError_t e = P.host.ws_prod == 2 ? cudaLaunchKernelEx(&cfg, k2_ws_kernel<K2_TILE_P, 2>, g, d_packs, count, P.d_work_counter)
-                                              : cudaLaunchKernelEx(&cfg, k2_ws_kernel<K2_TILE_P, 1>, g, d_packs, count, P.d_work_counter);
+    // scales folded into the weights: the ratios only (1), ratios and max(det) (3), none (0)
+    const uint32_t fold = (P.host.ws_fold & 3u) == 3u ? 3u : (P.host.ws_fold & 1u);
+    cudaError_t e;
+#define FEM2D_WS_LAUNCH(PRODW, FOLDV) e = cudaLaunchKernelEx(&cfg, k2_ws_kernel<K2_TILE_P, PRODW, FOLDV>, g, d_packs, count, P.d_work_counter)
+    if (P.host.ws_prod == 2) { if (fold == 3u) FEM2D_WS_LAUNCH(2, 3); else if (fold == 1u) FEM2D_WS_LAUNCH(2, 1); else FEM2D_WS_LAUNCH(2, 0); }
+    else { if (fold == 3u) FEM2D_WS_LAUNCH(1, 3); else if (fold == 1u) FEM2D_WS_LAUNCH(1, 1); else FEM2D_WS_LAUNCH(1, 0); }
+#undef FEM2D_WS_LAUNCH
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 

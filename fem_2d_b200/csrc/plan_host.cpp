@@ -480,6 +480,17 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
         }
         P.ws_prod = cols > K2_WS_TWO_STAGERS_ABOVE * tiles ? 2u : 1u;
         if (const char* ev = std::getenv("FEM2D_K2_WS_PROD")) P.ws_prod = std::atoi(ev) == 2 ? 2u : 1u;   // tuning
+        // scales that are powers of two in every class (same expressions as class_geom_kernel / the integrator's prologue; this
+        // translation unit is compiled with FP contraction off, and IEEE division gives the device's quotients)
+        P.ws_fold = 3u;
+        for (const ClassDesc& c : P.classes) {
+            const double detP = c.dxP * c.dyP - 0.0 * 0.0, detQ = c.dxQ * c.dyQ - 0.0 * 0.0;
+            const bool ge = detP >= detQ;
+            const double ratio_uv = ge ? c.dxP / c.dyP : c.dxQ / c.dyQ, ratio_vu = ge ? c.dyP / c.dxP : c.dyQ / c.dxQ, maxdet = detP > detQ ? detP : detQ;
+            if (!is_pow2_scale(ratio_uv) || !is_pow2_scale(ratio_vu)) P.ws_fold &= ~1u;
+            if (!is_pow2_scale(maxdet)) P.ws_fold &= ~2u;
+        }
+        if (const char* ev = std::getenv("FEM2D_K2_WS_FOLD")) P.ws_fold &= (uint32_t)std::atoi(ev);   // tuning: 0 = never fold
     }
     uint32_t cap = K2_ROUNDS * (P.use_ws && P.tile_p == (uint32_t)K2_TILE_P ? P.ws_round_slots() / K2_WS_TPT : (uint32_t)K2_THREADS);
     const uint32_t min_cap = P.tile_p == 1 ? 256u : 64u;   // latency shape: one full round per CTA measured best (128: +10 %, 512: +30 %)

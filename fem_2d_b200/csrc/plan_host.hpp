@@ -30,6 +30,7 @@ struct HostPlan {
     uint32_t max_list_n = 0;
     mutable int64_t first_shared_dof = -1;   // smallest DoF carried by more than one Elem (computed on first use by first_shared())
     uint32_t tile_p = 4;            // micro-tile height chosen for the exact integrator (4: throughput, 1: latency)
+    uint32_t ws_fold = 0;           // bit 0: every class's uv / vu ratios are powers of two, bit 1: every max(det) is (k2_ws_kernel FOLD)
     uint32_t ws_prod = 1;           // staging warps of the persistent integrator (1 or 2), see K2_WS_TWO_STAGERS_ABOVE
     uint32_t ws_round_slots() const { return (uint32_t)((K2_WS_WARPS - (int)ws_prod) * 32 * K2_WS_TPT); }   // micro-tiles one round of contraction threads holds
     bool use_ws = true;             // throughput shape: big items run in the warp-specialised persistent integrator (FEM2D_K2_WS=0: tuning)

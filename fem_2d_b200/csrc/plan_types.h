@@ -11,6 +11,7 @@
 //   slot      position of a key [row<=col] in the sorted unique upper-triangular pattern.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 namespace fem2d {
 
@@ -153,6 +154,19 @@ struct SubBlocks {
 #else
 #define FEM2D_HD
 #endif
+// v = 2^k with |k| <= 64 (v > 0): multiplying by v is exact for every operand the integrator meets, which lets the persistent
+// integrator fold such a scale into the quadrature weights (k2_ws_kernel FOLD)
+FEM2D_HD inline bool is_pow2_scale(double v) {
+    unsigned long long b;
+    static_assert(sizeof(b) == sizeof(v), "IEEE-754 binary64");
+#ifdef __CUDA_ARCH__
+    b = (unsigned long long)__double_as_longlong(v);
+#else
+    memcpy(&b, &v, sizeof(b));
+#endif
+    const unsigned e = (unsigned)(b >> 52);   // sign 0 and the biased exponent
+    return (b & 0x000fffffffffffffull) == 0ull && e >= 1023u - 64u && e <= 1023u + 64u;
+}
 FEM2D_HD inline uint32_t mt_div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 FEM2D_HD inline uint32_t mt_sub_at(uint32_t k) { return k == 0 ? 0u : k == 1 ? 3u : k == 2 ? 1u : 2u; }   // k-th sub-block in numbering order
 FEM2D_HD inline uint32_t mt_width(uint32_t sub) { return (sub == 1 || sub == 2) ? (uint32_t)MT_QX : (uint32_t)MT_Q; }
