@@ -758,6 +758,29 @@ int fem2d_debug_multi_timing(double* out, uint32_t n) {
     return FEM2D_OK;
 }
 
+/* Diagnostic, not in fem2d.h: how full the rounds of the persistent integrator are.  out: micro-tiles, thread slots of all rounds (rounds x
+ * contraction threads), packs, rounds, slab columns staged (per round), rounds whose slots are less than half full. */
+int fem2d_debug_round_fill(const fem2d_plan* plan, uint64_t out[6]) {
+    if (!plan || !out) return fail(FEM2D_ERR_BAD_ARGUMENT, "null argument");
+    using namespace fem2d;
+    const HostPlan& H = plan->p.host;
+    std::memset(out, 0, 6 * sizeof(uint64_t));
+    const uint64_t cons = H.ws_round_slots();
+    for (const PackDesc& pk : H.packs) {
+        uint64_t same = 0, cross = 0, cols = 0;
+        for (uint32_t k = 0; k < pk.n; k++) {
+            const WorkItem& it = H.items[pk.first + k];
+            same += it.n_same; cross += it.mt_count - it.n_same;
+            for (int sd = 0; sd < 2; sd++) for (int g = 0; g < 2; g++) cols += it.stage[sd][g][1] - it.stage[sd][g][0];
+        }
+        const uint64_t slots = same + cross + item_gap((uint32_t)same, (uint32_t)(same + cross));
+        const uint64_t rounds = (slots + cons - 1) / cons;
+        out[0] += same + cross; out[1] += rounds * cons; out[2] += 1; out[3] += rounds; out[4] += cols * rounds;
+        if (2 * (same + cross) < rounds * cons) out[5] += rounds;
+    }
+    return FEM2D_OK;
+}
+
 /* tuning builds only (-DFEM2D_WS_PROFILE; zeros otherwise): cycle counters of the warp-specialised integrator; not part of include/fem2d.h */
 int fem2d_debug_ws_profile(uint64_t out[16], int reset) {
     unsigned long long t[16];
