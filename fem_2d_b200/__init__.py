@@ -611,6 +611,13 @@ class Plan:
         keys = ["same_pairs", "cross_pairs", "same_tiles", "cross_tiles", "pairs_per_same_tile", "pairs_per_cross_tile", "warp_slots", "staging_warps"]
         return {k: int(out[i]) for i, k in enumerate(keys)}
 
+    def round_fill(self) -> dict:
+        """fem2d_debug_round_fill (diagnostic): how full the rounds of the persistent integrator are, and which scales it folds into the weights."""
+        out = (C.c_uint64 * 8)()
+        _ck(_L.fem2d_debug_round_fill(self._h, out))
+        keys = ["tiles", "round_slots", "packs", "rounds", "staged_columns", "rounds_under_half", "fold"]
+        return {k: int(out[i]) for i, k in enumerate(keys)}
+
     def fp64_lane_ops(self, nu: int, nv: int) -> int:
         """FP64 operations (lane-ops, none of them fusable) of the reference's per-pair quadrature for one numeric call: per same-direction pair
         8 per point (A: 3 products + 1 sum, B: the same) + 4 per quadrature row (solution += inner * u_w, twice); per cross-direction pair 3 per

@@ -759,12 +759,14 @@ int fem2d_debug_multi_timing(double* out, uint32_t n) {
 }
 
 /* Diagnostic, not in fem2d.h: how full the rounds of the persistent integrator are.  out: micro-tiles, thread slots of all rounds (rounds x
- * contraction threads), packs, rounds, slab columns staged (per round), rounds whose slots are less than half full. */
-int fem2d_debug_round_fill(const fem2d_plan* plan, uint64_t out[6]) {
+ * contraction threads), packs, rounds, slab columns staged (per round), rounds whose slots are less than half full, HostPlan::ws_fold (scales the
+ * integrator folds into the quadrature weights: bit 0 the uv / vu ratios, bit 1 max(det)), 0. */
+int fem2d_debug_round_fill(const fem2d_plan* plan, uint64_t out[8]) {
     if (!plan || !out) return fail(FEM2D_ERR_BAD_ARGUMENT, "null argument");
     using namespace fem2d;
     const HostPlan& H = plan->p.host;
-    std::memset(out, 0, 6 * sizeof(uint64_t));
+    std::memset(out, 0, 8 * sizeof(uint64_t));
+    out[6] = H.ws_fold;
     const uint64_t cons = H.ws_round_slots();
     for (const PackDesc& pk : H.packs) {
         uint64_t same = 0, cross = 0, cols = 0;
@@ -777,6 +779,14 @@ int fem2d_debug_round_fill(const fem2d_plan* plan, uint64_t out[6]) {
         const uint64_t rounds = (slots + cons - 1) / cons;
         out[0] += same + cross; out[1] += rounds * cons; out[2] += 1; out[3] += rounds; out[4] += cols * rounds;
         if (2 * (same + cross) < rounds * cons) out[5] += rounds;
+        if (std::getenv("FEM2D_DEBUG_FILL")) {   // tiles / slots by kind of pack: 0 one item, several rounds; 1 one item, one round, local; 2 the same, non-local; 3 several items
+            static uint64_t cat[4][3];
+            const bool nonlocal = !H.classes[H.items[pk.first].cls].local;
+            const int k = pk.n > 1 ? 3 : rounds > 1 ? 0 : nonlocal ? 2 : 1;
+            cat[k][0] += same + cross; cat[k][1] += rounds * cons; cat[k][2] += cols;
+            if (&pk == &H.packs.back())
+                for (int q = 0; q < 4; q++) { std::fprintf(stderr, "[fill] kind %d: tiles %llu slots %llu cols %llu\n", q, (unsigned long long)cat[q][0], (unsigned long long)cat[q][1], (unsigned long long)cat[q][2]); cat[q][0] = cat[q][1] = cat[q][2] = 0; }
+        }
     }
     return FEM2D_OK;
 }

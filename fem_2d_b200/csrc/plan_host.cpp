@@ -6,6 +6,8 @@
 #include <functional>
 #include <cstring>
 #include <numeric>
+#include <chrono>
+#include <cstdio>
 #include <thread>
 #include <unordered_map>
 
@@ -209,6 +211,15 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
     const uint32_t nbs = v->bs_off[ne];
     if (nbs && (!v->bs_i || !v->bs_j || !v->bs_dir || !v->bs_dof)) { err = "null basis-spec array in view"; return FEM2D_ERR_BAD_ARGUMENT; }
     if (v->i_max > 20 || v->j_max > 20) { err = "expansion order exceeds MAX_POLYNOMIAL_ORDER (20)"; return FEM2D_ERR_UNSUPPORTED; }
+    // FEM2D_PLAN_TIMING=1 (tuning): wall time of the planner's phases on stderr
+    static const bool timing = [] { const char* ev = std::getenv("FEM2D_PLAN_TIMING"); return ev && std::atoi(ev) != 0; }();
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[fem2d planner] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     P = HostPlan();
     P.n_elems = ne; P.n_dofs = v->n_dofs; P.i_max = v->i_max; P.j_max = v->j_max;
     P.bs_off.assign(v->bs_off, v->bs_off + ne + 1);
@@ -334,6 +345,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
         P.max_list_n = std::max(P.max_list_n, n);
     }
 
+    lap("lists");
     // ---- tables: ids 0 / 1 are the unscaled u / v tables
     std::unordered_map<TabKey, uint32_t, TabKeyHash> tab_pool;
     auto table_id = [&](double s, double o, uint32_t axis, uint32_t identity) {
@@ -360,6 +372,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
         return id;
     };
 
+    lap("tables");
     // ---- blocks and classes.  Block order: for every Elem d (ascending) its local block, then its blocks with each
     // ancestor that carries functions (nearest ancestor first).
     std::unordered_map<ClassKey, uint32_t, ClassKeyHash> class_pool;
@@ -442,6 +455,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
     if (P.blocks.empty()) { err = "the view carries DoFs but no basis specs: nothing to integrate"; return FEM2D_ERR_BAD_ARGUMENT; }
     if (P.n_values >= (1ull << 31) || P.n_pairs >= (1ull << 32)) { err = "domain too large for 32-bit source indices"; return FEM2D_ERR_UNSUPPORTED; }
 
+    lap("blocks + classes");
     // ---- work items: <= K2_ROUNDS * K2_THREADS micro-tiles each (balanced split); largest classes first (longest-processing-time order)
     std::vector<uint32_t> cls_order(P.classes.size());
     std::iota(cls_order.begin(), cls_order.end(), 0u);
@@ -487,6 +501,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
             const double detP = c.dxP * c.dyP - 0.0 * 0.0, detQ = c.dxQ * c.dyQ - 0.0 * 0.0;
             const bool ge = detP >= detQ;
             const double ratio_uv = ge ? c.dxP / c.dyP : c.dxQ / c.dyQ, ratio_vu = ge ? c.dyP / c.dxP : c.dyQ / c.dxQ, maxdet = detP > detQ ? detP : detQ;
+            if ((!is_pow2_scale(ratio_uv) || !is_pow2_scale(ratio_vu)) && (P.ws_fold & 1u) && std::getenv("FEM2D_DEBUG_FILL")) std::fprintf(stderr, "[fold] class dxP %.17g dyP %.17g dxQ %.17g dyQ %.17g uv %.17g vu %.17g\n", c.dxP, c.dyP, c.dxQ, c.dyQ, ratio_uv, ratio_vu);
             if (!is_pow2_scale(ratio_uv) || !is_pow2_scale(ratio_vu)) P.ws_fold &= ~1u;
             if (!is_pow2_scale(maxdet)) P.ws_fold &= ~2u;
         }
@@ -535,7 +550,9 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
         for (auto& t : th) t.join();
         for (auto& part : parts) P.items.insert(P.items.end(), part.begin(), part.end());
     }
+    lap("work items");
     pack_items(P, P.items, P.packs);
+    lap("packs");
     return FEM2D_OK;
 }
 

@@ -84,3 +84,39 @@ def test_throughput_shape_extreme_glq_shapes(nu, nv):
     _, _, a2, b2 = plan.assemble(glq2)
     assert np.array_equal(np.ascontiguousarray(a2).view(np.uint64), np.ascontiguousarray(ref2.a).view(np.uint64))
     assert np.array_equal(np.ascontiguousarray(b2).view(np.uint64), np.ascontiguousarray(ref2.b).view(np.uint64))
+
+
+@pytest.mark.parametrize("want_fold", [3, 1, 0])
+def test_throughput_shape_folded_scales_bit_identical(want_fold, tmp_path):
+    """The persistent integrator multiplies the quadrature weight instead of every product when a pass's scale is a power of two in every
+    class of the plan (k2_ws_kernel FOLD): 3 = ratios and max(det) (dyadic Element sides: mesh a), 1 = ratios only (one 3 x 3 Element at two
+    T-levels: square 1.5 / 2^k Elems, max(det) = 0.5625 / 4^k), 0 = neither (mesh c, 4.2 x 4.2: its refined sides carry rounding errors, the ratios of
+    some classes are an ulp off 1).  High orders, no dedupe (the
+    throughput tile shape needs 148 x 256 micro-tiles), 6 x 7 points, whole matrices against the oracle, bit for bit."""
+    import json
+    mesh3 = str(tmp_path / "mesh_3x3.json")
+    with open(mesh3, "w") as f:
+        json.dump({"Elements": [{"materials": [1.0, 0.0, 2.0, 0.0], "node_ids": [0, 1, 2, 3]}], "Nodes": [[0.0, 0.0], [3.0, 0.0], [0.0, 3.0], [3.0, 3.0]]}, f)
+
+    def build(api):
+        if want_fold == 3:
+            m = api.Mesh.from_file(recipes.MESH_A)
+            api.set_orders(m, 9, 9)
+            m.global_h_refinement(api.href(recipes.T))
+            m.h_refine_with_filter(lambda e: api.href(recipes.U) if e.id % 3 == 0 else api.href(recipes.V) if e.id % 3 == 1 else None)
+            return m
+        if want_fold == 1:
+            m = api.Mesh.from_file(mesh3)
+            api.set_orders(m, 12, 12)
+            m.global_h_refinement(api.href(recipes.T)); m.global_h_refinement(api.href(recipes.T))
+            return m
+        return recipes.mesh_cfg4(api, t_levels=3, rounds=3, pmin=2, pmax=10)
+    do, df = O.Domain.from_mesh(build(recipes.api("oracle"))), F.Domain.from_mesh(build(recipes.api("product")))
+    glq = (F.gauss_quadrature_points(6), F.gauss_quadrature_points(7))
+    ref = O.galerkin_sample_gep_hcurl(do, glq=glq, n_threads=16)
+    plan = F.Plan(df.view(), device=0, dedupe=False)
+    assert plan.info["tile_p"] == 4 and plan.round_fill()["fold"] == want_fold
+    rows, cols, a, b = plan.assemble(glq)
+    assert np.array_equal(rows, ref.rows) and np.array_equal(cols, ref.cols)
+    assert np.array_equal(np.ascontiguousarray(a).view(np.uint64), np.ascontiguousarray(ref.a).view(np.uint64)), "A differs"
+    assert np.array_equal(np.ascontiguousarray(b).view(np.uint64), np.ascontiguousarray(ref.b).view(np.uint64)), "B differs"
