@@ -49,7 +49,14 @@ struct ClassKey {
     uint32_t listP, listQ, local, pad;
     bool operator==(const ClassKey& o) const { return std::memcmp(this, &o, sizeof(ClassKey)) == 0; }
 };
-struct ClassKeyHash { size_t operator()(const ClassKey& k) const { return (size_t)fnv1a(&k, sizeof(ClassKey)); } };
+static_assert(sizeof(ClassKey) % 8 == 0, "ClassKey is hashed as 64-bit words");
+inline uint64_t class_key_hash(const ClassKey& k) {   // the key is built over a zeroed struct: no padding garbage
+    uint64_t w[sizeof(ClassKey) / 8];
+    std::memcpy(w, &k, sizeof(ClassKey));
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (uint64_t x : w) { h = (h ^ x) * 0xff51afd7ed558ccdull; h ^= h >> 32; }
+    return h;
+}
 struct TabKey {
     double s, o; uint32_t axis, identity;
     bool operator==(const TabKey& t) const { return std::memcmp(this, &t, sizeof(TabKey)) == 0; }
@@ -151,53 +158,84 @@ void pack_items(const HostPlan& H, std::vector<WorkItem>& items, std::vector<Pac
     packs.clear();
     if (!(H.use_ws && H.tile_p == (uint32_t)K2_TILE_P)) { order_items(H, items); return; }
     const uint32_t round_slots = H.ws_round_slots();
-    struct Bin { std::vector<uint32_t> seg; uint32_t same = 0, cross = 0, stride = 0; uint64_t key = ~0ull; };
+    struct Bin { uint32_t seg[K2_PACK_MAX]; uint32_t n = 0, same = 0, cross = 0, stride = 0; uint64_t key = ~0ull; };
     auto slots_of = [](uint32_t same, uint32_t cross) { return item_slots(same, same + cross); };
-    auto key_of = [&](const WorkItem& it) {   // scaled tables of a non-local item's P side; ~0 for local items (they only use the unscaled tables)
-        const ClassDesc& c = H.classes[it.cls];
-        return c.local ? ~0ull : ((uint64_t)c.tabPu << 32 | c.tabPv);
+    static const bool timing = [] { const char* ev = std::getenv("FEM2D_PLAN_TIMING"); return ev && std::atoi(ev) != 0; }();
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[fem2d planner]   %-26s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
     };
     std::vector<uint32_t> order(items.size());
     for (uint32_t k = 0; k < items.size(); k++) order[k] = k;
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return items[a].mt_count > items[b].mt_count; });
+    // slab row and scaled-table key per class, gathered once in class order (the per-item look-ups below then stay in a small array)
+    std::vector<uint32_t> cls_stride(H.classes.size());
+    std::vector<uint64_t> cls_key(H.classes.size());
+    for (size_t c = 0; c < H.classes.size(); c++) {
+        const ClassDesc& cd = H.classes[c];
+        const ListDesc& LP = H.lists[cd.listP]; const ListDesc& LQ = H.lists[cd.listQ];
+        cls_stride[c] = slab_pad4(LP.nU) + slab_pad4(LP.n - LP.nU) + (cd.local ? 0u : slab_pad4(LQ.nU) + slab_pad4(LQ.n - LQ.nU));
+        cls_key[c] = cd.local ? ~0ull : ((uint64_t)cd.tabPu << 32 | cd.tabPv);
+    }
+    uint32_t min_stride = UINT32_MAX;
+    for (const WorkItem& it : items) min_stride = std::min(min_stride, cls_stride[it.cls]);
+    lap("packs: order");
+    // bins hold up to K2_PACK_MAX segments inline; the window of bins that may still take a segment keeps copies of their running sums,
+    // so a probe touches 32 contiguous bytes (the first-fit search is most of this function's time on hp-meshes)
+    struct Open { uint32_t bin, same, cross, stride, nseg; uint64_t key; };
     std::vector<Bin> bins;
-    std::vector<uint32_t> open;   // bins that may still take a segment (a bounded window keeps the first-fit search linear)
+    bins.reserve(items.size());
+    std::vector<Open> open;
     for (uint32_t k : order) {
         const WorkItem& it = items[k];
-        const uint32_t same = it.n_same, cross = it.mt_count - it.n_same, stride = item_slab_stride(H, it);
-        const uint64_t key = key_of(it);
-        int target = -1;
+        const uint32_t same = it.n_same, cross = it.mt_count - it.n_same, stride = cls_stride[it.cls];
+        const uint64_t key = cls_key[it.cls];
+        int slot = -1;
         if (slots_of(same, cross) < round_slots && stride <= (uint32_t)K2_PACK_STRIDE) {
-            for (uint32_t b : open) {
-                const Bin& B = bins[b];
-                if (B.seg.size() >= (size_t)K2_PACK_MAX || B.stride + stride > (uint32_t)K2_PACK_STRIDE) continue;
+            for (size_t q = 0; q < open.size(); q++) {
+                const Open& B = open[q];
+                if (B.stride + stride > (uint32_t)K2_PACK_STRIDE) continue;
                 if (slots_of(B.same + same, B.cross + cross) > round_slots) continue;
                 if (key != ~0ull && B.key != ~0ull && B.key != key) continue;
-                target = (int)b; break;
+                slot = (int)q; break;
             }
         }
-        if (target < 0) {
+        uint32_t target;
+        if (slot < 0) {
             bins.push_back(Bin());
-            target = (int)bins.size() - 1;
+            target = (uint32_t)bins.size() - 1;
             if (slots_of(same, cross) + 16 < round_slots && stride < (uint32_t)K2_PACK_STRIDE) {
-                open.push_back((uint32_t)target);
+                open.push_back(Open{target, 0, 0, 0, 0, ~0ull});
                 if (open.size() > 64) open.erase(open.begin());
+                slot = (int)open.size() - 1;
             }
-        }
+        } else target = open[slot].bin;
         Bin& B = bins[target];
-        B.seg.push_back(k); B.same += same; B.cross += cross; B.stride += stride;
+        B.seg[B.n++] = k; B.same += same; B.cross += cross; B.stride += stride;
         if (key != ~0ull) B.key = key;
+        if (slot >= 0) {
+            Open& o = open[slot];
+            o.same = B.same; o.cross = B.cross; o.stride = B.stride; o.nseg = B.n; o.key = B.key;
+            // a bin that no later item can join (segment count, slab row, thread slots) leaves the window
+            if (o.nseg >= (uint32_t)K2_PACK_MAX || o.stride + min_stride > (uint32_t)K2_PACK_STRIDE || slots_of(o.same, o.cross) + 1 > round_slots)
+                open.erase(open.begin() + slot);
+        }
     }
+    lap("packs: first fit");
     std::vector<uint32_t> bo(bins.size());
     for (uint32_t k = 0; k < bins.size(); k++) bo[k] = k;
     std::stable_sort(bo.begin(), bo.end(), [&](uint32_t a, uint32_t b) { return bins[a].same + bins[a].cross > bins[b].same + bins[b].cross; });
     std::vector<WorkItem> out;
     out.reserve(items.size());
     for (uint32_t b : bo) {
-        packs.push_back(PackDesc{(uint32_t)out.size(), (uint32_t)bins[b].seg.size()});
-        for (uint32_t k : bins[b].seg) out.push_back(items[k]);
+        packs.push_back(PackDesc{(uint32_t)out.size(), bins[b].n});
+        for (uint32_t q = 0; q < bins[b].n; q++) out.push_back(items[bins[b].seg[q]]);
     }
     items.swap(out);
+    lap("packs: emit");
 }
 
 int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::string& err) {
@@ -227,6 +265,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
     // ---- per-Elem geometry
     if (int st = elem_geometry(v, P.elem_dx, P.elem_dy, err)) return st;
 
+    lap("geometry");
     // ---- canonical BasisSpec lists, pooled by content.
     // Phase A (parallel over Elems): validate, sort each Elem's specs by (dir, i, j), emit canon_dof and a content hash.
     // Phase B (serial): pool identical lists.
@@ -258,6 +297,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
         std::sort(keyed.begin(), keyed.end());
         for (uint32_t r = 0; r < KSg; r++) { rank_cell[r] = keyed[r].second; cell_rank[keyed[r].second] = r; }
     }
+    lap("lists: set-up");
     const unsigned n_threads = ne < 4096 ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     std::vector<int> bad(n_threads, 0);
     auto phase_a = [&](unsigned tid) {
@@ -321,6 +361,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
         if (bcode == 2) { err = "bs_dof out of range"; return FEM2D_ERR_BAD_ARGUMENT; }
         if (bcode == 3) { err = "basis-spec order exceeds i_max/j_max"; return FEM2D_ERR_BAD_ARGUMENT; }
     }
+    lap("lists: canonical order");
     std::unordered_map<uint64_t, std::vector<uint32_t>> list_pool;   // hash -> candidate list ids
     std::vector<uint32_t> list_first_elem;                          // an Elem that carries the list (for content comparison)
     for (uint32_t e = 0; e < ne; e++) {
@@ -345,7 +386,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
         P.max_list_n = std::max(P.max_list_n, n);
     }
 
-    lap("lists");
+    lap("lists: pooling");
     // ---- tables: ids 0 / 1 are the unscaled u / v tables
     std::unordered_map<TabKey, uint32_t, TabKeyHash> tab_pool;
     auto table_id = [&](double s, double o, uint32_t axis, uint32_t identity) {
@@ -375,10 +416,9 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
     lap("tables");
     // ---- blocks and classes.  Block order: for every Elem d (ascending) its local block, then its blocks with each
     // ancestor that carries functions (nearest ancestor first).
-    std::unordered_map<ClassKey, uint32_t, ClassKeyHash> class_pool;
     // Pass 1 (host threads over contiguous Elem ranges): the (ancestor, descendant) pairs that carry functions on both sides and the
     // descendant's sub-range inside the ancestor; pass 2 (serial, in Elem order): class pooling, tables, block numbering.
-    struct BlockRec { uint32_t e, d; double su, ou, sv, ov; };
+    struct BlockRec { uint32_t e, d; double su, ou, sv, ov; ClassKey key; uint64_t hash; };   // key without the dedupe-off block number
     auto records_of = [&](uint32_t d0, uint32_t d1, std::vector<BlockRec>& out) {
         std::vector<uint8_t> locs;
         for (uint32_t d = d0; d < d1; d++) {
@@ -390,7 +430,8 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
                 if (!local) locs.push_back(v->elem_loc[child_on_path]);   // locs: from d upwards to the child of e
                 child_on_path = (uint32_t)e;
                 if (v->bs_off[e + 1] == v->bs_off[e]) continue;
-                BlockRec r{(uint32_t)e, d, 1.0, 0.0, 1.0, 0.0};
+                BlockRec r; std::memset(&r, 0, sizeof(r));
+                r.e = (uint32_t)e; r.d = d; r.su = 1.0; r.ou = 0.0; r.sv = 1.0; r.ov = 0.0;
                 if (!local) {
                     // relative_parametric_range(e) of d: fold from the child of e down to d (elem.rs:170-188)
                     double rg[4] = {-1.0, 1.0, -1.0, 1.0}, t[4];
@@ -398,6 +439,14 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
                     r.su = (rg[1] - rg[0]) / 2.0; r.ou = (rg[1] + rg[0]) / 2.0;   // scale_gauss_quad_points glq.rs:238-249
                     r.sv = (rg[3] - rg[2]) / 2.0; r.ov = (rg[3] + rg[2]) / 2.0;
                 }
+                // class key (the inputs that make two blocks bit-identical) and its hash, computed here in parallel
+                const uint32_t elP = v->elem_element[e];
+                ClassKey& key = r.key;
+                key.g[0] = P.elem_dx[e]; key.g[1] = P.elem_dy[e]; key.g[2] = P.elem_dx[d]; key.g[3] = P.elem_dy[d];
+                key.g[4] = r.su; key.g[5] = r.ou; key.g[6] = r.sv; key.g[7] = r.ov;
+                key.g[8] = v->element_eps_re[elP]; key.g[9] = v->element_mu_re[elP];
+                key.listP = P.elem_list[e]; key.listQ = P.elem_list[d]; key.local = local ? 1u : 0u;
+                r.hash = class_key_hash(key);
                 out.push_back(r);
             }
         }
@@ -409,28 +458,33 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
         for (unsigned t = 0; t < n_threads; t++) th.emplace_back(records_of, (uint32_t)((uint64_t)ne * t / n_threads), (uint32_t)((uint64_t)ne * (t + 1) / n_threads), std::ref(rec_parts[t]));
         for (auto& t : th) t.join();
     }
-    {
-        size_t n_rec = 0;
-        for (auto& part : rec_parts) n_rec += part.size();
-        P.blocks.reserve(n_rec); class_pool.reserve(n_rec);
-    }
+    lap("blocks: records");
+    size_t n_rec = 0;
+    for (auto& part : rec_parts) n_rec += part.size();
+    P.blocks.reserve(n_rec);
+    // class pool: open addressing over the records' precomputed hashes (slot -> class id, keys kept next to the classes); without dedupe
+    // every block is its own class and the table is not used
+    size_t pool_size = 64;
+    while (pool_size < 2 * n_rec) pool_size *= 2;
+    std::vector<uint32_t> pool_slot(dedupe ? pool_size : 0, UINT32_MAX);
+    std::vector<ClassKey> pool_key;
+    if (dedupe) pool_key.reserve(n_rec);
+    P.classes.reserve(n_rec);
     for (auto& part : rec_parts)
         for (const BlockRec& r : part) {
             const uint32_t e = r.e, d = r.d;
             const bool local = e == d;
             const uint32_t nd = v->bs_off[d + 1] - v->bs_off[d], nE = v->bs_off[e + 1] - v->bs_off[e];
             const double su = r.su, ou = r.ou, sv = r.sv, ov = r.ov;
-            ClassKey key; std::memset(&key, 0, sizeof(key));
-            const uint32_t elP = v->elem_element[e];
-            key.g[0] = P.elem_dx[e]; key.g[1] = P.elem_dy[e]; key.g[2] = P.elem_dx[d]; key.g[3] = P.elem_dy[d];
-            key.g[4] = su; key.g[5] = ou; key.g[6] = sv; key.g[7] = ov;
-            key.g[8] = v->element_eps_re[elP]; key.g[9] = v->element_mu_re[elP];
-            key.listP = P.elem_list[e]; key.listQ = P.elem_list[d]; key.local = local ? 1u : 0u;
-            if (!dedupe) key.pad = (uint32_t)P.blocks.size() + 1;   // unique per block
-            uint32_t cls;
-            auto it = class_pool.find(key);
-            if (it != class_pool.end()) cls = it->second;
-            else {
+            const ClassKey& key = r.key;
+            uint32_t cls = UINT32_MAX;
+            size_t slot = 0;
+            if (dedupe) {
+                for (slot = (size_t)r.hash & (pool_size - 1); pool_slot[slot] != UINT32_MAX; slot = (slot + 1) & (pool_size - 1))
+                    if (pool_key[pool_slot[slot]] == key) { cls = pool_slot[slot]; break; }
+            }
+            if (cls == UINT32_MAX) {
+
                 cls = (uint32_t)P.classes.size();
                 ClassDesc c; std::memset(&c, 0, sizeof(c));
                 c.dxP = key.g[0]; c.dyP = key.g[1]; c.dxQ = key.g[2]; c.dyQ = key.g[3];
@@ -446,7 +500,7 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
                 P.n_values += (uint64_t)LP.n * LQ.n;
                 c.n_mt = 0;   // filled once the tile shape is chosen
                 P.classes.push_back(c);
-                class_pool.emplace(key, cls);
+                if (dedupe) { pool_slot[slot] = cls; pool_key.push_back(key); }
             }
             BlockDesc b; b.pair_off = P.n_pairs; b.cls = cls; b.elemP = e; b.elemQ = d; b.pad = 0;
             P.blocks.push_back(b);
@@ -479,7 +533,13 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
     };
     P.tile_p = K2_TILE_P;
     if (count_mt(K2_TILE_P) < (uint64_t)148 * K2_THREADS) { P.tile_p = 1; count_mt(1); }
-    std::stable_sort(cls_order.begin(), cls_order.end(), [&](uint32_t a, uint32_t b) { return P.classes[a].n_mt > P.classes[b].n_mt; });
+    lap("items: tile counts");
+    {   // largest classes first, ties in class order (a packed key sorts faster than a comparator that chases the 144-byte descriptors)
+        std::vector<uint64_t> keyed(P.classes.size());
+        for (size_t c = 0; c < P.classes.size(); c++) keyed[c] = (uint64_t)(UINT32_MAX - P.classes[c].n_mt) << 32 | (uint32_t)c;
+        std::sort(keyed.begin(), keyed.end());
+        for (size_t k = 0; k < keyed.size(); k++) cls_order[k] = (uint32_t)keyed[k];
+    }
     // Few, heavily deduplicated classes would leave most of the 148 SMs idle: shrink the item size until there are about two
     // CTAs per SM (each item re-stages its class's slabs, which is cheap next to an idle machine).
     if (const char* ev = std::getenv("FEM2D_K2_WS")) P.use_ws = std::atoi(ev) != 0;   // tuning: 0 = every item in k2_exact_kernel
@@ -501,12 +561,12 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
             const double detP = c.dxP * c.dyP - 0.0 * 0.0, detQ = c.dxQ * c.dyQ - 0.0 * 0.0;
             const bool ge = detP >= detQ;
             const double ratio_uv = ge ? c.dxP / c.dyP : c.dxQ / c.dyQ, ratio_vu = ge ? c.dyP / c.dxP : c.dyQ / c.dxQ, maxdet = detP > detQ ? detP : detQ;
-            if ((!is_pow2_scale(ratio_uv) || !is_pow2_scale(ratio_vu)) && (P.ws_fold & 1u) && std::getenv("FEM2D_DEBUG_FILL")) std::fprintf(stderr, "[fold] class dxP %.17g dyP %.17g dxQ %.17g dyQ %.17g uv %.17g vu %.17g\n", c.dxP, c.dyP, c.dxQ, c.dyQ, ratio_uv, ratio_vu);
             if (!is_pow2_scale(ratio_uv) || !is_pow2_scale(ratio_vu)) P.ws_fold &= ~1u;
             if (!is_pow2_scale(maxdet)) P.ws_fold &= ~2u;
         }
         if (const char* ev = std::getenv("FEM2D_K2_WS_FOLD")) P.ws_fold &= (uint32_t)std::atoi(ev);   // tuning: 0 = never fold
     }
+    lap("items: class order, fold");
     uint32_t cap = K2_ROUNDS * (P.use_ws && P.tile_p == (uint32_t)K2_TILE_P ? P.ws_round_slots() / K2_WS_TPT : (uint32_t)K2_THREADS);
     const uint32_t min_cap = P.tile_p == 1 ? 256u : 64u;   // latency shape: one full round per CTA measured best (128: +10 %, 512: +30 %)
     for (; cap > min_cap; cap /= 2) {
@@ -540,14 +600,27 @@ int build_host_plan(const fem2d_domain_view* v, bool dedupe, HostPlan& P, std::s
             }
         }
     };
+    lap("items: cap");
     const unsigned item_threads = cls_order.size() < 8192 ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     if (item_threads == 1) items_of(0, cls_order.size(), P.items);
     else {
+        // pieces of about equal item counts (cls_order has the largest classes first: equal class counts would give the first thread most of the items)
+        lap("items: pre");
+        std::vector<uint64_t> before(cls_order.size() + 1, 0);
+        for (size_t k = 0; k < cls_order.size(); k++) before[k + 1] = before[k] + (P.classes[cls_order[k]].n_mt + cap - 1) / cap;
+        std::vector<size_t> cut(item_threads + 1, cls_order.size());
+        cut[0] = 0;
+        for (unsigned t = 1; t < item_threads; t++)
+            cut[t] = (size_t)(std::lower_bound(before.begin(), before.end(), before.back() * t / item_threads) - before.begin());
         std::vector<std::vector<WorkItem>> parts(item_threads);
         std::vector<std::thread> th;
-        for (unsigned t = 0; t < item_threads; t++)
-            th.emplace_back(items_of, cls_order.size() * t / item_threads, cls_order.size() * (t + 1) / item_threads, std::ref(parts[t]));
+        for (unsigned t = 0; t < item_threads; t++) {
+            parts[t].reserve((size_t)(before[cut[t + 1]] - before[cut[t]]) + 16);
+            th.emplace_back(items_of, cut[t], cut[t + 1], std::ref(parts[t]));
+        }
         for (auto& t : th) t.join();
+        lap("items: threads");
+        P.items.reserve((size_t)before.back() + 16 * item_threads);
         for (auto& part : parts) P.items.insert(P.items.end(), part.begin(), part.end());
     }
     lap("work items");
