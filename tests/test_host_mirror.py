@@ -249,3 +249,33 @@ def test_petsc_aij_writer_matches_oracle_restatement(tmp_path):
     path = str(tmp_path / "m.dat")
     F.SparseMatrix(do.num_dofs, gep.rows, gep.cols, gep.a).print_to_petsc_binary_file(path)
     assert open(path, "rb").read() == O.petsc_aij_bytes(do.num_dofs, gep.rows, gep.cols, gep.a)
+
+
+def test_planner_folds_only_exact_power_of_two_scales(tmp_path):
+    """HostPlan::ws_fold (the scales the persistent integrator may multiply into the quadrature weights, bit for bit): both the uv / vu
+    ratios and max(det) on dyadic Element sides (mesh a, 1.0 x 0.5), the ratios only on a 3 x 3 Element (max(det) = 2.25 / 4^k), nothing on
+    mesh c (4.2 x 4.2: the refined sides are rounded, some ratios are an ulp off 1), and nothing when the tuning switch says so.  Host-only plans."""
+    import json
+    mesh3 = str(tmp_path / "mesh_3x3.json")
+    with open(mesh3, "w") as f:
+        json.dump({"Elements": [{"materials": [1.0, 0.0, 2.0, 0.0], "node_ids": [0, 1, 2, 3]}], "Nodes": [[0.0, 0.0], [3.0, 0.0], [0.0, 3.0], [3.0, 3.0]]}, f)
+    api = recipes.api("product")
+
+    def refined(path, order, levels):
+        m = api.Mesh.from_file(path)
+        api.set_orders(m, order, order)
+        for _ in range(levels):
+            m.global_h_refinement(api.href(recipes.T))
+        return F.Domain.from_mesh(m)
+
+    cases = [(refined(recipes.MESH_A, 9, 2), 3), (refined(mesh3, 12, 2), 1), (refined(recipes.MESH_C, 12, 2), 0)]
+    for dom, want in cases:
+        plan = F.Plan(dom.view(), device=-1, dedupe=False)
+        assert plan.info["tile_p"] == 4, "the throughput tile shape is what folds"
+        assert plan.round_fill()["fold"] == want
+        assert plan.check_work_items()["violations"] == 0
+    os.environ["FEM2D_K2_WS_FOLD"] = "0"
+    try:
+        assert F.Plan(cases[0][0].view(), device=-1, dedupe=False).round_fill()["fold"] == 0
+    finally:
+        os.environ.pop("FEM2D_K2_WS_FOLD", None)
